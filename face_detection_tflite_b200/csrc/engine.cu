@@ -1,0 +1,162 @@
+#include "engine.h"
+
+#include <algorithm>
+#include <cstdio>
+
+namespace fdt {
+
+Engine::~Engine() {
+  if (d_blob_) cudaFree(d_blob_);
+}
+
+bool Engine::init(const uint8_t* tflite, size_t len, int fuse_level, std::string* err) {
+  if (!model_.parse(tflite, len, err)) return false;
+  if (!plan_.build(model_, fuse_level, err)) return false;
+  size_t bytes = plan_.blob.size() * sizeof(float) + 64;
+  if (cudaMalloc(&d_blob_, bytes) != cudaSuccess) { *err = "cudaMalloc(weights) failed"; return false; }
+  cudaMemset(d_blob_, 0, bytes);
+  if (cudaMemcpy(d_blob_, plan_.blob.data(), plan_.blob.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+    *err = "weight upload failed";
+    return false;
+  }
+  return true;
+}
+
+bool Engine::make_ctx(int cap, EngineCtx* ctx, std::string* err) const {
+  ctx->cap = cap;
+  size_t bytes = (size_t)cap * plan_.arena_per_image * sizeof(float) + 256;
+  if (cudaMalloc(&ctx->arena, bytes) != cudaSuccess) { *err = "cudaMalloc(arena) failed"; return false; }
+  cudaMemset(ctx->arena, 0, bytes);
+  ctx->outputs.clear();
+  for (long long e : plan_.out_elems) {
+    float* p = nullptr;
+    size_t ob = (size_t)cap * e * sizeof(float) + 256;
+    if (cudaMalloc(&p, ob) != cudaSuccess) { *err = "cudaMalloc(outputs) failed"; return false; }
+    cudaMemset(p, 0, ob);
+    ctx->outputs.push_back(p);
+  }
+  return true;
+}
+
+void Engine::free_ctx(EngineCtx* ctx) const {
+  if (ctx->arena) cudaFree(ctx->arena);
+  for (float* p : ctx->outputs) cudaFree(p);
+  ctx->arena = nullptr;
+  ctx->outputs.clear();
+}
+
+TV Engine::view(const EngineCtx& ctx, int t) const {
+  const PTensor& x = plan_.tensors[t];
+  TV v;
+  v.H = x.H; v.W = x.W; v.C = x.C; v.Cs = x.Cs;
+  v.istride = x.istride;
+  if (x.root >= 0) v.p = ctx.outputs[x.root] + x.view_off;
+  else v.p = ctx.arena + (size_t)x.arena_off * ctx.cap;
+  return v;
+}
+
+static int cta_cap(size_t smem, int threads) {
+  int by_smem = (int)((227u * 1024u) / (smem + 1024u));
+  int by_thr = 2048 / std::max(threads, 32);
+  int per_sm = std::max(1, std::min(std::min(by_smem, by_thr), 16));
+  return 148 * per_sm;
+}
+
+int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t s) const {
+  int launches = 0;
+  const float* blob = d_blob_;
+  for (const PStep& st : plan_.steps) {
+    TV out = view(ctx, st.out);
+    switch (st.kind) {
+      case kStepNormalize:
+        launch_normalize(in_u8, out, B, s);
+        break;
+      case kStepNaiveConv: {
+        NaiveConvP p;
+        p.in = view(ctx, st.in); p.out = out;
+        p.w = blob + st.w; p.bias = blob + st.bias;
+        p.alpha = st.alpha >= 0 ? blob + st.alpha : nullptr;
+        p.kh = st.kh; p.kw = st.kw; p.sh = st.sh; p.sw = st.sw; p.pt = st.pt; p.pl = st.pl;
+        p.act = st.act; p.depthwise = st.depthwise;
+        launch_naive_conv(p, B, s);
+        break;
+      }
+      case kStepGemmConv: {
+        GemmConvP p;
+        const PTensor& it = plan_.tensors[st.in];
+        if (st.in_u8) {
+          p.in = nullptr; p.in8 = in_u8; p.in_istride = (long long)it.H * it.W * 3;
+          p.Cin = 3; p.CinS = 3;
+        } else {
+          TV iv = view(ctx, st.in);
+          p.in = iv.p; p.in8 = nullptr; p.in_istride = iv.istride; p.Cin = it.C; p.CinS = it.Cs;
+        }
+        p.H = it.H; p.W = it.W;
+        p.kh = st.kh; p.kw = st.kw; p.sh = st.sh; p.sw = st.sw; p.pt = st.pt; p.pl = st.pl;
+        p.OH = out.H; p.OW = out.W;
+        p.K = st.K; p.KP = st.KP; p.KS = st.KS;
+        p.out = out.p; p.out_istride = out.istride; p.Cout = st.Cout; p.CoutS = out.Cs;
+        p.vec_store = (out.Cs % 4 == 0 && out.istride % 4 == 0 && ((size_t)out.p % 16 == 0)) ? 1 : 0;
+        p.w = blob + st.w; p.bias = blob + st.bias; p.alpha = st.alpha >= 0 ? blob + st.alpha : nullptr;
+        p.act = st.act; p.CoutP = st.CoutP; p.NNG = st.NNG; p.NC = st.NC; p.nchunks = st.nchunks;
+        p.NPG = st.NPG; p.TM = st.TM; p.smem_bytes = st.smem;
+        launch_gemm_conv(p, B, s, cta_cap(st.smem, st.NPG * st.NNG));
+        break;
+      }
+      case kStepDwPw: {
+        DwPwP p;
+        TV iv = view(ctx, st.in);
+        p.in = iv.p; p.in_istride = iv.istride; p.H = iv.H; p.W = iv.W; p.Cin = iv.C; p.CinS = iv.Cs;
+        p.has_dw = st.has_dw ? 1 : 0; p.s = st.dws; p.dpt = st.dpt; p.dpl = st.dpl;
+        p.OH = out.H; p.OW = out.W;
+        p.dww = st.dww >= 0 ? blob + st.dww : nullptr; p.dwb = st.dwb >= 0 ? blob + st.dwb : nullptr;
+        p.KP = st.KP; p.KS = st.KS;
+        p.out = out.p; p.out_istride = out.istride; p.Cout = st.Cout; p.CoutS = out.Cs;
+        p.vec_store = (out.Cs % 4 == 0 && out.istride % 4 == 0 && ((size_t)out.p % 16 == 0)) ? 1 : 0;
+        p.w = blob + st.w; p.bias = blob + st.bias; p.alpha = st.alpha >= 0 ? blob + st.alpha : nullptr;
+        p.act = st.act; p.CoutP = st.CoutP; p.NNG = st.NNG; p.NC = st.NC; p.nchunks = st.nchunks;
+        p.NPG = st.NPG; p.TM = st.TM;
+        if (st.in2 >= 0) {
+          TV rv = view(ctx, st.in2);
+          p.res = rv.p; p.res_istride = rv.istride; p.res_H = rv.H; p.res_W = rv.W; p.res_C = rv.C; p.res_Cs = rv.Cs;
+        } else {
+          p.res = nullptr; p.res_istride = 0; p.res_H = p.res_W = p.res_C = p.res_Cs = 0;
+        }
+        p.res_pool = st.res_pool;
+        p.TH = st.TH; p.TW = st.TW; p.G = st.G; p.IH = st.IH; p.IW = st.IW; p.tilesX = st.tilesX; p.tilesY = st.tilesY;
+        p.smem_bytes = st.smem;
+        launch_dwpw(p, B, s, cta_cap(st.smem, st.NPG * st.NNG));
+        break;
+      }
+      case kStepAdd: case kStepAct: case kStepPadC: {
+        EltP p;
+        p.a = view(ctx, st.in);
+        p.b = st.in2 >= 0 ? view(ctx, st.in2) : p.a;
+        p.out = out;
+        p.alpha = st.alpha >= 0 ? blob + st.alpha : nullptr;
+        p.act = st.act;
+        if (st.kind == kStepAdd) launch_add(p, B, s);
+        else if (st.kind == kStepAct) launch_act(p, B, s);
+        else launch_padc(p, B, s);
+        break;
+      }
+      case kStepMaxPool: {
+        PoolP p;
+        p.in = view(ctx, st.in); p.out = out;
+        p.fh = st.fh; p.fw = st.fw; p.sh = st.sh; p.sw = st.sw; p.pt = st.pt; p.pl = st.pl;
+        launch_maxpool(p, B, s);
+        break;
+      }
+      case kStepResize: {
+        ResizeP p;
+        p.in = view(ctx, st.in); p.out = out; p.align_corners = st.align; p.half_pixel = st.half;
+        launch_resize_bilinear(p, B, s);
+        break;
+      }
+    }
+    ++launches;
+  }
+  return launches;
+}
+
+}  // namespace fdt

@@ -1,0 +1,141 @@
+// Kernel parameter blocks and launchers for the BlazeFace / face-mesh hot path (sm_100a).
+// Layout: activations are NHWC fp32 in HBM, channel stride Cs = roundup4(C) (padded lanes are
+// always written as 0) except for views into graph outputs, which are dense (Cs == C).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "../../include/fdt_api.h"
+
+namespace fdt {
+
+enum { kActNone = 0, kActRelu = 1, kActPrelu = 2 };
+
+struct TV {  // tensor view (device)
+  float* p = nullptr;       // image 0
+  long long istride = 0;    // floats between consecutive images
+  int H = 1, W = 1, C = 1, Cs = 1;
+};
+
+// ---- generic one-thread-per-element kernels (fuse_level 0 and shapes the tiled kernels skip) ----
+struct NaiveConvP {
+  TV in, out;
+  const float* w;      // OHWI [Cout][kh][kw][Cin]  (depthwise: [kh][kw][C])
+  const float* bias;   // [Cout] or nullptr
+  const float* alpha;  // PReLU slopes [Cout] or nullptr
+  int kh, kw, sh, sw, pt, pl, act, depthwise;
+};
+struct EltP {
+  TV a, b, out;        // b unused for unary ops
+  const float* alpha;
+  int act;
+};
+struct PoolP { TV in, out; int fh, fw, sh, sw, pt, pl; };
+struct ResizeP { TV in, out; int align_corners, half_pixel; };
+
+void launch_naive_conv(const NaiveConvP& p, int B, cudaStream_t s);
+void launch_add(const EltP& p, int B, cudaStream_t s);
+void launch_act(const EltP& p, int B, cudaStream_t s);
+void launch_padc(const EltP& p, int B, cudaStream_t s);
+void launch_maxpool(const PoolP& p, int B, cudaStream_t s);
+void launch_resize_bilinear(const ResizeP& p, int B, cudaStream_t s);
+
+// ---- preprocessing ----
+struct LetterboxP {
+  const uint8_t* frames;   // [B][H][row_stride]
+  long long frame_stride;  // bytes between frames
+  int row_stride, channels, src_w, src_h;
+  uint8_t* out;            // [B][S_h][S_w][3] BGR
+  int dst_w, dst_h, new_w, new_h, pad_top, pad_left;
+  // INTER_LINEAR tap tables (device): x: [new_w], y: [new_h]
+  const int* x0; const int* x1; const short* ax0; const short* ax1;
+  const int* y0; const int* y1; const short* by0; const short* by1;
+  int identity;            // 1: no resize (new == src)
+};
+void launch_letterbox(const LetterboxP& p, int B, cudaStream_t s);
+// u8 [B][S][S][3] BGR -> f32 [B][S][S][3] RGB, v*(1/127.5)-1
+void launch_normalize(const uint8_t* in, TV out, int B, cudaStream_t s);
+
+// ---- tiled conv kernels: im2col + register-tiled fp32 GEMM ----
+struct GemmConvP {
+  const float* in;          // f32 NHWC (or nullptr when in8 is used)
+  const uint8_t* in8;       // u8 [B][H][W][3] BGR letterboxed image: normalised + swapped on load
+  long long in_istride;
+  int H, W, Cin, CinS;
+  int kh, kw, sh, sw, pt, pl, OH, OW;
+  int K, KP, KS;
+  float* out; long long out_istride; int Cout, CoutS, vec_store;
+  const float* w;           // [KP][CoutP], row k = (ky,kx,c)
+  const float* bias;        // [CoutP]
+  const float* alpha;       // [CoutP] or nullptr
+  int act, CoutP, NNG, NC, nchunks, NPG, TM;
+  size_t smem_bytes;
+};
+void launch_gemm_conv(const GemmConvP& p, int B, cudaStream_t s, int max_ctas);
+
+// ---- fused BlazeBlock: [DW3x3] -> PW1x1 + bias [+ residual(maxpool, channel pad)] + act ----
+struct DwPwP {
+  const float* in; long long in_istride; int H, W, Cin, CinS;
+  int has_dw, s, dpt, dpl, OH, OW;
+  const float* dww;         // [9][KP]
+  const float* dwb;         // [KP]
+  int KP, KS;
+  float* out; long long out_istride; int Cout, CoutS, vec_store;
+  const float* w;           // [KP][CoutP]
+  const float* bias; const float* alpha;
+  int act, CoutP, NNG, NC, nchunks, NPG, TM;
+  const float* res; long long res_istride; int res_H, res_W, res_C, res_Cs, res_pool;
+  int TH, TW, G, IH, IW, tilesX, tilesY;
+  size_t smem_bytes;
+};
+void launch_dwpw(const DwPwP& p, int B, cudaStream_t s, int max_ctas);
+
+// ---- detector post-processing: one block per image ----
+struct DecodeP {
+  const float* boxes; long long boxes_istride;    // [B][N][16]
+  const float* scores; long long scores_istride;  // [B][N]
+  const double* anchors;                          // [N][2]
+  int N, input_h;
+  double raw_thresh, score_thresh, iou_thresh;
+  double pad_t, pad_b, pad_l, pad_r;              // normalised letterbox padding
+  double min_score, min_face_size, img_w, img_h;
+  int max_faces;
+  fdt_face* faces;                                // [B][max_faces]
+  int* counts;                                    // [B]
+  int* cand_idx; int cand_cap; int* cand_n;       // debug taps (may be null)
+};
+size_t decode_smem_bytes(int N);
+void launch_decode_nms(const DecodeP& p, int B, cudaStream_t s);
+
+// ---- mesh stage ----
+struct FaceListP {
+  const int* counts; int B, max_faces;
+  const fdt_face* faces;
+  double img_w, img_h; int out_size;
+  int cap;                 // capacity of the face list
+  int skip;                // first face (in chunk order) of this pass
+  int* total;              // [1] number of faces with a valid ROI (<= cap)
+  int* face_img; int* face_slot;   // [cap]
+  double* affine;          // [cap][6] inverse map (dst -> src), cv::warpAffine convention
+  double* align;           // [cap][4] theta,cx,cy,size
+  int* overflow;           // [1] set when more than cap faces were found
+};
+void launch_build_face_list(const FaceListP& p, cudaStream_t s);
+
+struct WarpP {
+  const uint8_t* frames; long long frame_stride; int row_stride, channels, src_w, src_h;
+  const int* face_img; const double* affine; int nfaces, out_size;
+  uint8_t* crops;          // [nfaces][out][out][3] BGR
+};
+void launch_warp_affine(const WarpP& p, cudaStream_t s);
+
+struct MeshPostP {
+  const float* raw; long long raw_istride;     // [F][1404]
+  const float* flag; long long flag_istride;   // [F][1]
+  const double* align; int nfaces, in_size;
+  float* mesh_out;                             // [F][1404] absolute pixels
+  double* score_out;                           // [F]
+};
+void launch_mesh_post(const MeshPostP& p, cudaStream_t s);
+
+}  // namespace fdt

@@ -1,0 +1,88 @@
+// Preprocessing kernels: fused letterbox (cv::resize INTER_LINEAR 8U fixed point +
+// copyMakeBorder(0) + BGRA/GRAY->BGR) and the [-1,1] normalisation.
+// Reference: convertImageToTensor / bgrMatToSignedFloat32 (lib/src/util/helpers.dart:303-421).
+#include "kernels.h"
+
+namespace fdt {
+namespace {
+
+__device__ __forceinline__ void load_bgr(const uint8_t* px, int channels, int* v) {
+  if (channels == 1) { v[0] = v[1] = v[2] = px[0]; }
+  else { v[0] = px[0]; v[1] = px[1]; v[2] = px[2]; }
+}
+
+__global__ void k_letterbox(LetterboxP p, int B) {
+  const int npx = p.dst_w * p.dst_h;
+  const long long total = (long long)B * npx;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int b = (int)(idx / npx);
+    int r = (int)(idx - (long long)b * npx);
+    int y = r / p.dst_w, x = r - y * p.dst_w;
+    int dy = y - p.pad_top, dx = x - p.pad_left;
+    uchar3 o = make_uchar3(0, 0, 0);
+    if (dy >= 0 && dy < p.new_h && dx >= 0 && dx < p.new_w) {
+      const uint8_t* src = p.frames + (size_t)b * p.frame_stride;
+      if (p.identity) {
+        int v[3];
+        load_bgr(src + (size_t)dy * p.row_stride + (size_t)dx * p.channels, p.channels, v);
+        o = make_uchar3((unsigned char)v[0], (unsigned char)v[1], (unsigned char)v[2]);
+      } else {
+        const int xa = p.x0[dx], xb = p.x1[dx], wa = p.ax0[dx], wb = p.ax1[dx];
+        const int ya = p.y0[dy], yb = p.y1[dy], va = p.by0[dy], vb = p.by1[dy];
+        int t00[3], t01[3], t10[3], t11[3];
+        const uint8_t* r0 = src + (size_t)ya * p.row_stride;
+        const uint8_t* r1 = src + (size_t)yb * p.row_stride;
+        load_bgr(r0 + (size_t)xa * p.channels, p.channels, t00);
+        load_bgr(r0 + (size_t)xb * p.channels, p.channels, t01);
+        load_bgr(r1 + (size_t)xa * p.channels, p.channels, t10);
+        load_bgr(r1 + (size_t)xb * p.channels, p.channels, t11);
+        int res[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          // HResizeLinear (11-bit) then VResizeLinear<uchar,int,short> fixed point (resize.cpp)
+          int h0 = t00[c] * wa + t01[c] * wb;
+          int h1 = t10[c] * wa + t11[c] * wb;
+          int v = ((va * (h0 >> 4)) >> 16) + ((vb * (h1 >> 4)) >> 16);
+          v = (v + 2) >> 2;
+          res[c] = v < 0 ? 0 : (v > 255 ? 255 : v);
+        }
+        o = make_uchar3((unsigned char)res[0], (unsigned char)res[1], (unsigned char)res[2]);
+      }
+    }
+    uint8_t* d = p.out + (size_t)idx * 3;
+    d[0] = o.x; d[1] = o.y; d[2] = o.z;
+  }
+}
+
+__global__ void k_normalize(const uint8_t* in, TV out, long long total) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(idx % out.Cs);
+    long long pix = idx / out.Cs;
+    long long hw = (long long)out.H * out.W;
+    int b = (int)(pix / hw);
+    long long sp = pix % hw;
+    float v = 0.f;
+    if (c < 3) v = fmaf((float)in[((size_t)b * hw + sp) * 3 + (2 - c)], 1.0f / 127.5f, -1.0f);
+    out.p[b * out.istride + sp * out.Cs + c] = v;
+  }
+}
+
+}  // namespace
+
+void launch_letterbox(const LetterboxP& p, int B, cudaStream_t s) {
+  long long total = (long long)B * p.dst_w * p.dst_h;
+  long long g = (total + 255) / 256;
+  if (g > 148LL * 64) g = 148LL * 64;
+  k_letterbox<<<(int)(g < 1 ? 1 : g), 256, 0, s>>>(p, B);
+}
+
+void launch_normalize(const uint8_t* in, TV out, int B, cudaStream_t s) {
+  long long total = (long long)B * out.H * out.W * out.Cs;
+  long long g = (total + 255) / 256;
+  if (g > 148LL * 32) g = 148LL * 32;
+  k_normalize<<<(int)(g < 1 ? 1 : g), 256, 0, s>>>(in, out, total);
+}
+
+}  // namespace fdt

@@ -1,0 +1,611 @@
+#include "plan.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+namespace fdt {
+namespace {
+
+constexpr size_t kSmemLimit = 200 * 1024;
+constexpr int kActNone = 0, kActRelu = 1, kActPrelu = 2;
+
+inline int ru(int v, int m) { return (v + m - 1) / m * m; }
+inline int smem_stride(int KP) { return KP + (((KP / 4) % 2 == 0) ? 4 : 0); }
+
+void same_pad(int in, int k, int s, int* before) {
+  int out = (in + s - 1) / s;
+  int total = (out - 1) * s + k - in;
+  if (total < 0) total = 0;
+  *before = total / 2;
+}
+
+struct View { int root = -1; long long off = 0; };
+
+struct Fused {       // analysis result for one CONV_2D
+  bool ok = false;
+  PStep st;
+  int src_tf = -1, res_tf = -1, out_tf = -1;
+};
+
+struct Builder {
+  const TfModel& m;
+  Plan& P;
+  int fuse;
+  std::string err;
+  std::vector<char> done;
+  std::vector<int> ncons;
+  std::vector<View> views;
+  std::map<int, Fused> fused;  // conv op index -> fused step
+
+  Builder(const TfModel& mm, Plan& pp, int f) : m(mm), P(pp), fuse(f) {}
+
+  bool fail(const std::string& e) { err = e; return false; }
+
+  long long numel(int t) const { return m.tensors[t].numel(); }
+
+  bool is_view(int t) const { return views[t].root >= 0; }
+
+  // ---- output views ---------------------------------------------------------------------------
+  bool assign_view(int t, int root, long long off) {
+    views[t].root = root;
+    views[t].off = off;
+    int p = m.producer(t);
+    if (p < 0) return true;
+    const TfOp& op = m.ops[p];
+    if (op.code == kOpReshape) {
+      done[p] = 1;
+      return assign_view(op.in[0], root, off);
+    }
+    if (op.code == kOpConcat) {
+      const TfTensor& ot = m.tensors[t];
+      int axis = op.axis < 0 ? op.axis + (int)ot.shape.size() : op.axis;
+      for (int d = 0; d < axis; ++d)
+        if (ot.shape[d] != 1) return fail("CONCATENATION over a non-leading axis is not supported");
+      done[p] = 1;
+      long long cur = off;
+      for (int i : op.in) {
+        if (!assign_view(i, root, cur)) return false;
+        cur += numel(i);
+      }
+    }
+    return true;
+  }
+
+  int pt(int tf) {
+    auto it = P.tf2pt.find(tf);
+    if (it != P.tf2pt.end()) return it->second;
+    const TfTensor& t = m.tensors[tf];
+    PTensor x;
+    x.tf = tf;
+    int r = (int)t.shape.size();
+    if (r == 4) { x.H = t.shape[1]; x.W = t.shape[2]; x.C = t.shape[3]; }
+    else if (r == 3) { x.H = 1; x.W = t.shape[1]; x.C = t.shape[2]; }
+    else if (r == 2) { x.H = 1; x.W = 1; x.C = t.shape[1]; }
+    else { x.H = 1; x.W = 1; x.C = (int)t.numel(); }
+    if (is_view(tf)) {
+      x.Cs = x.C;
+      x.root = views[tf].root;
+      x.view_off = views[tf].off;
+      x.istride = P.out_elems[x.root];
+    } else {
+      x.Cs = ru(x.C, 4);
+      x.istride = (long long)x.H * x.W * x.Cs;
+    }
+    P.tensors.push_back(x);
+    P.tf2pt[tf] = (int)P.tensors.size() - 1;
+    return (int)P.tensors.size() - 1;
+  }
+
+  long long push(const std::vector<float>& v, size_t padded) {
+    while (P.blob.size() % 4) P.blob.push_back(0.f);  // 16-byte alignment of every array
+    long long off = (long long)P.blob.size();
+    P.blob.insert(P.blob.end(), v.begin(), v.end());
+    if (padded > v.size()) P.blob.insert(P.blob.end(), padded - v.size(), 0.f);
+    return off;
+  }
+
+  // single consumer op of tensor t (or -1)
+  int sole_consumer(int t) const {
+    if (ncons[t] != 1) return -1;
+    auto c = m.consumers(t);
+    return c.size() == 1 ? c[0] : -1;
+  }
+
+  // Follows T -> [RELU | PRELU]; returns the activation to fuse and the final tensor.
+  void fuse_activation(int* cur, int* act, int* alpha_tf, std::vector<int>* absorbed) {
+    if (is_view(*cur)) return;
+    int c = sole_consumer(*cur);
+    if (c < 0 || done[c]) return;
+    const TfOp& op = m.ops[c];
+    if (op.code == kOpRelu) {
+      *act = kActRelu;
+    } else if (op.code == kOpPrelu) {
+      std::vector<float> a;
+      if (!m.const_f32(op.in[1], &a) || (int)a.size() != m.tensors[*cur].shape.back()) return;
+      *act = kActPrelu;
+      *alpha_tf = op.in[1];
+    } else {
+      return;
+    }
+    absorbed->push_back(c);
+    *cur = op.out[0];
+  }
+
+  bool pack_alpha(int alpha_tf, size_t padded, long long* off) {
+    std::vector<float> a;
+    if (!m.const_f32(alpha_tf, &a)) return fail("PRELU alpha is not constant");
+    *off = push(a, padded);
+    return true;
+  }
+
+  // ---- tiling of the GEMM part ----------------------------------------------------------------
+  static void plan_columns(PStep* s) {
+    s->CoutP = ru(s->Cout, 8);
+    int groups = s->CoutP / 8;
+    if (groups <= 12) {
+      s->nchunks = 1;
+      s->NNG = groups;
+    } else {
+      s->nchunks = (groups + 11) / 12;
+      s->NNG = (groups + s->nchunks - 1) / s->nchunks;
+    }
+    s->NC = s->NNG * 8;
+    s->TM = s->NNG >= 6 ? 8 : 4;
+    s->NPG = 128 / s->TM;
+  }
+
+  // ---- analysis of one pointwise conv: DW3x3 -> PW -> (+res) -> act ---------------------------
+  bool analyse_pointwise(int ci, Fused* F) {
+    const TfOp& conv = m.ops[ci];
+    const TfTensor& wt = m.tensors[conv.in[1]];
+    if (wt.shape.size() != 4 || wt.shape[1] != 1 || wt.shape[2] != 1) return false;
+    if (conv.stride_h != 1 || conv.stride_w != 1 || (conv.act != 0 && conv.act != 1)) return false;
+    PStep st;
+    st.kind = kStepDwPw;
+    std::vector<int> absorbed;
+    int X = conv.in[0];
+    int src = X;
+    int dwi = m.producer(X);
+    if (dwi >= 0 && !done[dwi] && m.ops[dwi].code == kOpDwConv2D && ncons[X] == 1 && !is_view(X)) {
+      const TfOp& dw = m.ops[dwi];
+      const TfTensor& dwt = m.tensors[dw.in[1]];
+      bool ok = dwt.shape.size() == 4 && dwt.shape[1] == 3 && dwt.shape[2] == 3 && dw.depth_mult == 1 &&
+                dw.dil_h == 1 && dw.dil_w == 1 && dw.padding == 0 && dw.stride_h == dw.stride_w &&
+                (dw.stride_h == 1 || dw.stride_h == 2) && dw.act == 0 && dw.in.size() >= 3;
+      if (ok) {
+        st.has_dw = true;
+        st.dws = dw.stride_h;
+        src = dw.in[0];
+        const TfTensor& it = m.tensors[src];
+        same_pad(it.dim(1), 3, st.dws, &st.dpt);
+        same_pad(it.dim(2), 3, st.dws, &st.dpl);
+        absorbed.push_back(dwi);
+      }
+    }
+    const TfTensor& st_in = m.tensors[src];
+    if (st_in.shape.size() != 4) return false;
+    if (is_view(src) && (st_in.dim(3) % 4 != 0 || views[src].off % 4 != 0 || P.out_elems[views[src].root] % 4 != 0))
+      return false;
+    int Cin = st_in.dim(3);
+    st.Cout = wt.shape[0];
+    st.K = Cin;
+    st.KP = ru(Cin, 4);
+    st.KS = smem_stride(st.KP);
+    plan_columns(&st);
+    // epilogue chain
+    int cur = conv.out[0];
+    int res = -1, alpha_tf = -1;
+    st.act = conv.act == 1 ? kActRelu : kActNone;
+    if (st.act == kActNone && !is_view(cur)) {
+      int c = sole_consumer(cur);
+      if (c >= 0 && !done[c] && m.ops[c].code == kOpAdd && (m.ops[c].act == 0 || m.ops[c].act == 1) &&
+          m.ops[c].in.size() == 2) {
+        const TfOp& add = m.ops[c];
+        int R = add.in[0] == cur ? add.in[1] : add.in[0];
+        std::vector<int> abs2;
+        int r = R;
+        int pool = 0;
+        bool good = R != cur;
+        int pp = m.producer(r);
+        if (good && pp >= 0 && m.ops[pp].code == kOpPad && ncons[r] == 1 && !is_view(r) && !done[pp]) {
+          std::vector<int> pads;
+          const TfTensor& pi = m.tensors[m.ops[pp].in[0]];
+          if (m.const_i32(m.ops[pp].in[1], &pads) && pads.size() == 8 && pads[0] == 0 && pads[1] == 0 &&
+              pads[2] == 0 && pads[3] == 0 && pads[4] == 0 && pads[5] == 0 && pads[6] == 0 && pi.shape.size() == 4) {
+            abs2.push_back(pp);
+            r = m.ops[pp].in[0];
+            pp = m.producer(r);
+          }
+        }
+        if (good && pp >= 0 && m.ops[pp].code == kOpMaxPool && ncons[r] == 1 && !is_view(r) && !done[pp]) {
+          const TfOp& mp = m.ops[pp];
+          if (mp.filter_h == 2 && mp.filter_w == 2 && mp.stride_h == 2 && mp.stride_w == 2 && mp.act == 0) {
+            abs2.push_back(pp);
+            r = mp.in[0];
+            pool = 1;
+          }
+        }
+        const TfTensor& rt = m.tensors[r];
+        const TfTensor& ot = m.tensors[cur];
+        int rp = m.producer(r);
+        // the residual source must be materialised by an earlier step: either a stand-alone op or
+        // the final tensor of an already fused chain (never an absorbed intermediate)
+        bool produced_before = rp >= 0 && rp < ci && (!done[rp] || is_output_of_fused(r));
+        good = good && rt.shape.size() == 4 && rt.dim(3) <= st.Cout && produced_before;
+        if (good) {
+          if (pool) good = (rt.dim(1) + 1) / 2 == ot.dim(1) && (rt.dim(2) + 1) / 2 == ot.dim(2);
+          else good = rt.dim(1) == ot.dim(1) && rt.dim(2) == ot.dim(2);
+        }
+        if (good) {
+          res = r;
+          st.res_pool = pool;
+          absorbed.push_back(c);
+          for (int a : abs2) absorbed.push_back(a);
+          cur = add.out[0];
+          if (add.act == 1) st.act = kActRelu;
+        }
+      }
+      if (st.act == kActNone) fuse_activation(&cur, &st.act, &alpha_tf, &absorbed);
+    }
+    // spatial tiling
+    const TfTensor& ot = m.tensors[conv.out[0]];
+    int OH = ot.dim(1), OW = ot.dim(2);
+    if (!plan_spatial(&st, OH, OW)) return false;
+    // commit
+    for (int a : absorbed) done[a] = 1;
+    done[ci] = 1;
+    F->ok = true;
+    F->st = st;
+    F->src_tf = src;
+    F->res_tf = res;
+    F->out_tf = cur;
+    F->st.name = m.tensors[cur].name;
+    fused_outputs.push_back(cur);
+    // weights
+    std::vector<float> w, b;
+    if (!m.const_f32(conv.in[1], &w)) return fail("conv weights are not constant");
+    if (conv.in.size() > 2 && conv.in[2] >= 0) { if (!m.const_f32(conv.in[2], &b)) return fail("conv bias is not constant"); }
+    b.resize(st.Cout, 0.f);
+    std::vector<float> wk((size_t)st.KP * st.CoutP, 0.f);
+    for (int co = 0; co < st.Cout; ++co)
+      for (int c = 0; c < Cin; ++c) wk[(size_t)c * st.CoutP + co] = w[(size_t)co * Cin + c];
+    size_t padded = (size_t)st.nchunks * st.NC + 8;
+    F->st.w = push(wk, wk.size());
+    F->st.bias = push(b, padded);
+    if (alpha_tf >= 0 && !pack_alpha(alpha_tf, padded, &F->st.alpha)) return false;
+    if (st.has_dw) {
+      const TfOp& dw = m.ops[absorbed[0]];
+      std::vector<float> dwv, dbv;
+      if (!m.const_f32(dw.in[1], &dwv) || !m.const_f32(dw.in[2], &dbv)) return fail("depthwise weights are not constant");
+      std::vector<float> dk((size_t)9 * st.KP, 0.f);
+      for (int t = 0; t < 9; ++t)
+        for (int c = 0; c < Cin; ++c) dk[(size_t)t * st.KP + c] = dwv[(size_t)t * Cin + c];
+      F->st.dww = push(dk, dk.size());
+      F->st.dwb = push(dbv, st.KP);
+    }
+    F->st.macs = (double)OH * OW * ((double)Cin * st.Cout + (st.has_dw ? 9.0 * Cin : 0.0));
+    return true;
+  }
+
+  std::vector<int> fused_outputs;
+  bool is_output_of_fused(int tf) const {
+    return std::find(fused_outputs.begin(), fused_outputs.end(), tf) != fused_outputs.end();
+  }
+
+  bool plan_spatial(PStep* s, int OH, int OW) {
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      int Pn = s->TM * s->NPG;
+      int bestTH = 0, bestTW = 0, bestG = 1;
+      double best = -1;
+      if (OH * OW <= Pn) {
+        bestTH = OH; bestTW = OW; bestG = Pn / (OH * OW);
+      } else {
+        for (int TW = std::min(OW, Pn); TW >= 1; --TW) {
+          int TH = std::min(OH, Pn / TW);
+          if (TH < 1) continue;
+          double tiles = (double)((OH + TH - 1) / TH) * ((OW + TW - 1) / TW);
+          double util = (double)OH * OW / (tiles * Pn);
+          double halo = (double)((TH - 1) * s->dws + 3) * ((TW - 1) * s->dws + 3) / ((double)TH * TW * s->dws * s->dws);
+          double score = util / (s->has_dw ? halo : 1.0);
+          if (score > best + 1e-9) { best = score; bestTH = TH; bestTW = TW; }
+        }
+      }
+      s->TH = bestTH; s->TW = bestTW; s->G = bestG;
+      s->IH = s->has_dw ? (s->TH - 1) * s->dws + 3 : s->TH;
+      s->IW = s->has_dw ? (s->TW - 1) * s->dws + 3 : s->TW;
+      s->tilesY = (OH + s->TH - 1) / s->TH;
+      s->tilesX = (OW + s->TW - 1) / s->TW;
+      size_t in_elems = (size_t)s->G * s->IH * s->IW * s->KS;
+      size_t a_elems = (size_t)Pn * s->KS;
+      size_t floats = s->has_dw ? in_elems + a_elems : std::max(in_elems, a_elems);
+      floats += (size_t)s->KP * s->NC;
+      s->smem = floats * 4;
+      if (s->smem <= kSmemLimit) return true;
+      if (s->NPG % 2 == 0 && attempt == 0) s->NPG /= 2; else break;   // retry with 64-pixel tiles
+    }
+    return false;
+  }
+
+  // ---- dense k x k conv as im2col GEMM ---------------------------------------------------------
+  bool analyse_dense(int ci, Fused* F) {
+    const TfOp& conv = m.ops[ci];
+    const TfTensor& wt = m.tensors[conv.in[1]];
+    const TfTensor& it = m.tensors[conv.in[0]];
+    const TfTensor& ot = m.tensors[conv.out[0]];
+    if (wt.shape.size() != 4 || it.shape.size() != 4 || conv.dil_h != 1 || conv.dil_w != 1) return false;
+    if (conv.act != 0 && conv.act != 1) return false;
+    PStep st;
+    st.kind = kStepGemmConv;
+    st.kh = wt.shape[1]; st.kw = wt.shape[2];
+    st.sh = conv.stride_h; st.sw = conv.stride_w;
+    int Cin = wt.shape[3];
+    st.Cout = wt.shape[0];
+    if (conv.padding == 0) { same_pad(it.dim(1), st.kh, st.sh, &st.pt); same_pad(it.dim(2), st.kw, st.sw, &st.pl); }
+    st.K = st.kh * st.kw * Cin;
+    st.KP = ru(st.K, 4);
+    st.KS = smem_stride(st.KP);
+    plan_columns(&st);
+    // shrink the weight chunk until A (128 x KS) + W (KP x NC) fit
+    for (;;) {
+      st.smem = ((size_t)st.TM * st.NPG * st.KS + (size_t)st.KP * st.NC) * 4;
+      if (st.smem <= kSmemLimit) break;
+      if (st.NNG <= 1) return false;
+      st.NNG = (st.NNG + 1) / 2;
+      st.NC = st.NNG * 8;
+      st.nchunks = (st.CoutP + st.NC - 1) / st.NC;
+      st.TM = st.NNG >= 6 ? 8 : 4;
+      st.NPG = 128 / st.TM;
+    }
+    std::vector<int> absorbed;
+    int cur = conv.out[0], alpha_tf = -1;
+    st.act = conv.act == 1 ? kActRelu : kActNone;
+    if (st.act == kActNone) fuse_activation(&cur, &st.act, &alpha_tf, &absorbed);
+    st.in_u8 = conv.in[0] == m.inputs[0] && Cin == 3;
+    for (int a : absorbed) done[a] = 1;
+    done[ci] = 1;
+    std::vector<float> w, b;
+    if (!m.const_f32(conv.in[1], &w)) return fail("conv weights are not constant");
+    if (conv.in.size() > 2 && conv.in[2] >= 0) { if (!m.const_f32(conv.in[2], &b)) return fail("conv bias is not constant"); }
+    b.resize(st.Cout, 0.f);
+    std::vector<float> wk((size_t)st.KP * st.CoutP, 0.f);
+    for (int co = 0; co < st.Cout; ++co)
+      for (int k = 0; k < st.K; ++k) wk[(size_t)k * st.CoutP + co] = w[(size_t)co * st.K + k];
+    size_t padded = (size_t)st.nchunks * st.NC + 8;
+    st.w = push(wk, wk.size());
+    st.bias = push(b, padded);
+    if (alpha_tf >= 0 && !pack_alpha(alpha_tf, padded, &st.alpha)) return false;
+    st.macs = (double)ot.dim(1) * ot.dim(2) * st.K * st.Cout;
+    st.name = m.tensors[cur].name;
+    F->ok = true;
+    F->st = st;
+    F->src_tf = conv.in[0];
+    F->out_tf = cur;
+    fused_outputs.push_back(cur);
+    return true;
+  }
+
+  // ---- emission ---------------------------------------------------------------------------------
+  void use(int step, int t) {
+    if (t < 0) return;
+    PTensor& x = P.tensors[t];
+    if (x.def_step < 0) x.def_step = step;
+    x.last_use = std::max(x.last_use, step);
+  }
+
+  bool emit(PStep s) {
+    int idx = (int)P.steps.size();
+    if (s.in >= 0 && !P.tensors[s.in].materialized && !(s.in_u8))
+      return fail("internal: step '" + s.name + "' reads a tensor that is not materialised");
+    if (s.in2 >= 0 && !P.tensors[s.in2].materialized)
+      return fail("internal: step '" + s.name + "' reads a residual that is not materialised");
+    P.tensors[s.out].materialized = true;
+    if (!s.in_u8) use(idx, s.in);
+    use(idx, s.in2);
+    use(idx, s.out);
+    P.steps.push_back(std::move(s));
+    return true;
+  }
+
+  bool run() {
+    size_t nt = m.tensors.size(), no = m.ops.size();
+    done.assign(no, 0);
+    ncons.assign(nt, 0);
+    views.assign(nt, View());
+    for (const TfOp& op : m.ops)
+      for (int i : op.in) if (i >= 0) ncons[i]++;
+    for (int o : m.outputs) ncons[o]++;
+    P.out_elems.clear();
+    for (int o : m.outputs) P.out_elems.push_back(numel(o));
+    for (size_t oi = 0; oi < m.outputs.size(); ++oi)
+      if (!assign_view(m.outputs[oi], (int)oi, 0)) return false;
+
+    const TfTensor& in = m.tensors[m.inputs[0]];
+    if (in.shape.size() != 4 || in.shape[3] != 3) return fail("model input must be [1,H,W,3]");
+    P.in_h = in.shape[1];
+    P.in_w = in.shape[2];
+
+    // pass 1: fusion analysis
+    if (fuse >= 1) {
+      for (size_t i = 0; i < no; ++i) {
+        if (done[i] || m.ops[i].code != kOpConv2D) continue;
+        Fused F;
+        if (!analyse_pointwise((int)i, &F) && err.empty()) analyse_dense((int)i, &F);
+        if (!err.empty()) return false;
+        if (F.ok) fused[(int)i] = F;
+      }
+    }
+    // graph input
+    P.input = pt(m.inputs[0]);
+    P.tensors[P.input].is_input = true;
+    bool need_f32_input = fuse == 0;
+    for (int c : m.consumers(m.inputs[0])) {
+      auto it = fused.find(c);
+      if (it == fused.end() || !it->second.st.in_u8) need_f32_input = true;
+    }
+    if (need_f32_input) {
+      PStep s;
+      s.kind = kStepNormalize;
+      s.name = "normalize";
+      s.out = P.input;
+      s.in_u8 = true;
+      if (!emit(s)) return false;
+    }
+    // pass 2: emission in graph order
+    for (size_t i = 0; i < no; ++i) {
+      const TfOp& op = m.ops[i];
+      auto fit = fused.find((int)i);
+      if (fit != fused.end()) {
+        Fused& F = fit->second;
+        PStep s = F.st;
+        s.in = pt(F.src_tf);
+        s.in2 = F.res_tf >= 0 ? pt(F.res_tf) : -1;
+        s.out = pt(F.out_tf);
+        if (s.in_u8) s.in = P.input;
+        if (!emit(s)) return false;
+        continue;
+      }
+      if (done[i] || op.code == kOpDequantize) continue;
+      PStep s;
+      s.name = op.out.empty() ? "" : m.tensors[op.out[0]].name;
+      switch (op.code) {
+        case kOpConv2D: case kOpDwConv2D: {
+          const TfTensor& wt = m.tensors[op.in[1]];
+          const TfTensor& it = m.tensors[op.in[0]];
+          if (wt.shape.size() != 4 || it.shape.size() != 4) return fail("conv rank");
+          if (op.dil_h != 1 || op.dil_w != 1 || (op.code == kOpDwConv2D && op.depth_mult != 1))
+            return fail("dilated / depth-multiplied convolutions are not supported");
+          if (op.act != 0 && op.act != 1) return fail("unsupported fused activation");
+          s.kind = kStepNaiveConv;
+          s.depthwise = op.code == kOpDwConv2D;
+          s.kh = wt.shape[1]; s.kw = wt.shape[2]; s.sh = op.stride_h; s.sw = op.stride_w;
+          if (op.padding == 0) { same_pad(it.dim(1), s.kh, s.sh, &s.pt); same_pad(it.dim(2), s.kw, s.sw, &s.pl); }
+          s.act = op.act == 1 ? kActRelu : kActNone;
+          std::vector<float> w, b;
+          if (!m.const_f32(op.in[1], &w)) return fail("conv weights are not constant");
+          if (op.in.size() > 2 && op.in[2] >= 0 && !m.const_f32(op.in[2], &b)) return fail("conv bias is not constant");
+          s.Cout = s.depthwise ? wt.shape[3] : wt.shape[0];
+          b.resize(s.Cout, 0.f);
+          s.w = push(w, w.size());
+          s.bias = push(b, b.size());
+          s.in = pt(op.in[0]);
+          s.out = pt(op.out[0]);
+          const TfTensor& ot = m.tensors[op.out[0]];
+          s.macs = (double)ot.dim(1) * ot.dim(2) * s.kh * s.kw * (s.depthwise ? s.Cout : (double)wt.shape[3] * s.Cout);
+          break;
+        }
+        case kOpAdd:
+          if (op.in.size() != 2 || numel(op.in[0]) != numel(op.in[1])) return fail("broadcasting ADD is not supported");
+          if (op.act != 0 && op.act != 1) return fail("unsupported fused activation");
+          s.kind = kStepAdd;
+          s.act = op.act == 1 ? kActRelu : kActNone;
+          s.in = pt(op.in[0]); s.in2 = pt(op.in[1]); s.out = pt(op.out[0]);
+          break;
+        case kOpRelu:
+          s.kind = kStepAct; s.act = kActRelu; s.in = pt(op.in[0]); s.out = pt(op.out[0]);
+          break;
+        case kOpPrelu: {
+          s.kind = kStepAct; s.act = kActPrelu; s.in = pt(op.in[0]); s.out = pt(op.out[0]);
+          std::vector<float> a;
+          if (!m.const_f32(op.in[1], &a) || (int)a.size() != P.tensors[s.out].C) return fail("PRELU alpha must be per-channel");
+          s.alpha = push(a, a.size() + 8);
+          break;
+        }
+        case kOpPad: {
+          std::vector<int> pads;
+          if (!m.const_i32(op.in[1], &pads) || pads.size() != 8) return fail("PAD paddings");
+          for (int k = 0; k < 7; ++k) if (pads[k] != 0) return fail("only trailing channel PAD is supported");
+          s.kind = kStepPadC; s.in = pt(op.in[0]); s.out = pt(op.out[0]);
+          break;
+        }
+        case kOpMaxPool: {
+          const TfTensor& it = m.tensors[op.in[0]];
+          s.kind = kStepMaxPool; s.fh = op.filter_h; s.fw = op.filter_w; s.sh = op.stride_h; s.sw = op.stride_w;
+          if (op.padding == 0) { same_pad(it.dim(1), s.fh, s.sh, &s.pt); same_pad(it.dim(2), s.fw, s.sw, &s.pl); }
+          s.in = pt(op.in[0]); s.out = pt(op.out[0]);
+          break;
+        }
+        case kOpResizeBilinear:
+          s.kind = kStepResize; s.align = op.align_corners; s.half = op.half_pixel;
+          s.in = pt(op.in[0]); s.out = pt(op.out[0]);
+          break;
+        default: {
+          char buf[96];
+          snprintf(buf, sizeof buf, "unsupported TFLite op %d in graph", op.code);
+          return fail(buf);
+        }
+      }
+      if (!emit(s)) return false;
+    }
+    // outputs
+    for (int o : m.outputs) {
+      int t = pt(o);
+      P.outputs.push_back(t);
+    }
+    // arena allocation
+    struct Block { long long off, size; int free_after; };
+    std::vector<Block> blocks;
+    long long top = 0;
+    std::vector<int> order;
+    for (size_t t = 0; t < P.tensors.size(); ++t)
+      if (P.tensors[t].materialized && P.tensors[t].root < 0) order.push_back((int)t);
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return P.tensors[a].def_step < P.tensors[b].def_step; });
+    for (int t : order) {
+      PTensor& x = P.tensors[t];
+      long long need = (x.istride + 3) / 4 * 4;
+      bool placed = false;
+      if (fuse == 1) {
+        for (Block& b : blocks) {
+          if (b.free_after < x.def_step && b.size >= need) {
+            x.arena_off = b.off;
+            b.free_after = x.last_use;
+            placed = true;
+            break;
+          }
+        }
+      }
+      if (!placed) {
+        x.arena_off = top;
+        blocks.push_back({top, need, x.last_use});
+        top += need;
+      }
+    }
+    P.arena_per_image = top;
+    return true;
+  }
+};
+
+}  // namespace
+
+bool Plan::build(const TfModel& m, int fuse, std::string* err) {
+  *this = Plan();
+  fuse_level = fuse;
+  Builder b(m, *this, fuse);
+  bool ok = b.run();
+  if (!ok && err) *err = b.err;
+  return ok;
+}
+
+std::string Plan::describe() const {
+  static const char* kn[] = {"normalize", "naive_conv", "gemm_conv", "dwpw", "add", "act", "padc", "maxpool", "resize"};
+  std::string s;
+  char buf[512];
+  double macs = 0;
+  for (size_t i = 0; i < steps.size(); ++i) {
+    const PStep& st = steps[i];
+    const PTensor& o = tensors[st.out];
+    macs += st.macs;
+    snprintf(buf, sizeof buf,
+             "%3zu %-10s in=%d res=%d%s out=%d[%dx%dx%d Cs%d %s] act=%d dw=%d/s%d K=%d NC=%dx%d TM=%d NPG=%d tile=%dx%dx%d smem=%zu  %s\n",
+             i, kn[st.kind], st.in >= 0 ? tensors[st.in].tf : -1, st.in2 >= 0 ? tensors[st.in2].tf : -1,
+             st.res_pool ? "(pool)" : "", o.tf, o.H, o.W, o.C, o.Cs, o.root >= 0 ? "view" : "arena", st.act,
+             (int)st.has_dw, st.dws, st.K, st.NC, st.nchunks, st.TM, st.NPG, st.TH, st.TW, st.G, st.smem, st.name.c_str());
+    s += buf;
+  }
+  snprintf(buf, sizeof buf, "steps=%zu  MACs/image=%.3fM  arena/image=%.1f KB  weights=%.1f KB\n", steps.size(),
+           macs / 1e6, arena_per_image * 4.0 / 1024, blob.size() * 4.0 / 1024);
+  s += buf;
+  return s;
+}
+
+}  // namespace fdt

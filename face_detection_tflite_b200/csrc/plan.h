@@ -1,0 +1,61 @@
+// Execution plan: the TFLite graph lowered to a list of kernel launches over a chunk of images.
+// fuse_level 0: one step per TFLite op (parity taps for every tensor);
+// fuse_level 1: BlazeBlock fusion (DW3x3 + PW1x1 + residual + activation in one kernel), stems as
+//               im2col GEMM reading the u8 letterboxed image, liveness-based activation reuse;
+// fuse_level 2: as 1 but without buffer reuse (every materialised tensor stays readable).
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "tflite_model.h"
+
+namespace fdt {
+
+struct PTensor {
+  int tf = -1;
+  int H = 1, W = 1, C = 1, Cs = 1;
+  long long istride = 0;     // floats per image
+  int root = -1;             // >= 0: dense view into graph output #root
+  long long view_off = 0;    // float offset inside that output's per-image row
+  long long arena_off = -1;  // per-image float offset inside the activation arena
+  int def_step = -1, last_use = -1;
+  bool materialized = false;
+  bool is_input = false;
+};
+
+enum StepKind { kStepNormalize, kStepNaiveConv, kStepGemmConv, kStepDwPw, kStepAdd, kStepAct, kStepPadC,
+                kStepMaxPool, kStepResize };
+
+struct PStep {
+  StepKind kind = kStepAct;
+  std::string name;
+  int in = -1, in2 = -1, out = -1;
+  int kh = 1, kw = 1, sh = 1, sw = 1, pt = 0, pl = 0, act = 0, depthwise = 0;
+  bool in_u8 = false;
+  bool has_dw = false;
+  int dws = 1, dpt = 0, dpl = 0, res_pool = 0;
+  long long w = -1, bias = -1, alpha = -1, dww = -1, dwb = -1;  // float offsets into Plan::blob
+  int K = 0, KP = 0, KS = 0, Cout = 0, CoutP = 0, NNG = 0, NC = 0, nchunks = 0, NPG = 0, TM = 0;
+  int TH = 0, TW = 0, G = 1, IH = 0, IW = 0, tilesX = 1, tilesY = 1;
+  size_t smem = 0;
+  int fh = 1, fw = 1, align = 0, half = 0;
+  double macs = 0;  // per image
+};
+
+struct Plan {
+  std::vector<PTensor> tensors;
+  std::vector<PStep> steps;
+  std::vector<float> blob;
+  std::map<int, int> tf2pt;
+  int input = -1, in_h = 0, in_w = 0;
+  std::vector<int> outputs;            // PTensor id per graph output
+  std::vector<long long> out_elems;    // floats per image per graph output
+  long long arena_per_image = 0;       // floats
+  int fuse_level = 1;
+
+  bool build(const TfModel& m, int fuse_level, std::string* err);
+  std::string describe() const;
+};
+
+}  // namespace fdt

@@ -1,0 +1,351 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libfdt_cuda.so), against the oracle on
+the same inputs.  Bars (BASELINE.json north_star):
+  * bit-exact: letterbox pad offsets + u8 letterboxed image, anchor table, surviving-anchor index set;
+  * raw head outputs: max|d| <= 1e-4 * max|ref| per head tensor (SURVEY.md 7.3 definition);
+  * boxes / keypoints / mesh points: <= 1e-3 normalised, identical face counts, matched IoU >= 0.99.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+from oracle import cv_ops as co, detect_post as dp, graph_exec, tflite_reader as tr
+from oracle.pipeline import OraclePipeline
+
+pytestmark = pytest.mark.gpu
+
+HEAD_REL_TOL = 1e-4       # of max|ref| per head tensor
+COORD_TOL = 1e-3          # normalised box / keypoint coordinates
+MODEL_ENUM = {"shortRange": 2, "full": 3, "backCamera": 1}
+
+
+@pytest.fixture(scope="module")
+def fdt(lib):
+    import face_detection_tflite_b200 as pkg
+    return pkg
+
+
+_dets = {}
+
+
+def get_detector(fdt, model, fuse=-1, mesh=True, **kw):
+    key = (model, fuse, mesh, tuple(sorted(kw.items())))
+    if key not in _dets:
+        _dets[key] = fdt.FaceDetector.create(fdt.FaceDetectionModel[model], fuseLevel=fuse, withMesh=mesh, **kw)
+    return _dets[key]
+
+
+_oracles = {}
+
+
+def get_oracle(model_bytes, model, backend="f64"):
+    key = (model, backend)
+    if key not in _oracles:
+        _oracles[key] = OraclePipeline(model_bytes[model], model, model_bytes["mesh"], backend)
+    return _oracles[key]
+
+
+def iou(a, b):
+    return dp.iou(a, b)
+
+
+def assert_faces_match(got_faces, want_dets):
+    assert len(got_faces) == len(want_dets)
+    for g, w in zip(got_faces, want_dets):
+        r = g.detectionData.boundingBox
+        assert g.anchorIndex == w.anchor
+        assert abs(g.score - w.score) <= 1e-4
+        assert np.abs(np.array([r.xmin, r.ymin, r.xmax, r.ymax]) - np.array([w.xmin, w.ymin, w.xmax, w.ymax])).max() <= COORD_TOL
+        assert np.abs(np.array(g.detectionData.keypointsXY) - np.array(w.kp)).max() <= COORD_TOL
+        assert iou((r.xmin, r.ymin, r.xmax, r.ymax), (w.xmin, w.ymin, w.xmax, w.ymax)) >= 0.99
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("model", ["shortRange", "full", "backCamera"])
+def test_anchor_table_bit_exact(fdt, model):
+    d = get_detector(fdt, model)
+    assert np.array_equal(d.anchors(), dp.generate_anchors(dp.ssd_options_for(model)))
+
+
+LB_SHAPES = [(720, 1280, 3), (1080, 1920, 3), (853, 1280, 3), (100, 100, 3), (1, 1, 3), (10, 10, 3), (50, 37, 3),
+             (128, 128, 3), (481, 641, 3), (300, 200, 4), (300, 200, 1), (64, 2000, 3), (2000, 64, 3)]
+
+
+@pytest.mark.parametrize("shape", LB_SHAPES)
+def test_letterbox_bit_exact_and_input_tensor(fdt, shape):
+    h, w, ch = shape
+    rng = np.random.default_rng(h * 7 + w)
+    frames = rng.integers(0, 256, (3, h, w, ch), dtype=np.uint8)
+    d = get_detector(fdt, "shortRange")
+    mt = {1: 0, 3: 16, 4: 24}[ch]
+    d.detectBatchRaw(frames, count=3, width=w, height=h, matType=mt)
+    got = d.debugLetterboxed(3)
+    t = d.debugInputTensor(3)
+    for b in range(3):
+        src = frames[b]
+        bgr = src[..., :3] if ch >= 3 else np.repeat(src, 3, 2)
+        want, p = co.letterbox_u8(np.ascontiguousarray(bgr), 128, 128)
+        assert np.array_equal(got[b], want)                                  # u8 stage: bit-exact
+        assert np.abs(t[b] - co.normalize_bgr_u8(want)).max() <= 1e-6       # fp32 stage: <= 2 ulp (Appendix B)
+
+
+def test_letterbox_golden_cv2_and_row_stride(fdt, golden, sample_images):
+    for model, S in (("shortRange", 128), ("full", 192), ("backCamera", 256)):
+        d = get_detector(fdt, model)
+        for name, img in sample_images.items():
+            h, w = img.shape[:2]
+            d.detectBatchRaw(img, count=1, width=w, height=h)
+            assert np.array_equal(d.debugLetterboxed(1)[0], golden["%s/%s/letterboxed_cv2" % (model, name)])
+    # padded rows (row_stride > width*3) give the same result
+    d = get_detector(fdt, "shortRange")
+    img = sample_images["landmark-ex1.jpg"]
+    h, w = img.shape[:2]
+    padded = np.zeros((h, w * 3 + 64), np.uint8)
+    padded[:, :w * 3] = img.reshape(h, -1)
+    d.detectBatchRaw(padded, count=1, width=w, height=h, rowStride=w * 3 + 64)
+    assert np.array_equal(d.debugLetterboxed(1)[0], golden["shortRange/landmark-ex1.jpg/letterboxed_cv2"])
+
+
+def _frames_for(model, sample_images, n_synth=3):
+    from face_detection_tflite_b200 import synth
+    S = {"shortRange": (1280, 720), "full": (1920, 1080), "backCamera": (1280, 720)}[model]
+    fr = list(synth.face_frames(n_synth, S[0], S[1], start=3))
+    fr.append(synth.noise_frames(1, S[0], S[1], seed=5)[0])
+    return fr
+
+
+@pytest.mark.parametrize("model,fuse", [("shortRange", 0), ("shortRange", 2), ("full", 0), ("full", 2), ("backCamera", 2)])
+def test_every_materialised_tensor(fdt, model_bytes, sample_images, model, fuse):
+    """Layer-by-layer parity: every activation the plan materialises vs the fp64 oracle."""
+    d = get_detector(fdt, model, fuse=fuse, mesh=False)
+    o = get_oracle(model_bytes, model)
+    img = sample_images["landmark-ex1.jpg"]
+    h, w = img.shape[:2]
+    frames = np.stack([img, img[::-1].copy()])
+    d.detectBatchRaw(frames, count=2, width=w, height=h)
+    t0, _, _ = o.preprocess(frames[0])
+    t1, _, _ = o.preprocess(frames[1])
+    ref = o.det.exe.run(np.stack([t0, t1]), taps="all")
+    checked, worst = 0, 0.0
+    for tf_idx, want in ref.items():
+        try:
+            got = d.debugTensor(0, tf_idx, 2)
+        except ValueError:
+            continue                                  # fused away in this plan
+        want = want.reshape(got.shape)
+        scale = max(np.abs(want).max(), 1e-6)
+        err = np.abs(got - want).max() / scale
+        worst = max(worst, err)
+        assert err <= HEAD_REL_TOL, "tensor %d (%s): rel err %.3e" % (tf_idx, o.det.model.tensors[tf_idx].name, err)
+        checked += 1
+    assert checked >= (20 if fuse else 60)
+    print("%s fuse=%d: %d tensors, worst rel err %.2e" % (model, fuse, checked, worst))
+
+
+@pytest.mark.parametrize("model", ["shortRange", "full", "backCamera"])
+def test_raw_heads_and_candidates(fdt, model_bytes, sample_images, golden, model):
+    d = get_detector(fdt, model)
+    o = get_oracle(model_bytes, model)
+    for name, img in sample_images.items():
+        h, w = img.shape[:2]
+        d.detectBatchRaw(img, count=1, width=w, height=h)
+        boxes, scores = d.debugRawHeads(1)
+        gb, gs = golden["%s/%s/boxes_f64" % (model, name)], golden["%s/%s/scores_f64" % (model, name)]
+        assert np.abs(boxes[0] - gb).max() <= HEAD_REL_TOL * np.abs(gb).max()
+        assert np.abs(scores[0] - gs).max() <= HEAD_REL_TOL * np.abs(gs).max()
+        cand = d.debugCandidates(0)
+        assert np.array_equal(cand, golden["%s/%s/candidates" % (model, name)])       # index set: bit-exact
+        # margin report: the smallest |logit| must sit far above the numerical noise
+        assert np.abs(gs).min() > 10 * np.abs(scores[0] - gs).max()
+
+
+@pytest.mark.parametrize("model", ["shortRange", "full", "backCamera"])
+def test_detections_match_oracle(fdt, model_bytes, sample_images, golden, model):
+    d = get_detector(fdt, model)
+    o = get_oracle(model_bytes, model)
+    expected = {("shortRange", "landmark-ex1.jpg"): 1, ("shortRange", "iris-detection-ex1.jpg"): 1,
+                ("shortRange", "group-shot-bounding-box-ex1.jpeg"): 0, ("backCamera", "group-shot-bounding-box-ex1.jpeg"): 4,
+                ("backCamera", "landmark-ex1.jpg"): 1, ("full", "landmark-ex1.jpg"): 1}
+    for name, img in sample_images.items():
+        h, w = img.shape[:2]
+        faces = d.detectFacesFromMatBytes(img.tobytes(), width=w, height=h, mode=fdt.FaceDetectionMode.fast)
+        g = golden["%s/%s/dets" % (model, name)]
+        want = [dp.Detection(*row[:5], list(row[5:17]), int(row[17])) for row in g]
+        assert_faces_match(faces, want)
+        if (model, name) in expected:
+            assert len(faces) == expected[(model, name)]               # pinned by the reference's integration tests
+        for f in faces:
+            assert 0.5 <= f.score <= 1.0
+            bb = f.boundingBox
+            assert bb.width == pytest.approx(f.detectionData.boundingBox.w * w) and len(f.landmarks) == 6
+    for k, fr in enumerate(_frames_for(model, sample_images)):
+        h, w = fr.shape[:2]
+        faces = d.detectFacesFromMat(fr, mode=fdt.FaceDetectionMode.fast)
+        assert_faces_match(faces, o.detect(fr))
+
+
+def test_batch_equals_single_and_chunking(fdt, model_bytes):
+    from face_detection_tflite_b200 import synth
+    frames = np.concatenate([synth.face_frames(9, 640, 360, max_side=300), synth.noise_frames(2, 640, 360)])
+    small = get_detector(fdt, "shortRange", mesh=False, maxBatch=4)       # 11 frames -> 3 chunks, both streams
+    big = get_detector(fdt, "shortRange")
+    a = small.detectFacesBatch(frames, count=11, width=640, height=360)
+    b = big.detectFacesBatch(frames, count=11, width=640, height=360)
+    c = [big.detectFacesFromMat(f, mode=fdt.FaceDetectionMode.fast) for f in frames]
+    o = get_oracle(model_bytes, "shortRange", "cv2dnn")
+    assert sum(len(x) for x in a) >= 5
+    for fa, fb, fc, fr in zip(a, b, c, frames):
+        assert len(fa) == len(fb) == len(fc) == len(o.detect(fr))
+        for x, y, z in zip(fa, fb, fc):
+            assert x.detectionData == y.detectionData == z.detectionData          # bitwise identical across batchings
+    # permutation property: results follow their frames
+    perm = np.random.default_rng(0).permutation(11)
+    p = big.detectFacesBatch(frames[perm], count=11, width=640, height=360)
+    for i, j in enumerate(perm):
+        assert [f.detectionData for f in p[i]] == [f.detectionData for f in b[j]]
+    # device-resident input gives the same answer as host input
+    import torch
+    dev = torch.from_numpy(frames).cuda()
+    faces, counts, _ = big.detectBatchRaw(dev.data_ptr(), count=11, width=640, height=360, memKind=1)
+    assert list(counts) == [len(x) for x in b]
+
+
+def test_edge_cases(fdt):
+    d = get_detector(fdt, "shortRange")
+    fast = fdt.FaceDetectionMode.fast
+    for h, w in ((1, 1), (10, 10), (50, 50)):                               # edge_cases_test.dart:44-83 -> []
+        assert d.detectFacesFromMat(np.full((h, w, 3), 127, np.uint8), mode=fast) == []
+    grad = np.tile(np.arange(256, dtype=np.uint8)[None, :, None], (200, 1, 3))
+    assert d.detectFacesFromMat(grad, mode=fast) == []
+    assert isinstance(d.detectFacesFromMat(np.random.default_rng(0).integers(0, 256, (480, 640, 3), dtype=np.uint8), mode=fast), list)
+    for h, w in ((2160, 3840), (50, 2000), (2000, 50)):                      # 4K and extreme aspect ratios do not crash
+        assert isinstance(d.detectFacesFromMat(np.zeros((h, w, 3), np.uint8), mode=fast), list)
+    with pytest.raises(ValueError):                                          # helpers.dart:440-447 length check
+        d.detectFacesFromMatBytes(b"\x00" * 10, width=4, height=4, mode=fast)
+    with pytest.raises(NotImplementedError):
+        d.detectFacesFromMatBytes(b"\x00" * 48, width=4, height=4, mode=fdt.FaceDetectionMode.full)
+    assert d.detectFacesBatch(np.zeros((0,), np.uint8), count=0, width=8, height=8) == []
+    with pytest.raises(ValueError):
+        fdt.FaceDetector.create(fdt.FaceDetectionModel.shortRange, minScore=2.0)
+    t = fdt.FaceDetector.create(fdt.FaceDetectionModel.shortRange, withMesh=False)
+    with pytest.raises(fdt.StateError):
+        t.initialize(fdt.FaceDetectionModel.shortRange)                      # double initialise (face_detector.dart:315-317)
+    with pytest.raises(fdt.StateError):
+        t.detectFacesFromMatBytes(b"\x00" * 48, width=4, height=4, mode=fdt.FaceDetectionMode.standard)   # no mesh model
+    t.dispose()
+    with pytest.raises(fdt.StateError):
+        t.detectFacesFromMatBytes(b"\x00" * 48, width=4, height=4, mode=fast)
+
+
+def test_gates(fdt, sample_images):
+    img = sample_images["group-shot-bounding-box-ex1.jpeg"]
+    h, w = img.shape[:2]
+    base = get_detector(fdt, "backCamera").detectFacesFromMat(img, mode=fdt.FaceDetectionMode.fast)
+    assert len(base) == 4
+    thr = sorted(f.score for f in base)[1] + 1e-9
+    g = get_detector(fdt, "backCamera", mesh=False, minScore=thr).detectFacesFromMat(img, mode=fdt.FaceDetectionMode.fast)
+    assert [f.detectionData for f in g] == [f.detectionData for f in base if f.score >= thr]
+    widths = sorted(f.detectionData.boundingBox.w for f in base)
+    g = get_detector(fdt, "backCamera", mesh=False, minFaceSize=float(widths[2])).detectFacesFromMat(img, mode=fdt.FaceDetectionMode.fast)
+    assert len(g) == 2
+
+
+# ---- mesh stage (C4) -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("model", ["backCamera", "shortRange"])
+def test_standard_mode_mesh(fdt, model_bytes, sample_images, golden, model):
+    d = get_detector(fdt, model)
+    o = get_oracle(model_bytes, model)
+    std = fdt.FaceDetectionMode.standard
+    for name, img in sample_images.items():
+        h, w = img.shape[:2]
+        faces = d.detectFacesFromMat(img, mode=std)
+        want = o.detect_faces(img, "standard")
+        assert len(faces) == len(want) == len(golden["%s/%s/mesh_scores" % (model, name)])
+        n_all = len(o.detect(img))
+        crops, raw, flag = d.debugMeshStage(max(n_all, 1))
+        want_all = OraclePipeline.detect_faces(_NoGate(o), img, "standard") if n_all else []
+        for i, wf in enumerate(want_all):
+            diff = np.abs(crops[i].astype(int) - wf.crop.astype(int))
+            assert (diff > 0).mean() <= 1e-3 and diff.max() <= 2            # warpAffine: bit-exact up to f64 libm ulps in the ROI
+            assert np.abs(raw[i] - wf.mesh_raw).max() <= 2e-3 * np.abs(wf.mesh_raw).max()
+        if want_all and "%s/%s/crop0_cv2" % (model, name) in golden:
+            assert (crops[0] != golden["%s/%s/crop0_cv2" % (model, name)]).mean() <= 1e-3   # the real cv2.warpAffine
+        for g, wf in zip(faces, want):
+            assert g.mesh is not None and len(g.mesh) == 468                  # face_detection_integration_test.dart:124-135
+            assert abs(g.meshScore - wf.mesh_score) <= 1e-3 and 0.0 <= g.meshScore <= 1.0
+            size = wf.align[3]
+            assert np.abs(g.mesh.packed - wf.mesh_px).max() <= COORD_TOL * size * 2   # <= 1e-3 normalised (of the ROI side) x2 for crop ulps
+    # batched standard mode == per-frame standard mode
+    img = sample_images["group-shot-bounding-box-ex1.jpeg"]
+    h, w = img.shape[:2]
+    two = d.detectFacesBatch(np.stack([img, img[:, ::-1].copy()]), count=2, width=w, height=h, mode=std)
+    one = d.detectFacesFromMat(img, mode=std)
+    assert [f.detectionData for f in two[0]] == [f.detectionData for f in one]
+    assert all(np.array_equal(a.mesh.packed, b.mesh.packed) for a, b in zip(two[0], one))
+
+
+class _NoGate:
+    """The oracle pipeline with the presence gate off, to compare every crop the GPU produced."""
+    def __init__(self, o):
+        self.__dict__.update(o.__dict__)
+        self.min_presence = 0.0
+    detect = OraclePipeline.detect
+    preprocess = OraclePipeline.preprocess
+    raw_heads = OraclePipeline.raw_heads
+
+
+def test_mesh_layers(fdt, model_bytes, sample_images):
+    """Every materialised tensor of the face_landmark graph (fuse levels 0 and 2) vs the fp64 oracle."""
+    img = sample_images["landmark-ex1.jpg"]
+    h, w = img.shape[:2]
+    o = get_oracle(model_bytes, "backCamera")
+    crop = OraclePipeline.detect_faces(_NoGate(o), img, "standard")[0].crop
+    ref = o.mesh.exe.run(co.normalize_bgr_u8(crop)[None], taps="all")
+    for fuse in (0, 2):
+        d = get_detector(fdt, "backCamera", fuse=fuse)
+        d.detectFacesFromMat(img, mode=fdt.FaceDetectionMode.standard)
+        crops, _, _ = d.debugMeshStage(1)
+        if not np.array_equal(crops[0], crop):
+            ref_f = o.mesh.exe.run(co.normalize_bgr_u8(crops[0])[None], taps="all")
+        else:
+            ref_f = ref
+        n = 0
+        for tf_idx, want in ref_f.items():
+            try:
+                got = d.debugTensor(1, tf_idx, 1)
+            except ValueError:
+                continue
+            want = want.reshape(got.shape)
+            err = np.abs(got - want).max() / max(np.abs(want).max(), 1e-6)
+            assert err <= HEAD_REL_TOL, "mesh tensor %d: %.3e (fuse %d)" % (tf_idx, err, fuse)
+            n += 1
+        assert n >= 10
+
+
+# ---- full benchmark sizes: size-independent properties -------------------------------------------------
+def test_full_size_c2_properties(fdt, model_bytes):
+    """BASELINE config 2 at full size (4096 x 1280x720): determinism, tiling/periodicity, and agreement
+    of a sampled subset with the oracle."""
+    import torch
+    from face_detection_tflite_b200 import synth
+    d = get_detector(fdt, "shortRange")
+    period = 64
+    base = np.concatenate([synth.face_frames(period - 8, 1280, 720), synth.noise_frames(8, 1280, 720)])
+    dev = torch.from_numpy(base).cuda().repeat(4096 // period, 1, 1, 1).contiguous()
+    f1, c1, _ = d.detectBatchRaw(dev.data_ptr(), count=4096, width=1280, height=720, memKind=1)
+    c1 = c1.copy()
+    a1 = np.frombuffer(f1, np.uint8).copy()
+    f2, c2, _ = d.detectBatchRaw(dev.data_ptr(), count=4096, width=1280, height=720, memKind=1)
+    assert np.array_equal(c1, c2)
+    rec = np.frombuffer(f2, np.uint8).reshape(4096, -1)
+    a1 = a1.reshape(4096, -1)
+    for b in range(4096):                                                     # determinism (valid slots only)
+        n = c1[b] * C.sizeof(type(f1[0]))
+        assert np.array_equal(a1[b, :n], rec[b, :n])
+    assert np.array_equal(c1.reshape(-1, period), np.tile(c1[:period], (4096 // period, 1)))   # periodic input -> periodic output
+    assert c1[period - 8:period].sum() == 0                                   # noise frames: no faces
+    assert c1[:period].sum() >= 40
+    o = get_oracle(model_bytes, "shortRange", "cv2dnn")
+    for k in (1, 7, 18, 33, 49):
+        assert c1[k] == len(o.detect(base[k]))
