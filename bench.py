@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py — BlazeFace detect throughput (preprocess + infer + decode + NMS), BASELINE.json configs[1]:
+short-range BlazeFace, 4096 synthetic 1280x720 BGR frames per GPU, on N B200s (weak scaling; frames
+are independent so the batch shards across ranks with no collective on the data path).
+
+  python bench.py --gpus 1 --steps 5 --warmup 3
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...   # the CPU pipeline (oracle port: cv2 + cv2.dnn) on the host cores
+
+One JSON line on stdout (rank 0).  `value` = device-resident throughput (CUDA events on the library's
+streams, max over ranks); `e2e` = the same metric through fdt_detect_batch with pinned HOST frames,
+H2D + D2H inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "images/sec BlazeFace detect (pre+infer+NMS)"
+WIDTH, HEIGHT = 1280, 720
+PERIOD = 64            # unique synthetic frames; the batch tiles them
+MODEL = "shortRange"
+MODEL_FILE = "face_detection_short_range.tflite"
+
+
+def synth_base():
+    from face_detection_tflite_b200 import synth
+    return np.concatenate([synth.face_frames(PERIOD - 8, WIDTH, HEIGHT), synth.noise_frames(8, WIDTH, HEIGHT)])
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons, pw = [], None, set(), []
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8 or not f[0].isdigit() or int(f[0]) != self.idx:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2]); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s, p in zip(sm, pw) if p > 200] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_reference(steps: int, warmup: int, sample: int, quiet=False):
+    """The reference's CPU path, as the oracle port, on all host cores."""
+    from oracle.cpu_bench import CpuPipeline
+    det = (ROOT / "assets/models" / MODEL_FILE).read_bytes()
+    cp = CpuPipeline(det, MODEL, "bench", "synth_base")
+    for _ in range(warmup):
+        cp.run(min(sample, 4 * cp.workers))
+    times = []
+    for _ in range(steps):
+        t, _faces = cp.run(sample)
+        times.append(t)
+    cp.close()
+    total = sum(times)
+    return {"value": sample * steps / total, "ms_per_step": 1e3 * total / steps, "cores": cp.workers,
+            "sample": "%d of the same synthetic 1280x720 frames per step, %d steps, one cv2.dnn fp32 worker per core "
+                      "(stand-in for TFLite/XNNPACK)" % (sample, steps)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="frames per GPU per step")
+    ap.add_argument("--chunk", type=int, default=0, help="frames per internal chunk (0 = library default)")
+    ap.add_argument("--cpu-sample", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    config = {"workload": "configs[1]: short-range BlazeFace 128x128 (896 anchors), batch %d synthetic 1280x720 BGR frames per GPU, "
+                          "letterbox->detect->weighted NMS" % args.batch,
+              "frames_per_gpu": args.batch, "frame": "1280x720x3 u8 BGR", "sharding": "frames split across ranks, no collective",
+              "l2": "inputs_exceed_l2 (%.1f GB of frames per step)" % (args.batch * WIDTH * HEIGHT * 3 / 1e9)}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample = args.cpu_sample or 2048
+        r = cpu_reference(args.steps, max(args.warmup, 1), sample)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "images/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from face_detection_tflite_b200 import _ffi, build, sharding
+    import face_detection_tflite_b200 as fdt
+
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    torch.cuda.set_device(local)
+    lib = _ffi.load()
+    det = fdt.FaceDetector.create(fdt.FaceDetectionModel.shortRange, withMesh=False, device=local, maxBatch=args.chunk)
+    h = det._h
+    B = args.batch
+    frame_bytes = WIDTH * HEIGHT * 3
+    base = synth_base()
+    reps = (B + PERIOD - 1) // PERIOD
+    dev = torch.from_numpy(base).cuda().repeat(reps, 1, 1, 1)[:B].contiguous()
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    pf, pc = C.c_void_p(), C.c_void_p()
+
+    def step_device():
+        rc = lib.fdt_detect_batch_device(h, dev.data_ptr(), B, WIDTH, HEIGHT, WIDTH * 3, 16, 0, C.byref(pf), C.byref(pc))
+        if rc != 0:
+            raise RuntimeError(lib.fdt_last_error(h).decode())
+
+    # ---- device-resident throughput -----------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    lib.fdt_synchronize(h)
+    launches_per_step = int(lib.fdt_last_launch_count(h))
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ms = C.c_float()
+    lib.fdt_timer_begin(h)
+    for _ in range(args.steps):
+        step_device()
+    lib.fdt_timer_end(h, C.byref(ms))
+    barrier()
+    clocks = sampler.stop()
+    t_ms = sharding.max_over_ranks(float(ms.value), world, torch.device("cuda", local))
+    value = world * B * args.steps / (t_ms / 1e3)
+    # face count of the last step (also proves the work was done)
+    host_counts = np.empty(B, np.int32)
+    if lib.fdt_copy_to_host(h, host_counts.ctypes.data, pc.value, B * 4) != 0:
+        raise RuntimeError(lib.fdt_last_error(h).decode())
+    faces_found = int(host_counts.sum())
+
+    # ---- end to end: pinned host frames -> fdt_detect_batch -> host results ------------------------------
+    e2e = None
+    if not args.no_e2e:
+        pin = C.c_void_p()
+        if lib.fdt_alloc_pinned(B * frame_bytes, C.byref(pin)) != 0:
+            raise RuntimeError("pinned allocation failed")
+        harr = np.ctypeslib.as_array((C.c_uint8 * (B * frame_bytes)).from_address(pin.value)).reshape(B, HEIGHT, WIDTH, 3)
+        for r in range(reps):
+            n = min(PERIOD, B - r * PERIOD)
+            harr[r * PERIOD:r * PERIOD + n] = base[:n]
+        mf = det._max_faces
+        out_faces = C.c_void_p(); out_counts = C.c_void_p()
+        lib.fdt_alloc_pinned(B * mf * C.sizeof(_ffi.FdtFace), C.byref(out_faces))
+        lib.fdt_alloc_pinned(B * 4, C.byref(out_counts))
+        fptr = C.cast(out_faces, C.POINTER(_ffi.FdtFace)); cptr = C.cast(out_counts, _ffi.i32p)
+
+        def step_e2e():
+            rc = lib.fdt_detect_batch(h, pin.value, B, WIDTH, HEIGHT, WIDTH * 3, 16, 0, 0, fptr, cptr, None)
+            if rc != 0:
+                raise RuntimeError(lib.fdt_last_error(h).decode())
+
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        e_steps = max(2, min(args.steps, 5))
+        lib.fdt_timer_begin(h)
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            step_e2e()
+        wall = (time.perf_counter() - t0) * 1e3
+        lib.fdt_timer_end(h, C.byref(ms))
+        barrier()
+        e_ms = sharding.max_over_ranks(max(float(ms.value), wall), world, torch.device("cuda", local))
+        e2e_counts = np.ctypeslib.as_array(cptr, (B,)).copy()
+        assert int(e2e_counts.sum()) == faces_found, "host and device paths disagree"
+        e2e = {"value": world * B * e_steps / (e_ms / 1e3), "unit": "images/s", "h2d_bytes_per_step": B * frame_bytes,
+               "d2h_bytes_per_step": B * mf * C.sizeof(_ffi.FdtFace) + B * 4, "steps": e_steps,
+               "note": "fdt_detect_batch on pinned host frames; PCIe-bound"}
+        lib.fdt_free_pinned(pin); lib.fdt_free_pinned(out_faces); lib.fdt_free_pinned(out_counts)
+
+    # ---- per-kernel timing + roofline of the dominant kernel (rank 0) ----------------------------------------
+    roofline, kernels = None, None
+    if rank == 0:
+        n = int(det.maxBatch)
+        cap = 256
+        arr = (C.c_float * cap)()
+        nl = C.c_int32()
+        rc = lib.fdt_profile_chunk(h, dev.data_ptr(), n, WIDTH, HEIGHT, WIDTH * 3, 16, 20, arr, cap, C.byref(nl))
+        if rc == 0:
+            kernels = []
+            kn, tn = C.create_string_buffer(64), C.create_string_buffer(128)
+            macs, byt = C.c_double(), C.c_double()
+            for i in range(nl.value):
+                lib.fdt_get_step_info(h, i, kn, tn, 64, C.byref(macs), C.byref(byt))
+                b = byt.value
+                if i == 0:
+                    b = 128 * 72 * 4 * 3 + 128 * 128 * 3   # unique source bytes of INTER_LINEAR taps + u8 output
+                kernels.append({"launch": i, "kernel": kn.value.decode(), "tensor": tn.value.decode(), "ms": arr[i],
+                                "macs_per_image": macs.value, "bytes_per_image": b,
+                                "gbs": b * n / (arr[i] * 1e-3) / 1e9 if arr[i] > 0 else None,
+                                "tflops": 2 * macs.value * n / (arr[i] * 1e-3) / 1e12 if arr[i] > 0 else None})
+            top = max(kernels, key=lambda k: k["ms"])
+            peak, how = peaks()
+            roofline = {"kernel": "%s[%s]" % (top["kernel"], top["tensor"]), "bound": "hbm", "achieved": top["gbs"], "peak": peak,
+                        "unit": "GB/s", "frac": top["gbs"] / peak, "traffic": None, "peak_source": how,
+                        "share_of_step": top["ms"] / sum(k["ms"] for k in kernels), "images_per_launch": n,
+                        "fp32_tflops": top["tflops"],
+                        "conv_stack_tflops": 2 * sum(k["macs_per_image"] for k in kernels) * n / (sum(k["ms"] for k in kernels) * 1e-3) / 1e12}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        det.dispose()
+        r = cpu_reference(1, 1, args.cpu_sample or 1024)
+        cpu = {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
+                "gpu_launches": launches_per_step * args.steps, "faces_per_step": faces_found,
+                "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -52,6 +52,7 @@ SIGNATURES = {
     "fdt_alloc_device": (C.c_int32, [P, C.c_size_t, C.POINTER(P)]),
     "fdt_free_device": (C.c_int32, [P, P]),
     "fdt_copy_to_device": (C.c_int32, [P, P, P, C.c_size_t]),
+    "fdt_copy_to_host": (C.c_int32, [P, P, P, C.c_size_t]),
     "fdt_debug_get_letterboxed": (C.c_int32, [P, C.c_int32, P]),
     "fdt_debug_get_input_tensor": (C.c_int32, [P, C.c_int32, P]),
     "fdt_debug_get_raw_heads": (C.c_int32, [P, C.c_int32, P, P]),
@@ -63,6 +64,8 @@ SIGNATURES = {
     "fdt_get_stage_ms": (C.c_int32, [P, C.c_int32, f32p, i32p]),
     "fdt_timer_begin": (C.c_int32, [P]),
     "fdt_timer_end": (C.c_int32, [P, f32p]),
+    "fdt_profile_chunk": (C.c_int32, [P, P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, f32p, C.c_int32, i32p]),
+    "fdt_get_step_info": (C.c_int32, [P, C.c_int32, C.c_char_p, C.c_char_p, C.c_int32, f64p, f64p]),
     "fdt_host_anchors": (C.c_int32, [C.c_int32, P, C.c_int32]),
     "fdt_host_plan_describe": (C.c_int32, [C.c_char_p, C.c_size_t, C.c_int32, C.c_char_p, C.c_size_t]),
     "fdt_host_resize_taps": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, P, P, P, P]),

@@ -62,10 +62,11 @@ static int cta_cap(size_t smem, int threads) {
   return 148 * per_sm;
 }
 
-int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t s) const {
+int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t s, cudaEvent_t* evs) const {
   int launches = 0;
   const float* blob = d_blob_;
   for (const PStep& st : plan_.steps) {
+    if (evs) cudaEventRecord(evs[launches], s);
     TV out = view(ctx, st.out);
     switch (st.kind) {
       case kStepNormalize:
@@ -156,6 +157,7 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
     }
     ++launches;
   }
+  if (evs) cudaEventRecord(evs[launches], s);
   return launches;
 }
 

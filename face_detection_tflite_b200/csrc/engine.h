@@ -26,7 +26,8 @@ class Engine {
   void free_ctx(EngineCtx* ctx) const;
   // Runs the plan on B <= ctx.cap images whose u8 BGR input lives at `in_u8` ([B][H][W][3]).
   // Returns the number of kernel launches.
-  int run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t s) const;
+  // `evs` (optional): steps()+1 events, evs[i] recorded before step i and evs[steps()] after the last.
+  int run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t s, cudaEvent_t* evs = nullptr) const;
   TV view(const EngineCtx& ctx, int ptensor) const;
 
   const Plan& plan() const { return plan_; }

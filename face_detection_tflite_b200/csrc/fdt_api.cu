@@ -607,6 +607,13 @@ int32_t fdt_copy_to_device(fdt_handle* h, void* dst, const void* src, size_t nby
   return cuda_ok(h, cudaMemcpy(dst, src, nbytes, cudaMemcpyHostToDevice), "cudaMemcpy") ? FDT_OK : FDT_ERR_CUDA;
 }
 
+int32_t fdt_copy_to_host(fdt_handle* h, void* dst, const void* src, size_t nbytes) {
+  if (!h || !h->ready) return fail(h, FDT_ERR_NOT_READY, "detector is not initialised");
+  cudaSetDevice(h->cfg.device);
+  for (int i = 0; i < kStreams; ++i) cudaStreamSynchronize(h->streams[i]);
+  return cuda_ok(h, cudaMemcpy(dst, src, nbytes, cudaMemcpyDeviceToHost), "cudaMemcpy") ? FDT_OK : FDT_ERR_CUDA;
+}
+
 // ---- parity taps ------------------------------------------------------------------------------
 int32_t fdt_debug_get_letterboxed(fdt_handle* h, int32_t n, uint8_t* out) {
   if (!h || !h->ready) return fail(h, FDT_ERR_NOT_READY, "detector is not initialised");
@@ -750,6 +757,96 @@ int32_t fdt_timer_end(fdt_handle* h, float* ms) {
   float t = 0;
   cudaEventElapsedTime(&t, h->tev[0], h->tev[1]);
   if (ms) *ms = t;
+  return FDT_OK;
+}
+
+int32_t fdt_profile_chunk(fdt_handle* h, const uint8_t* d_frames, int32_t n, int32_t width, int32_t height,
+                          int32_t row_stride, int32_t mat_type, int32_t repeats, float* out_ms, int32_t capacity,
+                          int32_t* out_launches) {
+  if (!h || !h->ready) return fail(h, FDT_ERR_NOT_READY, "detector is not initialised");
+  std::lock_guard<std::mutex> g(h->mu);
+  int channels = channels_of(mat_type);
+  const int S = (int)h->det.plan().steps.size();
+  if (out_launches) *out_launches = S + 2;
+  if (!d_frames || n <= 0 || n > h->chunk || channels == 0 || row_stride < width * channels || repeats <= 0)
+    return fail(h, FDT_ERR_BAD_ARG, "bad profile arguments");
+  if (!out_ms || capacity < S + 2) return fail(h, FDT_ERR_SIZE_MISMATCH, "out_ms too small");
+  cudaSetDevice(h->cfg.device);
+  if (!ensure_results(h, n)) return FDT_ERR_CUDA;
+  const LbTables* tb = get_tables(h, width, height);
+  if (!tb) return fail(h, FDT_ERR_CUDA, "letterbox table upload failed");
+  std::vector<cudaEvent_t> ev(S + 3);
+  for (auto& e : ev) cudaEventCreate(&e);
+  std::vector<double> acc(S + 2, 0.0);
+  cudaStream_t s = h->streams[0];
+  const int S_w = h->det.in_w(), S_h = h->det.in_h();
+  for (int r = 0; r < repeats; ++r) {
+    LetterboxP lb;
+    lb.frames = d_frames; lb.frame_stride = (long long)height * row_stride; lb.row_stride = row_stride; lb.channels = channels;
+    lb.src_w = width; lb.src_h = height; lb.out = h->d_lb[0]; lb.dst_w = S_w; lb.dst_h = S_h;
+    lb.new_w = tb->lp.new_w; lb.new_h = tb->lp.new_h; lb.pad_top = tb->lp.pad_top; lb.pad_left = tb->lp.pad_left;
+    lb.x0 = tb->x0; lb.x1 = tb->x1; lb.ax0 = tb->ax0; lb.ax1 = tb->ax1;
+    lb.y0 = tb->y0; lb.y1 = tb->y1; lb.by0 = tb->by0; lb.by1 = tb->by1;
+    lb.identity = tb->identity ? 1 : 0;
+    cudaEventRecord(ev[0], s);
+    launch_letterbox(lb, n, s);
+    h->det.run(h->det_ctx[0], h->d_lb[0], n, s, ev.data() + 1);
+    const Plan& dp = h->det.plan();
+    DecodeP d;
+    d.boxes = h->det_ctx[0].outputs[0]; d.boxes_istride = dp.out_elems[0];
+    d.scores = h->det_ctx[0].outputs[1]; d.scores_istride = dp.out_elems[1];
+    d.anchors = h->d_anchors; d.N = h->num_anchors; d.input_h = S_h;
+    d.raw_thresh = std::log(kMinScore / (1.0 - kMinScore));
+    d.score_thresh = kMinScore; d.iou_thresh = kMinSuppression;
+    d.pad_t = (double)tb->lp.pad_top / S_h; d.pad_b = (double)tb->lp.pad_bottom / S_h;
+    d.pad_l = (double)tb->lp.pad_left / S_w; d.pad_r = (double)tb->lp.pad_right / S_w;
+    d.min_score = h->cfg.min_score; d.min_face_size = h->cfg.min_face_size;
+    d.img_w = width; d.img_h = height; d.max_faces = h->max_faces;
+    d.faces = h->d_faces; d.counts = h->d_counts;
+    d.cand_idx = nullptr; d.cand_cap = 0; d.cand_n = nullptr;
+    launch_decode_nms(d, n, s);
+    cudaEventRecord(ev[S + 2], s);
+    if (!cuda_ok(h, cudaStreamSynchronize(s), "profile")) { for (auto& e : ev) cudaEventDestroy(e); return FDT_ERR_CUDA; }
+    for (int i = 0; i < S + 2; ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      acc[i] += ms;
+    }
+  }
+  for (int i = 0; i < S + 2; ++i) out_ms[i] = (float)(acc[i] / repeats);
+  for (auto& e : ev) cudaEventDestroy(e);
+  return FDT_OK;
+}
+
+int32_t fdt_get_step_info(fdt_handle* h, int32_t launch, char* kernel, char* tensor, int32_t str_cap, double* macs_per_image,
+                          double* bytes_per_image) {
+  if (!h || !h->ready) return fail(h, FDT_ERR_NOT_READY, "detector is not initialised");
+  const Plan& p = h->det.plan();
+  const int S = (int)p.steps.size();
+  if (launch < 0 || launch > S + 1) return fail(h, FDT_ERR_BAD_ARG, "launch index out of range");
+  static const char* kn[] = {"k_normalize", "k_naive_conv", "k_gemm_conv", "k_dwpw", "k_add", "k_act", "k_padc", "k_maxpool", "k_resize_bilinear"};
+  std::string kname, tname;
+  double macs = 0, bytes = 0;
+  const int S_w = h->det.in_w(), S_h = h->det.in_h();
+  if (launch == 0) {
+    kname = "k_letterbox"; tname = "letterboxed_u8";
+    bytes = 0;  // depends on the frame size: 4 taps x 3 B per content pixel read + S*S*3 written (filled by the caller)
+  } else if (launch == S + 1) {
+    kname = "k_decode_nms"; tname = "faces";
+    bytes = (double)h->num_anchors * 17 * 4;
+  } else {
+    const PStep& st = p.steps[launch - 1];
+    kname = kn[st.kind]; tname = st.name; macs = st.macs;
+    const PTensor& o = p.tensors[st.out];
+    bytes = (double)o.H * o.W * o.C * 4;
+    if (st.in_u8) bytes += (double)S_w * S_h * 3;
+    else if (st.in >= 0) { const PTensor& i = p.tensors[st.in]; bytes += (double)i.H * i.W * i.C * 4; }
+    if (st.in2 >= 0 && st.in2 != st.in) { const PTensor& r = p.tensors[st.in2]; bytes += (double)r.H * r.W * r.C * 4; }
+  }
+  if (kernel && str_cap > 0) { std::snprintf(kernel, str_cap, "%s", kname.c_str()); }
+  if (tensor && str_cap > 0) { std::snprintf(tensor, str_cap, "%s", tname.c_str()); }
+  if (macs_per_image) *macs_per_image = macs;
+  if (bytes_per_image) *bytes_per_image = bytes;
   return FDT_OK;
 }
 

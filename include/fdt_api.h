@@ -160,6 +160,7 @@ FDT_EXPORT int32_t fdt_free_pinned(void* p);
 FDT_EXPORT int32_t fdt_alloc_device(fdt_handle* h, size_t nbytes, void** out);
 FDT_EXPORT int32_t fdt_free_device(fdt_handle* h, void* p);
 FDT_EXPORT int32_t fdt_copy_to_device(fdt_handle* h, void* dst, const void* src, size_t nbytes);
+FDT_EXPORT int32_t fdt_copy_to_host(fdt_handle* h, void* dst, const void* src, size_t nbytes);
 
 /* ---- parity taps (test / debug only; valid for the frames of the LAST detect call, first chunk) ----
  * fdt_debug_get_letterboxed : u8 [n, S, S, 3] BGR after resize + copyMakeBorder
@@ -194,6 +195,17 @@ FDT_EXPORT int32_t fdt_get_stage_ms(fdt_handle* h, int32_t stage, float* ms, int
  * number of detect calls; *ms is measured with CUDA events recorded on the library's own streams. */
 FDT_EXPORT int32_t fdt_timer_begin(fdt_handle* h);
 FDT_EXPORT int32_t fdt_timer_end(fdt_handle* h, float* ms);
+
+/* Per-kernel device timing of the detector plan (bench.py roofline): runs `repeats` passes of one
+ * chunk (n <= max_batch frames already in device memory) on one stream with a CUDA event between
+ * consecutive kernels; out_ms[i] = mean duration of launch i, i = 0 letterbox, 1..S conv-stack
+ * steps, S+1 decode+NMS.  fdt_get_step_info describes launch i: kernel name, tensor name, MACs and
+ * algorithmic bytes (activation read + write, fp32) per image. */
+FDT_EXPORT int32_t fdt_profile_chunk(fdt_handle* h, const uint8_t* d_frames, int32_t n, int32_t width,
+                                     int32_t height, int32_t row_stride, int32_t mat_type, int32_t repeats,
+                                     float* out_ms, int32_t capacity, int32_t* out_launches);
+FDT_EXPORT int32_t fdt_get_step_info(fdt_handle* h, int32_t launch, char* kernel, char* tensor, int32_t str_cap,
+                                     double* macs_per_image, double* bytes_per_image);
 
 /* ---- host-only helpers (no CUDA device needed; used by the CPU test-suite and by bindings) ----
  * fdt_host_anchors        : generateAnchors for a FaceDetectionModel; returns the anchor count

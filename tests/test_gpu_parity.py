@@ -118,7 +118,7 @@ def _frames_for(model, sample_images, n_synth=3):
 @pytest.mark.parametrize("model,fuse", [("shortRange", 0), ("shortRange", 2), ("full", 0), ("full", 2), ("backCamera", 2)])
 def test_every_materialised_tensor(fdt, model_bytes, sample_images, model, fuse):
     """Layer-by-layer parity: every activation the plan materialises vs the fp64 oracle."""
-    d = get_detector(fdt, model, fuse=fuse, mesh=False)
+    d = get_detector(fdt, model, fuse=fuse, mesh=False, maxBatch=4)
     o = get_oracle(model_bytes, model)
     img = sample_images["landmark-ex1.jpg"]
     h, w = img.shape[:2]
@@ -303,7 +303,7 @@ def test_mesh_layers(fdt, model_bytes, sample_images):
     crop = OraclePipeline.detect_faces(_NoGate(o), img, "standard")[0].crop
     ref = o.mesh.exe.run(co.normalize_bgr_u8(crop)[None], taps="all")
     for fuse in (0, 2):
-        d = get_detector(fdt, "backCamera", fuse=fuse)
+        d = get_detector(fdt, "backCamera", fuse=fuse, maxBatch=4)
         d.detectFacesFromMat(img, mode=fdt.FaceDetectionMode.standard)
         crops, _, _ = d.debugMeshStage(1)
         if not np.array_equal(crops[0], crop):

@@ -59,7 +59,7 @@ for model, f in FILES.items():
     for fuse in (0, 2, 1):
         section("%s fuse=%d" % (model, fuse))
         try:
-            d = fdt.FaceDetector.create(fdt.FaceDetectionModel[model], fuseLevel=fuse, withMesh=True)
+            d = fdt.FaceDetector.create(fdt.FaceDetectionModel[model], fuseLevel=fuse, withMesh=True, maxBatch=(256 if fuse == 1 else 4))
             faces, counts, _ = d.detectBatchRaw(frames, count=2, width=w, height=h)
             lb = d.debugLetterboxed(2)
             want_lb = co.letterbox_u8(frames[0], o.in_w, o.in_h)[0]
