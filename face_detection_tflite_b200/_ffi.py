@@ -60,6 +60,7 @@ SIGNATURES = {
     "fdt_debug_get_tensor": (C.c_int32, [P, C.c_int32, C.c_int32, C.c_int32, P, C.c_size_t, i32p]),
     "fdt_debug_get_mesh_stage": (C.c_int32, [P, C.c_int32, P, P, P, i32p]),
     "fdt_last_launch_count": (C.c_int64, [P]),
+    "fdt_last_h2d_bytes": (C.c_int64, [P]),
     "fdt_set_stage_timing": (C.c_int32, [P, C.c_int32]),
     "fdt_get_stage_ms": (C.c_int32, [P, C.c_int32, f32p, i32p]),
     "fdt_timer_begin": (C.c_int32, [P]),

@@ -76,6 +76,12 @@ struct LbTables {
   int *x0 = nullptr, *x1 = nullptr, *y0 = nullptr, *y1 = nullptr;
   short *ax0 = nullptr, *ax1 = nullptr, *by0 = nullptr, *by1 = nullptr;
   bool identity = false;
+  // Sparse upload (host frames, fast mode): INTER_LINEAR only reads the rows y0/y1 name.  When those
+  // rows form a periodic pattern (`run` consecutive rows every `period`, e.g. rows 10y+4,10y+5 for
+  // 720 -> 72) a single strided DMA copies just them; y0c/y1c index the compacted frame.
+  bool sparse = false;
+  int r0 = 0, run = 0, period = 0, rows_c = 0;
+  int *y0c = nullptr, *y1c = nullptr;
 };
 
 template <typename T> T* dev_upload(const std::vector<T>& v) {
@@ -123,6 +129,7 @@ struct fdt_handle {
   std::mutex mu;
   std::string err;
   long long launches = 0;
+  long long h2d_bytes = 0;
   int last_first_chunk = 0;         // images of the last call's first chunk (debug taps)
   bool stage_timing = false;
   float stage_ms[kNumStages] = {};
@@ -169,6 +176,29 @@ const LbTables* get_tables(fdt_handle* h, int w, int hh) {
   t.x0 = dev_upload(x0); t.x1 = dev_upload(x1); t.ax0 = dev_upload(ax0); t.ax1 = dev_upload(ax1);
   t.y0 = dev_upload(y0); t.y1 = dev_upload(y1); t.by0 = dev_upload(by0); t.by1 = dev_upload(by1);
   if (!t.x0 || !t.x1 || !t.ax0 || !t.ax1 || !t.y0 || !t.y1 || !t.by0 || !t.by1) return nullptr;
+  if (!t.identity) {
+    std::vector<char> need(hh, 0);
+    for (int i = 0; i < t.lp.new_h; ++i) { need[y0[i]] = 1; need[y1[i]] = 1; }
+    int first = 0;
+    while (first < hh && !need[first]) ++first;
+    int run = 0;
+    while (first + run < hh && need[first + run]) ++run;
+    int next = first + run;
+    while (next < hh && !need[next]) ++next;
+    int period = next < hh ? next - first : 0;
+    bool ok = period > run && hh % period == 0 && first + run <= period;
+    for (int r = 0; ok && r < hh; ++r) {
+      int ph = r % period;
+      ok = (need[r] != 0) == (ph >= first && ph < first + run);
+    }
+    if (ok && run * 2 <= period) {
+      std::vector<int> y0c(t.lp.new_h), y1c(t.lp.new_h);
+      auto compact = [&](int r) { return (r / period) * run + (r % period - first); };
+      for (int i = 0; i < t.lp.new_h; ++i) { y0c[i] = compact(y0[i]); y1c[i] = compact(y1[i]); }
+      t.y0c = dev_upload(y0c); t.y1c = dev_upload(y1c);
+      if (t.y0c && t.y1c) { t.sparse = true; t.r0 = first; t.run = run; t.period = period; t.rows_c = hh / period * run; }
+    }
+  }
   h->tables.push_back(t);
   return &h->tables.back();
 }
@@ -292,6 +322,7 @@ int detect_impl(fdt_handle* h, const uint8_t* frames, int batch, int w, int hh, 
   if (!keep_on_device && (!out_faces || !out_counts)) return fail(h, FDT_ERR_BAD_ARG, "null output buffers");
   cudaSetDevice(h->cfg.device);
   h->launches = 0;
+  h->h2d_bytes = 0;
   for (int i = 0; i < kNumStages; ++i) { h->stage_ms[i] = 0; h->stage_launches[i] = 0; }
   if (batch == 0) return FDT_OK;
   if (!ensure_results(h, batch)) return FDT_ERR_CUDA;
@@ -306,6 +337,8 @@ int detect_impl(fdt_handle* h, const uint8_t* frames, int batch, int w, int hh, 
     const int si = (mode == FDT_MODE_STANDARD) ? 0 : c % kStreams;
     cudaStream_t s = h->streams[si];
     const uint8_t* d_fr;
+    const bool sparse = mem_kind == FDT_MEM_HOST && mode == FDT_MODE_FAST && tb->sparse;
+    long long dev_frame_stride = frame_stride;
     if (mem_kind == FDT_MEM_HOST) {
       size_t need = (size_t)h->chunk * frame_stride;
       if (h->d_frames_cap[si] < need) {
@@ -315,7 +348,18 @@ int detect_impl(fdt_handle* h, const uint8_t* frames, int batch, int w, int hh, 
         if (!cuda_ok(h, cudaMalloc(&h->d_frames[si], need), "cudaMalloc(frame staging)")) return FDT_ERR_CUDA;
         h->d_frames_cap[si] = need;
       }
-      cudaMemcpyAsync(h->d_frames[si], frames + (size_t)off * frame_stride, (size_t)n * frame_stride, cudaMemcpyHostToDevice, s);
+      const uint8_t* src = frames + (size_t)off * frame_stride;
+      if (sparse) {
+        // one strided DMA: `run` rows out of every `period`, for all n frames (frames are contiguous)
+        size_t width_b = (size_t)tb->run * row_stride;
+        cudaMemcpy2DAsync(h->d_frames[si], width_b, src + (size_t)tb->r0 * row_stride, (size_t)tb->period * row_stride,
+                          width_b, (size_t)n * (hh / tb->period), cudaMemcpyHostToDevice, s);
+        dev_frame_stride = (long long)tb->rows_c * row_stride;
+        h->h2d_bytes += (long long)width_b * n * (hh / tb->period);
+      } else {
+        cudaMemcpyAsync(h->d_frames[si], src, (size_t)n * frame_stride, cudaMemcpyHostToDevice, s);
+        h->h2d_bytes += (long long)n * frame_stride;
+      }
       d_fr = h->d_frames[si];
     } else {
       d_fr = frames + (size_t)off * frame_stride;
@@ -323,11 +367,11 @@ int detect_impl(fdt_handle* h, const uint8_t* frames, int batch, int w, int hh, 
     {
       StageTimer t(h, 0, s);
       LetterboxP lb;
-      lb.frames = d_fr; lb.frame_stride = frame_stride; lb.row_stride = row_stride; lb.channels = channels;
+      lb.frames = d_fr; lb.frame_stride = dev_frame_stride; lb.row_stride = row_stride; lb.channels = channels;
       lb.src_w = w; lb.src_h = hh; lb.out = h->d_lb[si]; lb.dst_w = S_w; lb.dst_h = S_h;
       lb.new_w = tb->lp.new_w; lb.new_h = tb->lp.new_h; lb.pad_top = tb->lp.pad_top; lb.pad_left = tb->lp.pad_left;
       lb.x0 = tb->x0; lb.x1 = tb->x1; lb.ax0 = tb->ax0; lb.ax1 = tb->ax1;
-      lb.y0 = tb->y0; lb.y1 = tb->y1; lb.by0 = tb->by0; lb.by1 = tb->by1;
+      lb.y0 = sparse ? tb->y0c : tb->y0; lb.y1 = sparse ? tb->y1c : tb->y1; lb.by0 = tb->by0; lb.by1 = tb->by1;
       lb.identity = tb->identity ? 1 : 0;
       launch_letterbox(lb, n, s);
       t.launches = 1;
@@ -508,7 +552,7 @@ int32_t fdt_destroy(fdt_handle* h) {
     void* pin[] = {h->h_mesh_out, h->h_mesh_score, h->h_counts, h->h_faces};
     for (void* p : pin) if (p) cudaFreeHost(p);
     for (LbTables& t : h->tables) {
-      void* tp[] = {t.x0, t.x1, t.y0, t.y1, t.ax0, t.ax1, t.by0, t.by1};
+      void* tp[] = {t.x0, t.x1, t.y0, t.y1, t.ax0, t.ax1, t.by0, t.by1, t.y0c, t.y1c};
       for (void* p : tp) if (p) cudaFree(p);
     }
     if (h->ev[0]) cudaEventDestroy(h->ev[0]);
@@ -721,6 +765,7 @@ int32_t fdt_debug_get_mesh_stage(fdt_handle* h, int32_t n, uint8_t* out_crops, f
 }
 
 int64_t fdt_last_launch_count(fdt_handle* h) { return h ? h->launches : 0; }
+int64_t fdt_last_h2d_bytes(fdt_handle* h) { return h ? h->h2d_bytes : 0; }
 
 int32_t fdt_set_stage_timing(fdt_handle* h, int32_t enable) {
   if (!h) return FDT_ERR_NOT_READY;

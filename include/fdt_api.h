@@ -185,6 +185,10 @@ FDT_EXPORT int32_t fdt_debug_get_mesh_stage(fdt_handle* h, int32_t n, uint8_t* o
                                             float* out_raw1404, float* out_flag, int32_t* out_n);
 /* Number of kernel launches issued by the last detect call (bench.py "gpu_launches"). */
 FDT_EXPORT int64_t fdt_last_launch_count(fdt_handle* h);
+/* Bytes copied host->device by the last detect call.  In fast mode only the source rows the
+ * INTER_LINEAR taps read are uploaded when they form a periodic pattern (e.g. 2 of every 10 rows
+ * for 720 -> 72), so this can be far below batch * frame size. */
+FDT_EXPORT int64_t fdt_last_h2d_bytes(fdt_handle* h);
 /* Device time in ms of the named stage summed over the last call when stage timing was enabled
  * with fdt_set_stage_timing(h,1) (adds cudaEvent records; off by default).
  * stage: 0 letterbox, 1 conv stack, 2 decode+nms, 3 warp, 4 mesh net, 5 mesh post */
