@@ -82,11 +82,23 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         launch_naive_conv(p, B, s);
         break;
       }
+      case kStepStem: {
+        StemP p;
+        const PTensor& it = plan_.tensors[st.in];
+        p.in8 = in_u8; p.H = it.H; p.W = it.W; p.OH = out.H; p.OW = out.W;
+        p.kw = st.kw; p.pt = st.pt; p.pl = st.pl; p.K = st.K; p.KP = st.KP;
+        p.out = out.p; p.out_istride = out.istride; p.Cout = st.Cout; p.CoutS = out.Cs;
+        p.vec_store = (out.Cs % 4 == 0 && out.istride % 4 == 0 && ((size_t)out.p % 16 == 0)) ? 1 : 0;
+        p.w = blob + st.w; p.bias = blob + st.bias; p.alpha = st.alpha >= 0 ? blob + st.alpha : nullptr;
+        p.act = st.act; p.CoutP = st.CoutP; p.NC = st.NC; p.smem_bytes = st.smem;
+        launch_stem(p, B, s, cta_cap(st.smem, 32 * (st.NC / 4)));
+        break;
+      }
       case kStepGemmConv: {
         GemmConvP p;
         const PTensor& it = plan_.tensors[st.in];
         if (st.in_u8) {
-          p.in = nullptr; p.in8 = in_u8; p.in_istride = (long long)it.H * it.W * 3;
+          p.in = nullptr; p.in8 = in_u8; p.in_istride = (long long)it.H * it.W * 4;
           p.Cin = 3; p.CinS = 3;
         } else {
           TV iv = view(ctx, st.in);
@@ -99,9 +111,9 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         p.out = out.p; p.out_istride = out.istride; p.Cout = st.Cout; p.CoutS = out.Cs;
         p.vec_store = (out.Cs % 4 == 0 && out.istride % 4 == 0 && ((size_t)out.p % 16 == 0)) ? 1 : 0;
         p.w = blob + st.w; p.bias = blob + st.bias; p.alpha = st.alpha >= 0 ? blob + st.alpha : nullptr;
-        p.act = st.act; p.CoutP = st.CoutP; p.NNG = st.NNG; p.NC = st.NC; p.nchunks = st.nchunks;
+        p.act = st.act; p.CoutP = st.CoutP; p.NC = st.NC; p.nchunks = st.nchunks;
         p.NPG = st.NPG; p.TM = st.TM; p.smem_bytes = st.smem;
-        launch_gemm_conv(p, B, s, cta_cap(st.smem, st.NPG * st.NNG));
+        launch_gemm_conv(p, B, s, cta_cap(st.smem, st.NPG * (st.NC / 4)));
         break;
       }
       case kStepDwPw: {
@@ -115,8 +127,9 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         p.out = out.p; p.out_istride = out.istride; p.Cout = st.Cout; p.CoutS = out.Cs;
         p.vec_store = (out.Cs % 4 == 0 && out.istride % 4 == 0 && ((size_t)out.p % 16 == 0)) ? 1 : 0;
         p.w = blob + st.w; p.bias = blob + st.bias; p.alpha = st.alpha >= 0 ? blob + st.alpha : nullptr;
-        p.act = st.act; p.CoutP = st.CoutP; p.NNG = st.NNG; p.NC = st.NC; p.nchunks = st.nchunks;
+        p.act = st.act; p.CoutP = st.CoutP; p.NC = st.NC; p.nchunks = st.nchunks;
         p.NPG = st.NPG; p.TM = st.TM;
+        p.res_mode = st.in2 >= 0 ? st.res_mode : 0;
         if (st.in2 >= 0) {
           TV rv = view(ctx, st.in2);
           p.res = rv.p; p.res_istride = rv.istride; p.res_H = rv.H; p.res_W = rv.W; p.res_C = rv.C; p.res_Cs = rv.Cs;
@@ -126,7 +139,7 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         p.res_pool = st.res_pool;
         p.TH = st.TH; p.TW = st.TW; p.G = st.G; p.IH = st.IH; p.IW = st.IW; p.tilesX = st.tilesX; p.tilesY = st.tilesY;
         p.smem_bytes = st.smem;
-        launch_dwpw(p, B, s, cta_cap(st.smem, st.NPG * st.NNG));
+        launch_dwpw(p, B, s, cta_cap(st.smem, st.NPG * (st.NC / 4)));
         break;
       }
       case kStepAdd: case kStepAct: case kStepPadC: {

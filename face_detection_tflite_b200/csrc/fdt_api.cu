@@ -489,7 +489,7 @@ int32_t fdt_create(const fdt_config* cfg_in, const uint8_t* det_tflite, size_t d
   for (int i = 0; i < kStreams; ++i) {
     if (cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking) != cudaSuccess) return bail(FDT_ERR_CUDA, "stream creation failed");
     if (!h->det.make_ctx(h->chunk, &h->det_ctx[i], &err)) return bail(FDT_ERR_CUDA, err);
-    size_t lb = (size_t)h->chunk * h->det.in_h() * h->det.in_w() * 3;
+    size_t lb = (size_t)h->chunk * h->det.in_h() * h->det.in_w() * 4;   // BGRX
     if (cudaMalloc(&h->d_lb[i], lb) != cudaSuccess) return bail(FDT_ERR_CUDA, "cudaMalloc(letterboxed) failed");
     if (cudaMalloc(&h->d_cand_idx[i], (size_t)h->chunk * h->cand_cap * sizeof(int)) != cudaSuccess ||
         cudaMalloc(&h->d_cand_n[i], (size_t)h->chunk * sizeof(int)) != cudaSuccess)
@@ -513,7 +513,7 @@ int32_t fdt_create(const fdt_config* cfg_in, const uint8_t* det_tflite, size_t d
               cudaMalloc(&h->d_face_img, mc * sizeof(int)) == cudaSuccess && cudaMalloc(&h->d_face_slot, mc * sizeof(int)) == cudaSuccess &&
               cudaMalloc(&h->d_affine, mc * 6 * sizeof(double)) == cudaSuccess && cudaMalloc(&h->d_align, mc * 4 * sizeof(double)) == cudaSuccess &&
               cudaMalloc(&h->d_mesh_score, mc * sizeof(double)) == cudaSuccess &&
-              cudaMalloc(&h->d_crops, mc * kMeshInput * kMeshInput * 3) == cudaSuccess &&
+              cudaMalloc(&h->d_crops, mc * kMeshInput * kMeshInput * 4) == cudaSuccess &&
               cudaMalloc(&h->d_mesh_out, mc * FDT_MESH_FLOATS * sizeof(float)) == cudaSuccess &&
               cudaMallocHost(&h->h_mesh_out, mc * FDT_MESH_FLOATS * sizeof(float)) == cudaSuccess &&
               cudaMallocHost(&h->h_mesh_score, mc * sizeof(double)) == cudaSuccess;
@@ -664,8 +664,11 @@ int32_t fdt_debug_get_letterboxed(fdt_handle* h, int32_t n, uint8_t* out) {
   std::lock_guard<std::mutex> g(h->mu);
   if (n < 0 || n > h->last_first_chunk || !out) return fail(h, FDT_ERR_BAD_ARG, "n exceeds the last call's first chunk");
   cudaSetDevice(h->cfg.device);
-  size_t bytes = (size_t)n * h->det.in_h() * h->det.in_w() * 3;
-  return cuda_ok(h, cudaMemcpy(out, h->d_lb[0], bytes, cudaMemcpyDeviceToHost), "tap") ? FDT_OK : FDT_ERR_CUDA;
+  size_t px = (size_t)n * h->det.in_h() * h->det.in_w();
+  std::vector<uint8_t> tmp(px * 4);
+  if (!cuda_ok(h, cudaMemcpy(tmp.data(), h->d_lb[0], px * 4, cudaMemcpyDeviceToHost), "tap")) return FDT_ERR_CUDA;
+  for (size_t i = 0; i < px; ++i) { out[3 * i] = tmp[4 * i]; out[3 * i + 1] = tmp[4 * i + 1]; out[3 * i + 2] = tmp[4 * i + 2]; }
+  return FDT_OK;
 }
 
 int32_t fdt_debug_get_input_tensor(fdt_handle* h, int32_t n, float* out) {
@@ -754,7 +757,12 @@ int32_t fdt_debug_get_mesh_stage(fdt_handle* h, int32_t n, uint8_t* out_crops, f
   cudaSetDevice(h->cfg.device);
   const Plan& mp = h->mesh.plan();
   bool ok = true;
-  if (out_crops) ok &= cuda_ok(h, cudaMemcpy(out_crops, h->d_crops, (size_t)n * kMeshInput * kMeshInput * 3, cudaMemcpyDeviceToHost), "tap");
+  if (out_crops) {
+    size_t px = (size_t)n * kMeshInput * kMeshInput;
+    std::vector<uint8_t> tmp(px * 4);
+    ok &= cuda_ok(h, cudaMemcpy(tmp.data(), h->d_crops, px * 4, cudaMemcpyDeviceToHost), "tap");
+    for (size_t i = 0; i < px; ++i) { out_crops[3 * i] = tmp[4 * i]; out_crops[3 * i + 1] = tmp[4 * i + 1]; out_crops[3 * i + 2] = tmp[4 * i + 2]; }
+  }
   for (size_t k = 0; k < mp.out_elems.size(); ++k) {
     if (mp.out_elems[k] == FDT_MESH_FLOATS && out_raw1404)
       ok &= cuda_ok(h, cudaMemcpy(out_raw1404, h->mesh_ctx.outputs[k], (size_t)n * FDT_MESH_FLOATS * sizeof(float), cudaMemcpyDeviceToHost), "tap");
@@ -869,7 +877,7 @@ int32_t fdt_get_step_info(fdt_handle* h, int32_t launch, char* kernel, char* ten
   const Plan& p = h->det.plan();
   const int S = (int)p.steps.size();
   if (launch < 0 || launch > S + 1) return fail(h, FDT_ERR_BAD_ARG, "launch index out of range");
-  static const char* kn[] = {"k_normalize", "k_naive_conv", "k_gemm_conv", "k_dwpw", "k_add", "k_act", "k_padc", "k_maxpool", "k_resize_bilinear"};
+  static const char* kn[] = {"k_normalize", "k_naive_conv", "k_gemm_conv", "k_dwpw", "k_add", "k_act", "k_padc", "k_maxpool", "k_resize_bilinear", "k_stem"};
   std::string kname, tname;
   double macs = 0, bytes = 0;
   const int S_w = h->det.in_w(), S_h = h->det.in_h();
@@ -884,7 +892,7 @@ int32_t fdt_get_step_info(fdt_handle* h, int32_t launch, char* kernel, char* ten
     kname = kn[st.kind]; tname = st.name; macs = st.macs;
     const PTensor& o = p.tensors[st.out];
     bytes = (double)o.H * o.W * o.C * 4;
-    if (st.in_u8) bytes += (double)S_w * S_h * 3;
+    if (st.in_u8) bytes += (double)S_w * S_h * 4;
     else if (st.in >= 0) { const PTensor& i = p.tensors[st.in]; bytes += (double)i.H * i.W * i.C * 4; }
     if (st.in2 >= 0 && st.in2 != st.in) { const PTensor& r = p.tensors[st.in2]; bytes += (double)r.H * r.W * r.C * 4; }
   }

@@ -45,7 +45,7 @@ struct LetterboxP {
   const uint8_t* frames;   // [B][H][row_stride]
   long long frame_stride;  // bytes between frames
   int row_stride, channels, src_w, src_h;
-  uint8_t* out;            // [B][S_h][S_w][3] BGR
+  uint8_t* out;            // [B][S_h][S_w][4] BGRX (X = 0)
   int dst_w, dst_h, new_w, new_h, pad_top, pad_left;
   // INTER_LINEAR tap tables (device): x: [new_w], y: [new_h]
   const int* x0; const int* x1; const short* ax0; const short* ax1;
@@ -53,13 +53,25 @@ struct LetterboxP {
   int identity;            // 1: no resize (new == src)
 };
 void launch_letterbox(const LetterboxP& p, int B, cudaStream_t s);
-// u8 [B][S][S][3] BGR -> f32 [B][S][S][3] RGB, v*(1/127.5)-1
+// u8 [B][S][S][4] BGRX -> f32 [B][S][S][3] RGB, v*(1/127.5)-1
 void launch_normalize(const uint8_t* in, TV out, int B, cudaStream_t s);
+
+// ---- stem: k x k / stride 2 conv of the u8x4 BGRX image (normalise + BGR->RGB on load) ----
+struct StemP {
+  const uint8_t* in8;       // [B][H][W][4] BGRX
+  int H, W, OH, OW, kw, pt, pl, K, KP;
+  float* out; long long out_istride; int Cout, CoutS, vec_store;
+  const float* w;           // [KP][CoutP], row k = (ky*kw + kx)*3 + c
+  const float* bias; const float* alpha;
+  int act, CoutP, NC;
+  size_t smem_bytes;
+};
+void launch_stem(const StemP& p, int B, cudaStream_t s, int max_ctas);
 
 // ---- tiled conv kernels: im2col + register-tiled fp32 GEMM ----
 struct GemmConvP {
   const float* in;          // f32 NHWC (or nullptr when in8 is used)
-  const uint8_t* in8;       // u8 [B][H][W][3] BGR letterboxed image: normalised + swapped on load
+  const uint8_t* in8;       // u8 [B][H][W][4] BGRX image: normalised + swapped on load
   long long in_istride;
   int H, W, Cin, CinS;
   int kh, kw, sh, sw, pt, pl, OH, OW;
@@ -68,7 +80,7 @@ struct GemmConvP {
   const float* w;           // [KP][CoutP], row k = (ky,kx,c)
   const float* bias;        // [CoutP]
   const float* alpha;       // [CoutP] or nullptr
-  int act, CoutP, NNG, NC, nchunks, NPG, TM;
+  int act, CoutP, NC, nchunks, NPG, TM;
   size_t smem_bytes;
 };
 void launch_gemm_conv(const GemmConvP& p, int B, cudaStream_t s, int max_ctas);
@@ -83,8 +95,9 @@ struct DwPwP {
   float* out; long long out_istride; int Cout, CoutS, vec_store;
   const float* w;           // [KP][CoutP]
   const float* bias; const float* alpha;
-  int act, CoutP, NNG, NC, nchunks, NPG, TM;
+  int act, CoutP, NC, nchunks, NPG, TM;
   const float* res; long long res_istride; int res_H, res_W, res_C, res_Cs, res_pool;
+  int res_mode;             // 0 none, 1 from the staged input tile (shared memory), 2 from global
   int TH, TW, G, IH, IW, tilesX, tilesY;
   size_t smem_bytes;
 };
@@ -125,7 +138,7 @@ void launch_build_face_list(const FaceListP& p, cudaStream_t s);
 struct WarpP {
   const uint8_t* frames; long long frame_stride; int row_stride, channels, src_w, src_h;
   const int* face_img; const double* affine; int nfaces, out_size;
-  uint8_t* crops;          // [nfaces][out][out][3] BGR
+  uint8_t* crops;          // [nfaces][out][out][4] BGRX
 };
 void launch_warp_affine(const WarpP& p, cudaStream_t s);
 

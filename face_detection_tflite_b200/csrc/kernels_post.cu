@@ -267,12 +267,13 @@ __global__ void k_warp_affine(WarpP p) {
         acc[0] += px[0] * iw[t]; acc[1] += px[1] * iw[t]; acc[2] += px[2] * iw[t];
       }
     }
-    uint8_t* dst = p.crops + ((size_t)f * S * S + i) * 3;
+    uint8_t o[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       int v = (acc[c] + 16384) >> 15;
-      dst[c] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+      o[c] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
     }
+    reinterpret_cast<uchar4*>(p.crops)[(size_t)f * S * S + i] = make_uchar4(o[0], o[1], o[2], 0);
   }
 }
 

@@ -50,8 +50,7 @@ __global__ void k_letterbox(LetterboxP p, int B) {
         o = make_uchar3((unsigned char)res[0], (unsigned char)res[1], (unsigned char)res[2]);
       }
     }
-    uint8_t* d = p.out + (size_t)idx * 3;
-    d[0] = o.x; d[1] = o.y; d[2] = o.z;
+    reinterpret_cast<uchar4*>(p.out)[idx] = make_uchar4(o.x, o.y, o.z, 0);
   }
 }
 
@@ -64,7 +63,7 @@ __global__ void k_normalize(const uint8_t* in, TV out, long long total) {
     int b = (int)(pix / hw);
     long long sp = pix % hw;
     float v = 0.f;
-    if (c < 3) v = fmaf((float)in[((size_t)b * hw + sp) * 3 + (2 - c)], 1.0f / 127.5f, -1.0f);
+    if (c < 3) v = fmaf((float)in[((size_t)b * hw + sp) * 4 + (2 - c)], 1.0f / 127.5f, -1.0f);
     out.p[b * out.istride + sp * out.Cs + c] = v;
   }
 }

@@ -140,18 +140,15 @@ struct Builder {
   }
 
   // ---- tiling of the GEMM part ----------------------------------------------------------------
+  // Output-channel chunking and thread tile: quads of 4 channels, <= 24 quads per chunk; 4 pixels per
+  // thread while that keeps the CTA <= 384 threads, else 8.
   static void plan_columns(PStep* s) {
-    s->CoutP = ru(s->Cout, 8);
-    int groups = s->CoutP / 8;
-    if (groups <= 12) {
-      s->nchunks = 1;
-      s->NNG = groups;
-    } else {
-      s->nchunks = (groups + 11) / 12;
-      s->NNG = (groups + s->nchunks - 1) / s->nchunks;
-    }
-    s->NC = s->NNG * 8;
-    s->TM = s->NNG >= 6 ? 8 : 4;
+    s->CoutP = ru(s->Cout, 4);
+    int quads = s->CoutP / 4;
+    s->nchunks = (quads + 23) / 24;
+    int nq = (quads + s->nchunks - 1) / s->nchunks;
+    s->NC = nq * 4;
+    s->TM = nq <= 12 ? 4 : 8;
     s->NPG = 128 / s->TM;
   }
 
@@ -240,6 +237,9 @@ struct Builder {
         if (good) {
           res = r;
           st.res_pool = pool;
+          // the residual is the block input itself: take it from the staged tile when it is there
+          bool even = rt.dim(1) % 2 == 0 && rt.dim(2) % 2 == 0;
+          st.res_mode = (st.has_dw && r == src && (!pool || (even && st.dws == 2))) ? 1 : 2;
           absorbed.push_back(c);
           for (int a : abs2) absorbed.push_back(a);
           cur = add.out[0];
@@ -350,11 +350,12 @@ struct Builder {
     for (;;) {
       st.smem = ((size_t)st.TM * st.NPG * st.KS + (size_t)st.KP * st.NC) * 4;
       if (st.smem <= kSmemLimit) break;
-      if (st.NNG <= 1) return false;
-      st.NNG = (st.NNG + 1) / 2;
-      st.NC = st.NNG * 8;
+      int nq = st.NC / 4;
+      if (nq <= 1) return false;
+      nq = (nq + 1) / 2;
+      st.NC = nq * 4;
       st.nchunks = (st.CoutP + st.NC - 1) / st.NC;
-      st.TM = st.NNG >= 6 ? 8 : 4;
+      st.TM = nq <= 12 ? 4 : 8;
       st.NPG = 128 / st.TM;
     }
     std::vector<int> absorbed;
@@ -362,6 +363,14 @@ struct Builder {
     st.act = conv.act == 1 ? kActRelu : kActNone;
     if (st.act == kActNone) fuse_activation(&cur, &st.act, &alpha_tf, &absorbed);
     st.in_u8 = conv.in[0] == m.inputs[0] && Cin == 3;
+    if (st.in_u8 && st.kh == st.kw && (st.kw == 3 || st.kw == 5) && st.sh == 2 && st.sw == 2 && ru(st.Cout, 4) <= 64) {
+      st.kind = kStepStem;                       // direct strip convolution from the staged patch
+      st.CoutP = ru(st.Cout, 4);
+      st.NC = st.CoutP;
+      st.nchunks = 1;
+      int PH = 14 + st.kw, PW = 30 + st.kw;
+      st.smem = (size_t)PH * PW * 16 + (size_t)st.KP * st.NC * 4;
+    }
     for (int a : absorbed) done[a] = 1;
     done[ci] = 1;
     std::vector<float> w, b;
@@ -587,7 +596,7 @@ bool Plan::build(const TfModel& m, int fuse, std::string* err) {
 }
 
 std::string Plan::describe() const {
-  static const char* kn[] = {"normalize", "naive_conv", "gemm_conv", "dwpw", "add", "act", "padc", "maxpool", "resize"};
+  static const char* kn[] = {"normalize", "naive_conv", "gemm_conv", "dwpw", "add", "act", "padc", "maxpool", "resize", "stem"};
   std::string s;
   char buf[512];
   double macs = 0;
@@ -596,9 +605,9 @@ std::string Plan::describe() const {
     const PTensor& o = tensors[st.out];
     macs += st.macs;
     snprintf(buf, sizeof buf,
-             "%3zu %-10s in=%d res=%d%s out=%d[%dx%dx%d Cs%d %s] act=%d dw=%d/s%d K=%d NC=%dx%d TM=%d NPG=%d tile=%dx%dx%d smem=%zu  %s\n",
+             "%3zu %-10s in=%d res=%d%s/m%d out=%d[%dx%dx%d Cs%d %s] act=%d dw=%d/s%d K=%d NC=%dx%d TM=%d NPG=%d tile=%dx%dx%d smem=%zu  %s\n",
              i, kn[st.kind], st.in >= 0 ? tensors[st.in].tf : -1, st.in2 >= 0 ? tensors[st.in2].tf : -1,
-             st.res_pool ? "(pool)" : "", o.tf, o.H, o.W, o.C, o.Cs, o.root >= 0 ? "view" : "arena", st.act,
+             st.res_pool ? "(pool)" : "", st.res_mode, o.tf, o.H, o.W, o.C, o.Cs, o.root >= 0 ? "view" : "arena", st.act,
              (int)st.has_dw, st.dws, st.K, st.NC, st.nchunks, st.TM, st.NPG, st.TH, st.TW, st.G, st.smem, st.name.c_str());
     s += buf;
   }

@@ -25,7 +25,7 @@ struct PTensor {
 };
 
 enum StepKind { kStepNormalize, kStepNaiveConv, kStepGemmConv, kStepDwPw, kStepAdd, kStepAct, kStepPadC,
-                kStepMaxPool, kStepResize };
+                kStepMaxPool, kStepResize, kStepStem };
 
 struct PStep {
   StepKind kind = kStepAct;
@@ -34,9 +34,9 @@ struct PStep {
   int kh = 1, kw = 1, sh = 1, sw = 1, pt = 0, pl = 0, act = 0, depthwise = 0;
   bool in_u8 = false;
   bool has_dw = false;
-  int dws = 1, dpt = 0, dpl = 0, res_pool = 0;
+  int dws = 1, dpt = 0, dpl = 0, res_pool = 0, res_mode = 0;
   long long w = -1, bias = -1, alpha = -1, dww = -1, dwb = -1;  // float offsets into Plan::blob
-  int K = 0, KP = 0, KS = 0, Cout = 0, CoutP = 0, NNG = 0, NC = 0, nchunks = 0, NPG = 0, TM = 0;
+  int K = 0, KP = 0, KS = 0, Cout = 0, CoutP = 0, NC = 0, nchunks = 0, NPG = 0, TM = 0;
   int TH = 0, TW = 0, G = 1, IH = 0, IW = 0, tilesX = 1, tilesY = 1;
   size_t smem = 0;
   int fh = 1, fw = 1, align = 0, half = 0;
