@@ -17,6 +17,7 @@ OBJ = PKG / "build"
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-I", str(PKG.parent / "include")]
+COMMON += os.environ.get("FDT_NVCC_FLAGS", "").split()   # tuning experiments, e.g. -DFDT_MINB=2
 SOURCES = {
     "tflite_model.cpp": [],
     "plan.cpp": [],
@@ -42,6 +43,7 @@ def _stamp() -> str:
     for p in sorted(list(CSRC.glob("*")) + [PKG.parent / "include" / "fdt_api.h", Path(__file__)]):
         h.update(p.name.encode())
         h.update(p.read_bytes())
+    h.update(os.environ.get("FDT_NVCC_FLAGS", "").encode())
     return h.hexdigest()
 
 

@@ -138,6 +138,9 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         }
         p.res_pool = st.res_pool;
         p.TH = st.TH; p.TW = st.TW; p.G = st.G; p.IH = st.IH; p.IW = st.IW; p.tilesX = st.tilesX; p.tilesY = st.tilesY;
+        p.fd_Q = FastDiv(st.KP / 4); p.fd_IW = FastDiv(st.IW); p.fd_IH = FastDiv(st.IH); p.fd_TW = FastDiv(st.TW);
+        p.fd_thw = FastDiv(st.TH * st.TW); p.fd_NQ = FastDiv(st.NC / 4); p.fd_tpg = FastDiv(st.tilesX * st.tilesY);
+        p.fd_tilesX = FastDiv(st.tilesX);
         p.smem_bytes = st.smem;
         launch_dwpw(p, B, s, cta_cap(st.smem, st.NPG * (st.NC / 4)));
         break;

@@ -11,6 +11,24 @@ namespace fdt {
 
 enum { kActNone = 0, kActRelu = 1, kActPrelu = 2 };
 
+// Division by a runtime-constant divisor as multiply-high + shift (n < 2^31), so the index
+// arithmetic of the staging / epilogue loops costs 3 instructions instead of ~30.
+struct FastDiv {
+  unsigned mul = 0, shr = 0, d = 1;
+  FastDiv() {}
+  explicit FastDiv(int div) {
+    d = div < 1 ? 1u : (unsigned)div;
+    unsigned l = 0;
+    while ((1ull << l) < d) ++l;
+    shr = l;
+    mul = (unsigned)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  }
+#ifdef __CUDACC__
+  __device__ __forceinline__ int div(int n) const { return (int)((__umulhi(mul, (unsigned)n) + (unsigned)n) >> shr); }
+  __device__ __forceinline__ void divmod(int n, int& q, int& r) const { q = div(n); r = n - q * (int)d; }
+#endif
+};
+
 struct TV {  // tensor view (device)
   float* p = nullptr;       // image 0
   long long istride = 0;    // floats between consecutive images
@@ -99,6 +117,7 @@ struct DwPwP {
   const float* res; long long res_istride; int res_H, res_W, res_C, res_Cs, res_pool;
   int res_mode;             // 0 none, 1 from the staged input tile (shared memory), 2 from global
   int TH, TW, G, IH, IW, tilesX, tilesY;
+  FastDiv fd_Q, fd_IW, fd_IH, fd_TW, fd_thw, fd_NQ, fd_tpg, fd_tilesX;
   size_t smem_bytes;
 };
 void launch_dwpw(const DwPwP& p, int B, cudaStream_t s, int max_ctas);

@@ -22,6 +22,10 @@
 
 #include "kernels.h"
 
+#ifndef FDT_MINB
+#define FDT_MINB 1   // min resident CTAs per SM the register allocator must allow (tuning knob)
+#endif
+
 namespace fdt {
 namespace {
 
@@ -71,7 +75,7 @@ __device__ __forceinline__ void gemm_core(const float* __restrict__ sA, int KS, 
 __device__ __forceinline__ void load_weights(float* sW, const float* __restrict__ w, int KP, int CoutP, int c0,
                                              int NC, int tid, int nt) {
   const int nq = NC >> 2;
-  for (int i = tid; i < KP * nq; i += nt) {
+  for (int i = tid; i < KP * nq; i += nt) {   // once per CTA and chunk: plain division is fine here
     int k = i / nq, q = i - k * nq;
     int c = c0 + 4 * q;
     cp_async16(sW + (size_t)k * NC + 4 * q, c < CoutP ? w + (size_t)k * CoutP + c : w, c < CoutP);
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(512) k_stem(StemP p, int B, int ntiles) {
 
 // ------------------------------------------------------------------------------------------------
 template <int TM>
-__global__ void __launch_bounds__(384) k_gemm_conv(GemmConvP p, int B, int ntiles) {
+__global__ void __launch_bounds__(384, FDT_MINB) k_gemm_conv(GemmConvP p, int B, int ntiles) {
   extern __shared__ __align__(16) float smem[];
   const int P = TM * p.NPG;
   float* sA = smem;                          // [P][KS]
@@ -255,7 +259,7 @@ __global__ void __launch_bounds__(384) k_gemm_conv(GemmConvP p, int B, int ntile
 
 // ------------------------------------------------------------------------------------------------
 template <int TM>
-__global__ void __launch_bounds__(384) k_dwpw(DwPwP p, int B, int ntiles) {
+__global__ void __launch_bounds__(384, FDT_MINB) k_dwpw(DwPwP p, int B, int ntiles) {
   extern __shared__ __align__(16) float smem[];
   const int P = TM * p.NPG;
   const int in_elems = p.G * p.IH * p.IW * p.KS;
@@ -263,10 +267,9 @@ __global__ void __launch_bounds__(384) k_dwpw(DwPwP p, int B, int ntiles) {
   float* sA = p.has_dw ? smem + in_elems : smem;      // [P][KS]  (aliases sIn without DW)
   float* sW = sA + (size_t)P * p.KS;                  // [KP][NC]
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int NQ = p.NC >> 2;
-  const int q = tid % NQ, pg = tid / NQ;
+  int q, pg;
+  p.fd_NQ.divmod(tid, pg, q);
   const int Q = p.KP >> 2;
-  const int tiles_per_group = p.tilesX * p.tilesY;
   const int thw = p.TH * p.TW;
 
   for (int chunk = 0; chunk < p.nchunks; ++chunk) {
@@ -274,19 +277,21 @@ __global__ void __launch_bounds__(384) k_dwpw(DwPwP p, int B, int ntiles) {
     __syncthreads();
     load_weights(sW, p.w, p.KP, p.CoutP, c0, p.NC, tid, nt);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int grp = tile / tiles_per_group;
-      const int trem = tile - grp * tiles_per_group;
-      const int ty0 = (trem / p.tilesX) * p.TH, tx0 = (trem % p.tilesX) * p.TW;
+      int grp, trem, tyi, txi;
+      p.fd_tpg.divmod(tile, grp, trem);
+      p.fd_tilesX.divmod(trem, tyi, txi);
+      const int ty0 = tyi * p.TH, tx0 = txi * p.TW;
       const int b0 = grp * p.G;
       const int iy0 = ty0 * p.s - p.dpt, ix0 = tx0 * p.s - p.dpl;  // input coords of sIn(0,0)
       __syncthreads();
       // ---- stage the input tile (+halo) with cp.async; zero outside the image (TFLite SAME padding)
       {
-        const int rowq = p.IW * Q;
-        for (int i = tid; i < p.G * p.IH * rowq; i += nt) {
-          int gy = i / rowq, r = i - gy * rowq;
-          int lx = r / Q, qq = r - lx * Q;
-          int g = gy / p.IH, ly = gy - g * p.IH;
+        const int total = p.G * p.IH * p.IW * Q;
+        for (int i = tid; i < total; i += nt) {
+          int pix, qq, gy, lx, g, ly;
+          p.fd_Q.divmod(i, pix, qq);
+          p.fd_IW.divmod(pix, gy, lx);
+          p.fd_IH.divmod(gy, g, ly);
           int b = b0 + g, y = iy0 + ly, x = ix0 + lx;
           bool ok = b < B && y >= 0 && y < p.H && x >= 0 && x < p.W;
           const float* src = ok ? p.in + (size_t)b * p.in_istride + ((size_t)y * p.W + x) * p.CinS + 4 * qq : p.in;
@@ -300,9 +305,9 @@ __global__ void __launch_bounds__(384) k_dwpw(DwPwP p, int B, int ntiles) {
         //      consecutive pixels, stride KS floats => conflict-free), TH outputs each
         const int nitems = p.G * Q * p.TW;
         for (int it = tid; it < nitems; it += nt) {
-          int tx = it % p.TW;
-          int r = it / p.TW;
-          int qq = r % Q, g = r / Q;
+          int tx, r, qq, g;
+          p.fd_TW.divmod(it, r, tx);
+          p.fd_Q.divmod(r, g, qq);
           float4 w[9];
 #pragma unroll
           for (int t = 0; t < 9; ++t) w[t] = *reinterpret_cast<const float4*>(p.dww + (size_t)t * p.KP + 4 * qq);
@@ -376,8 +381,9 @@ __global__ void __launch_bounds__(384) k_dwpw(DwPwP p, int B, int ntiles) {
         for (int i = 0; i < TM; ++i) {
           int slot = pg + p.NPG * i;
           if (slot >= p.G * thw) continue;
-          int g = slot / thw, r = slot - g * thw;
-          int ty = r / p.TW, tx = r - ty * p.TW;
+          int g, r, ty, tx;
+          p.fd_thw.divmod(slot, g, r);
+          p.fd_TW.divmod(r, ty, tx);
           int oy = ty0 + ty, ox = tx0 + tx;
           int b = b0 + g;
           if (b >= B || oy >= p.OH || ox >= p.OW) continue;
