@@ -25,6 +25,7 @@ SOURCES = {
     "fdt_api.cu": [],
     "kernels_naive.cu": [],
     "kernels_tiled.cu": [],
+    "kernels_tc.cu": [],
     "kernels_pre.cu": [],
     # f64 geometry must be evaluated operation by operation (no fused multiply-add contraction)
     "kernels_post.cu": ["-fmad=false"],

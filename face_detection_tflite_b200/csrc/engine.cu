@@ -9,9 +9,9 @@ Engine::~Engine() {
   if (d_blob_) cudaFree(d_blob_);
 }
 
-bool Engine::init(const uint8_t* tflite, size_t len, int fuse_level, std::string* err) {
+bool Engine::init(const uint8_t* tflite, size_t len, int fuse_level, std::string* err, bool use_tc) {
   if (!model_.parse(tflite, len, err)) return false;
-  if (!plan_.build(model_, fuse_level, err)) return false;
+  if (!plan_.build(model_, fuse_level, err, use_tc)) return false;
   size_t bytes = plan_.blob.size() * sizeof(float) + 64;
   if (cudaMalloc(&d_blob_, bytes) != cudaSuccess) { *err = "cudaMalloc(weights) failed"; return false; }
   cudaMemset(d_blob_, 0, bytes);
@@ -143,6 +143,34 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         p.fd_tilesX = FastDiv(st.tilesX);
         p.smem_bytes = st.smem;
         launch_dwpw(p, B, s, cta_cap(st.smem, st.NPG * (st.NC / 4)));
+        break;
+      }
+      case kStepDwPwTc: {
+        DwPwTcP p;
+        TV iv = view(ctx, st.in);
+        p.in = iv.p; p.in_istride = iv.istride; p.H = iv.H; p.W = iv.W; p.Cin = iv.C; p.CinS = iv.Cs;
+        p.has_dw = st.has_dw ? 1 : 0; p.s = st.dws; p.dpt = st.dpt; p.dpl = st.dpl;
+        p.OH = out.H; p.OW = out.W;
+        p.dww = st.dww >= 0 ? blob + st.dww : nullptr; p.dwb = st.dwb >= 0 ? blob + st.dwb : nullptr;
+        p.K8 = st.K8; p.KS = st.KS;
+        p.out = out.p; p.out_istride = out.istride; p.Cout = st.Cout; p.CoutS = out.Cs;
+        p.vec_store = (out.Cs % 4 == 0 && out.istride % 4 == 0 && ((size_t)out.p % 16 == 0)) ? 1 : 0;
+        p.wB = blob + st.w; p.bias = blob + st.bias; p.alpha = st.alpha >= 0 ? blob + st.alpha : nullptr;
+        p.act = st.act; p.Npad = st.Npad; p.tmem_cols = st.tmem_cols; p.a_rows = st.a_rows; p.RS = st.RS;
+        p.res_mode = st.in2 >= 0 ? st.res_mode : 0;
+        if (st.in2 >= 0) {
+          TV rv = view(ctx, st.in2);
+          p.res = rv.p; p.res_istride = rv.istride; p.res_H = rv.H; p.res_W = rv.W; p.res_C = rv.C; p.res_Cs = rv.Cs;
+        } else {
+          p.res = nullptr; p.res_istride = 0; p.res_H = p.res_W = p.res_C = p.res_Cs = 0;
+        }
+        p.res_pool = st.res_pool; p.res_lim = iv.Cs;
+        p.TH = st.TH; p.TW = st.TW; p.G = st.G; p.IH = st.IH; p.IW = st.IW; p.tilesX = st.tilesX; p.tilesY = st.tilesY;
+        p.fd_Q8 = FastDiv(st.K8 / 4); p.fd_IW = FastDiv(st.IW); p.fd_IH = FastDiv(st.IH); p.fd_TW = FastDiv(st.TW);
+        p.fd_thw = FastDiv(st.TH * st.TW); p.fd_tpg = FastDiv(st.tilesX * st.tilesY); p.fd_tilesX = FastDiv(st.tilesX);
+        p.fd_nstrips = FastDiv(st.TH / st.RS); p.fd_nslots = FastDiv(st.G * st.TH * st.TW);
+        p.smem_bytes = st.smem;
+        launch_dwpw_tc(p, B, s, cta_cap(st.smem, 256));
         break;
       }
       case kStepAdd: case kStepAct: case kStepPadC: {

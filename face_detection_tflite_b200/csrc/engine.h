@@ -21,7 +21,7 @@ struct EngineCtx {
 class Engine {
  public:
   ~Engine();
-  bool init(const uint8_t* tflite, size_t len, int fuse_level, std::string* err);
+  bool init(const uint8_t* tflite, size_t len, int fuse_level, std::string* err, bool use_tc = true);
   bool make_ctx(int cap, EngineCtx* ctx, std::string* err) const;
   void free_ctx(EngineCtx* ctx) const;
   // Runs the plan on B <= ctx.cap images whose u8 BGR input lives at `in_u8` ([B][H][W][3]).

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -468,13 +469,16 @@ int32_t fdt_create(const fdt_config* cfg_in, const uint8_t* det_tflite, size_t d
   h->chunk = cfg.max_batch > 0 ? cfg.max_batch : 256;
   h->max_faces = cfg.max_faces > 0 ? std::min(cfg.max_faces, (int)FDT_MAX_FACES) : FDT_MAX_FACES;
   int fuse = cfg.fuse_level < 0 ? 1 : cfg.fuse_level;
+  // FDT_NO_TC=1 keeps the pointwise GEMMs on the fp32 CUDA-core kernels (A/B measurements)
+  const char* no_tc = std::getenv("FDT_NO_TC");
+  const bool use_tc = !(no_tc && no_tc[0] == '1');
   std::string err;
   auto bail = [&](int code, const std::string& m) {
     fail(nullptr, code, m);
     fdt_destroy(h);
     return code;
   };
-  if (!h->det.init(det_tflite, det_len, fuse, &err)) return bail(FDT_ERR_MODEL, "detector model: " + err);
+  if (!h->det.init(det_tflite, det_len, fuse, &err, use_tc)) return bail(FDT_ERR_MODEL, "detector model: " + err);
   SsdOptions so = ssd_options(cfg.model);
   if (h->det.in_h() != so.input_h || h->det.in_w() != so.input_w)
     return bail(FDT_ERR_MODEL, "detector input size does not match the selected FaceDetectionModel");
@@ -500,7 +504,7 @@ int32_t fdt_create(const fdt_config* cfg_in, const uint8_t* det_tflite, size_t d
   cudaEventCreate(&h->ev[1]);
   for (int i = 0; i < 3; ++i) cudaEventCreate(&h->tev[i]);
   if (mesh_tflite && mesh_len) {
-    if (!h->mesh.init(mesh_tflite, mesh_len, fuse, &err)) return bail(FDT_ERR_MODEL, "mesh model: " + err);
+    if (!h->mesh.init(mesh_tflite, mesh_len, fuse, &err, use_tc)) return bail(FDT_ERR_MODEL, "mesh model: " + err);
     if (h->mesh.in_h() != kMeshInput || h->mesh.in_w() != kMeshInput) return bail(FDT_ERR_MODEL, "mesh model input must be 192x192");
     const Plan& mp = h->mesh.plan();
     bool has3 = false, has1 = false;
@@ -877,7 +881,7 @@ int32_t fdt_get_step_info(fdt_handle* h, int32_t launch, char* kernel, char* ten
   const Plan& p = h->det.plan();
   const int S = (int)p.steps.size();
   if (launch < 0 || launch > S + 1) return fail(h, FDT_ERR_BAD_ARG, "launch index out of range");
-  static const char* kn[] = {"k_normalize", "k_naive_conv", "k_gemm_conv", "k_dwpw", "k_add", "k_act", "k_padc", "k_maxpool", "k_resize_bilinear", "k_stem"};
+  static const char* kn[] = {"k_normalize", "k_naive_conv", "k_gemm_conv", "k_dwpw", "k_add", "k_act", "k_padc", "k_maxpool", "k_resize_bilinear", "k_stem", "k_dwpw_tc"};
   std::string kname, tname;
   double macs = 0, bytes = 0;
   const int S_w = h->det.in_w(), S_h = h->det.in_h();

@@ -122,6 +122,24 @@ struct DwPwP {
 };
 void launch_dwpw(const DwPwP& p, int B, cudaStream_t s, int max_ctas);
 
+// ---- fused BlazeBlock with the pointwise conv on tcgen05 tensor cores (TF32 hi/lo split) ----
+struct DwPwTcP {
+  const float* in; long long in_istride; int H, W, Cin, CinS;
+  int has_dw, s, dpt, dpl, OH, OW;
+  const float* dww;         // [9][K8]
+  const float* dwb;         // [K8]
+  int K8, KS;               // K padded to 8; smem pixel stride of the staged tile
+  float* out; long long out_istride; int Cout, CoutS, vec_store;
+  const float* wB;          // [Npad x K8] in the UMMA K-major core-matrix layout
+  const float* bias; const float* alpha;   // [Npad]
+  int act, Npad, tmem_cols, a_rows, RS;
+  const float* res; long long res_istride; int res_H, res_W, res_C, res_Cs, res_pool, res_mode, res_lim;
+  int TH, TW, G, IH, IW, tilesX, tilesY;
+  FastDiv fd_Q8, fd_IW, fd_IH, fd_TW, fd_thw, fd_tpg, fd_tilesX, fd_nstrips, fd_nslots;
+  size_t smem_bytes;
+};
+void launch_dwpw_tc(const DwPwTcP& p, int B, cudaStream_t s, int max_ctas);
+
 // ---- detector post-processing: one block per image ----
 struct DecodeP {
   const float* boxes; long long boxes_istride;    // [B][N][16]

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cstdint>
 
 namespace fdt {
 namespace {
@@ -38,6 +39,7 @@ struct Builder {
   std::vector<View> views;
   std::map<int, Fused> fused;  // conv op index -> fused step
 
+  bool use_tc = true;
   Builder(const TfModel& mm, Plan& pp, int f) : m(mm), P(pp), fuse(f) {}
 
   bool fail(const std::string& e) { err = e; return false; }
@@ -267,25 +269,97 @@ struct Builder {
     if (!m.const_f32(conv.in[1], &w)) return fail("conv weights are not constant");
     if (conv.in.size() > 2 && conv.in[2] >= 0) { if (!m.const_f32(conv.in[2], &b)) return fail("conv bias is not constant"); }
     b.resize(st.Cout, 0.f);
-    std::vector<float> wk((size_t)st.KP * st.CoutP, 0.f);
-    for (int co = 0; co < st.Cout; ++co)
-      for (int c = 0; c < Cin; ++c) wk[(size_t)c * st.CoutP + co] = w[(size_t)co * Cin + c];
-    size_t padded = (size_t)st.nchunks * st.NC + 8;
-    F->st.w = push(wk, wk.size());
-    F->st.bias = push(b, padded);
-    if (alpha_tf >= 0 && !pack_alpha(alpha_tf, padded, &F->st.alpha)) return false;
+    bool tc = use_tc && tf32_exact(w) && (st.res_mode != 1 || st.has_dw) && plan_tc(&F->st, Cin, OH, OW);
+    const PStep& fs = F->st;
+    if (tc) {
+      // B operand [Npad x K8] in the UMMA K-major core-matrix layout (8 rows x 16 bytes per core matrix)
+      const size_t SBO = (size_t)(fs.K8 / 4) * 128, LBO = 128;
+      std::vector<float> wb((size_t)fs.Npad * fs.K8, 0.f);
+      for (int n = 0; n < fs.Cout; ++n)
+        for (int k = 0; k < Cin; ++k)
+          wb[((size_t)(n >> 3) * SBO + (size_t)(k >> 2) * LBO + (size_t)(n & 7) * 16 + (size_t)(k & 3) * 4) / 4] = w[(size_t)n * Cin + k];
+      F->st.w = push(wb, wb.size());
+      F->st.bias = push(b, (size_t)fs.Npad + 8);
+      if (alpha_tf >= 0 && !pack_alpha(alpha_tf, (size_t)fs.Npad + 8, &F->st.alpha)) return false;
+    } else {
+      std::vector<float> wk((size_t)st.KP * st.CoutP, 0.f);
+      for (int co = 0; co < st.Cout; ++co)
+        for (int c = 0; c < Cin; ++c) wk[(size_t)c * st.CoutP + co] = w[(size_t)co * Cin + c];
+      size_t padded = (size_t)st.nchunks * st.NC + 8;
+      F->st.w = push(wk, wk.size());
+      F->st.bias = push(b, padded);
+      if (alpha_tf >= 0 && !pack_alpha(alpha_tf, padded, &F->st.alpha)) return false;
+    }
     if (st.has_dw) {
       const TfOp& dw = m.ops[absorbed[0]];
       std::vector<float> dwv, dbv;
       if (!m.const_f32(dw.in[1], &dwv) || !m.const_f32(dw.in[2], &dbv)) return fail("depthwise weights are not constant");
-      std::vector<float> dk((size_t)9 * st.KP, 0.f);
+      const int kp = tc ? fs.K8 : st.KP;
+      std::vector<float> dk((size_t)9 * kp, 0.f);
       for (int t = 0; t < 9; ++t)
-        for (int c = 0; c < Cin; ++c) dk[(size_t)t * st.KP + c] = dwv[(size_t)t * Cin + c];
+        for (int c = 0; c < Cin; ++c) dk[(size_t)t * kp + c] = dwv[(size_t)t * Cin + c];
       F->st.dww = push(dk, dk.size());
-      F->st.dwb = push(dbv, st.KP);
+      F->st.dwb = push(dbv, kp);
     }
     F->st.macs = (double)OH * OW * ((double)Cin * st.Cout + (st.has_dw ? 9.0 * Cin : 0.0));
     return true;
+  }
+
+  // ---- tensor-core variant of a fused pointwise step -------------------------------------------
+  static bool tf32_exact(const std::vector<float>& w) {
+    for (float v : w) {
+      uint32_t u;
+      std::memcpy(&u, &v, 4);
+      if (u & 0x1FFFu) return false;
+    }
+    return true;
+  }
+
+  // Re-plans `st` (a kStepDwPw) for k_dwpw_tc: M = 128 pixel slots, N = Cout padded to 16, K padded to 8.
+  bool plan_tc(PStep* st, int Cin, int OH, int OW) {
+    PStep s = *st;
+    s.K8 = ru(Cin, 8);
+    s.Npad = ru(s.Cout, 16);
+    if (s.Npad > 128 || s.K8 > 256) return false;
+    s.KS = s.K8 + (((s.K8 / 4) % 2 == 0) ? 4 : 0);
+    s.tmem_cols = 32;
+    while (s.tmem_cols < s.Npad) s.tmem_cols *= 2;
+    for (int Pn = 128; Pn >= 32; Pn /= 2) {
+      s.TM = 1; s.NPG = Pn;                       // plan_spatial reads TM * NPG as the slot budget
+      int bestTH = 0, bestTW = 0, bestG = 1;
+      double best = -1;
+      if (OH * OW <= Pn) {
+        bestTH = OH; bestTW = OW; bestG = Pn / (OH * OW);
+      } else {
+        for (int TW = std::min(OW, Pn); TW >= 1; --TW) {
+          int TH = std::min(OH, Pn / TW);
+          if (TH < 1) continue;
+          double tiles = (double)((OH + TH - 1) / TH) * ((OW + TW - 1) / TW);
+          double util = (double)OH * OW / (tiles * Pn);
+          double halo = (double)((TH - 1) * s.dws + 3) * ((TW - 1) * s.dws + 3) / ((double)TH * TW * s.dws * s.dws);
+          double score = util / (s.has_dw ? halo : 1.0);
+          if (score > best + 1e-9) { best = score; bestTH = TH; bestTW = TW; }
+        }
+      }
+      s.TH = bestTH; s.TW = bestTW; s.G = bestG;
+      s.IH = s.has_dw ? (s.TH - 1) * s.dws + 3 : s.TH;
+      s.IW = s.has_dw ? (s.TW - 1) * s.dws + 3 : s.TW;
+      s.tilesY = (OH + s.TH - 1) / s.TH;
+      s.tilesX = (OW + s.TW - 1) / s.TW;
+      int nslots = s.G * s.TH * s.TW;
+      s.a_rows = ru(nslots, 8);
+      s.RS = 1;
+      for (int rs : {8, 4, 2}) if (s.TH % rs == 0 && s.G * (s.K8 / 4) * (s.TH / rs) * s.TW >= 256) { s.RS = rs; break; }
+      size_t head = (size_t)s.Npad * s.K8 + 2 * (size_t)s.Npad;
+      size_t a = 2 * (size_t)s.a_rows * s.K8;
+      size_t in = (size_t)s.G * s.IH * s.IW * s.KS;
+      // the MMA always reads 128 rows of each A tile: keep those addresses inside the allocation
+      size_t need_tail = (size_t)(128 - s.a_rows) * s.K8;      // floats past the end of A_lo
+      if (in < need_tail) in = need_tail;
+      s.smem = (head + a + in) * 4 + 128;
+      if (s.smem <= 220 * 1024) { s.kind = kStepDwPwTc; *st = s; return true; }
+    }
+    return false;
   }
 
   std::vector<int> fused_outputs;
@@ -586,17 +660,18 @@ struct Builder {
 
 }  // namespace
 
-bool Plan::build(const TfModel& m, int fuse, std::string* err) {
+bool Plan::build(const TfModel& m, int fuse, std::string* err, bool use_tc) {
   *this = Plan();
   fuse_level = fuse;
   Builder b(m, *this, fuse);
+  b.use_tc = use_tc;
   bool ok = b.run();
   if (!ok && err) *err = b.err;
   return ok;
 }
 
 std::string Plan::describe() const {
-  static const char* kn[] = {"normalize", "naive_conv", "gemm_conv", "dwpw", "add", "act", "padc", "maxpool", "resize", "stem"};
+  static const char* kn[] = {"normalize", "naive_conv", "gemm_conv", "dwpw", "add", "act", "padc", "maxpool", "resize", "stem", "dwpw_tc"};
   std::string s;
   char buf[512];
   double macs = 0;

@@ -25,7 +25,7 @@ struct PTensor {
 };
 
 enum StepKind { kStepNormalize, kStepNaiveConv, kStepGemmConv, kStepDwPw, kStepAdd, kStepAct, kStepPadC,
-                kStepMaxPool, kStepResize, kStepStem };
+                kStepMaxPool, kStepResize, kStepStem, kStepDwPwTc };
 
 struct PStep {
   StepKind kind = kStepAct;
@@ -39,6 +39,7 @@ struct PStep {
   int K = 0, KP = 0, KS = 0, Cout = 0, CoutP = 0, NC = 0, nchunks = 0, NPG = 0, TM = 0;
   int TH = 0, TW = 0, G = 1, IH = 0, IW = 0, tilesX = 1, tilesY = 1;
   size_t smem = 0;
+  int K8 = 0, Npad = 0, a_rows = 0, RS = 1, tmem_cols = 0;   // tensor-core variant
   int fh = 1, fw = 1, align = 0, half = 0;
   double macs = 0;  // per image
 };
@@ -54,7 +55,7 @@ struct Plan {
   long long arena_per_image = 0;       // floats
   int fuse_level = 1;
 
-  bool build(const TfModel& m, int fuse_level, std::string* err);
+  bool build(const TfModel& m, int fuse_level, std::string* err, bool use_tc = true);
   std::string describe() const;
 };
 
