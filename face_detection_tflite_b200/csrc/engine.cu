@@ -169,6 +169,11 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         p.fd_Q8 = FastDiv(st.K8 / 4); p.fd_IW = FastDiv(st.IW); p.fd_IH = FastDiv(st.IH); p.fd_TW = FastDiv(st.TW);
         p.fd_thw = FastDiv(st.TH * st.TW); p.fd_tpg = FastDiv(st.tilesX * st.tilesY); p.fd_tilesX = FastDiv(st.tilesX);
         p.fd_nstrips = FastDiv(st.TH / st.RS); p.fd_nslots = FastDiv(st.G * st.TH * st.TW);
+        {
+          int nrows = st.G * st.IH, lg = 0;
+          while ((256 >> (lg + 1)) >= nrows && lg < 5) ++lg;   // largest power of two with 256/TPR >= nrows (<= 32)
+          p.TPR_log2 = lg; p.TPR = 1 << lg;
+        }
         p.smem_bytes = st.smem;
         launch_dwpw_tc(p, B, s, cta_cap(st.smem, 256));
         break;

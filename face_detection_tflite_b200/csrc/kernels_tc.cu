@@ -67,7 +67,10 @@ __device__ __forceinline__ void split_store(float* sAhi, float* sAlo, size_t off
   *reinterpret_cast<float4*>(sAlo + off) = lo;
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1) k_dwpw_tc(DwPwTcP p, int B, int ntiles) {
+#ifndef FDT_TC_MINB
+#define FDT_TC_MINB 1
+#endif
+__global__ void __launch_bounds__(kTcThreads, FDT_TC_MINB) k_dwpw_tc(DwPwTcP p, int B, int ntiles) {
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t mbar;
   __shared__ uint32_t tmem_base_s;
@@ -114,18 +117,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dwpw_tc(DwPwTcP p, int B, int
     const int ty0 = tyi * p.TH, tx0 = txi * p.TW;
     const int b0 = grp * p.G;
     const int iy0 = ty0 * p.s - p.dpt, ix0 = tx0 * p.s - p.dpl;
-    // ---- stage the input tile (+halo); zero outside the image and in the K padding lanes
+    // ---- stage the input tile (+halo); zero outside the image and in the K padding lanes.
+    //      TPR threads share one tile row: the row's 64-bit base and the y / batch bounds are computed
+    //      once, each 16-byte chunk then costs one FastDiv, an x bound check and two adds.
     {
-      const int total = p.G * p.IH * p.IW * Q8;
-      for (int i = tid; i < total; i += kTcThreads) {
-        int pix, qq, gy, lx, g, ly;
-        p.fd_Q8.divmod(i, pix, qq);
-        p.fd_IW.divmod(pix, gy, lx);
-        p.fd_IH.divmod(gy, g, ly);
-        int b = b0 + g, y = iy0 + ly, x = ix0 + lx;
-        bool ok = b < B && y >= 0 && y < p.H && x >= 0 && x < p.W && 4 * qq < p.CinS;
-        const float* src = ok ? p.in + (size_t)b * p.in_istride + ((size_t)y * p.W + x) * p.CinS + 4 * qq : p.in;
-        cp_async16(sIn + ((size_t)gy * p.IW + lx) * p.KS + 4 * qq, src, ok);
+      const int nrows = p.G * p.IH;
+      const int lane_r = tid & (p.TPR - 1);
+      const int chunks = p.IW * Q8;
+      for (int r = tid >> p.TPR_log2; r < nrows; r += (kTcThreads >> p.TPR_log2)) {
+        int g, ly;
+        p.fd_IH.divmod(r, g, ly);
+        const int b = b0 + g, y = iy0 + ly;
+        const bool row_ok = b < B && y >= 0 && y < p.H;
+        const float* grow = p.in + (size_t)(row_ok ? b : 0) * p.in_istride + ((long long)(row_ok ? y : 0) * p.W + ix0) * p.CinS;
+        float* srow = sIn + (size_t)r * p.IW * p.KS;
+        for (int c = lane_r; c < chunks; c += p.TPR) {
+          int lx, qq;
+          p.fd_Q8.divmod(c, lx, qq);
+          const int x = ix0 + lx;
+          const bool ok = row_ok && x >= 0 && x < p.W && 4 * qq < p.CinS;
+          cp_async16(srow + lx * p.KS + 4 * qq, ok ? grow + lx * p.CinS + 4 * qq : p.in, ok);
+        }
       }
     }
     cp_async_wait_all();
