@@ -50,7 +50,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
@@ -179,20 +179,21 @@ def main():
             raise RuntimeError(lib.fdt_last_error(h).decode())
 
     # ---- device-resident throughput -----------------------------------------------------------------
+    # nvidia-smi needs ~100 ms per sample: it runs from the warm-up to the end of the e2e phase (the same
+    # kernels under the same load) so that even a short timed region yields under-load samples
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         step_device()
     lib.fdt_synchronize(h)
     launches_per_step = int(lib.fdt_last_launch_count(h))
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
     ms = C.c_float()
     lib.fdt_timer_begin(h)
     for _ in range(args.steps):
         step_device()
     lib.fdt_timer_end(h, C.byref(ms))
     barrier()
-    clocks = sampler.stop()
     t_ms = sharding.max_over_ranks(float(ms.value), world, torch.device("cuda", local))
     value = world * B * args.steps / (t_ms / 1e3)
     # face count of the last step (also proves the work was done)
@@ -243,6 +244,9 @@ def main():
                "note": "fdt_detect_batch on pinned host frames; only the source rows the INTER_LINEAR taps read (2 of every 10) are uploaded, by one strided DMA per chunk"}
         lib.fdt_free_pinned(pin); lib.fdt_free_pinned(out_faces); lib.fdt_free_pinned(out_counts)
 
+    clocks = sampler.stop()
+    clocks["window"] = "warm-up + timed steps + e2e steps"
+
     # ---- per-kernel timing + roofline of the dominant kernel (rank 0) ----------------------------------------
     roofline, kernels = None, None
     if rank == 0:
@@ -275,7 +279,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         det.dispose()
-        r = cpu_reference(1, 1, args.cpu_sample or 1024)
+        r = cpu_reference(2, 1, args.cpu_sample or 2048)
         cpu = {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
     if rank == 0:
