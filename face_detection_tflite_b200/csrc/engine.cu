@@ -169,10 +169,11 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         p.fd_Q8 = FastDiv(st.K8 / 4); p.fd_IW = FastDiv(st.IW); p.fd_IH = FastDiv(st.IH); p.fd_TW = FastDiv(st.TW);
         p.fd_thw = FastDiv(st.TH * st.TW); p.fd_tpg = FastDiv(st.tilesX * st.tilesY); p.fd_tilesX = FastDiv(st.tilesX);
         p.fd_nstrips = FastDiv(st.TH / st.RS); p.fd_nslots = FastDiv(st.G * st.TH * st.TW);
+        p.n_chunks = st.G * st.IH * st.IW * (st.K8 / 4);
+        p.n_items = st.has_dw ? st.G * (st.K8 / 4) * (st.TH / st.RS) * st.TW : 0;
         {
-          int nrows = st.G * st.IH, lg = 0;
-          while ((256 >> (lg + 1)) >= nrows && lg < 5) ++lg;   // largest power of two with 256/TPR >= nrows (<= 32)
-          p.TPR_log2 = lg; p.TPR = 1 << lg;
+          long long in = (long long)st.G * st.IH * st.IW * st.KS, tail = (long long)(128 - st.a_rows) * st.K8;
+          p.in_floats = (int)((std::max(in, tail) + 3) / 4 * 4);
         }
         p.smem_bytes = st.smem;
         launch_dwpw_tc(p, B, s, cta_cap(st.smem, 256));

@@ -133,7 +133,7 @@ struct DwPwTcP {
   const float* wB;          // [Npad x K8] in the UMMA K-major core-matrix layout
   const float* bias; const float* alpha;   // [Npad]
   int act, Npad, tmem_cols, a_rows, RS;
-  int TPR, TPR_log2;        // threads sharing one tile row while staging (power of two)
+  int in_floats, n_chunks, n_items;   // staged tile size (floats), staging-table / depthwise-table entries
   const float* res; long long res_istride; int res_H, res_W, res_C, res_Cs, res_pool, res_mode, res_lim;
   int TH, TW, G, IH, IW, tilesX, tilesY;
   FastDiv fd_Q8, fd_IW, fd_IH, fd_TW, fd_thw, fd_tpg, fd_tilesX, fd_nstrips, fd_nslots;

@@ -7,10 +7,19 @@
 //   epilogue: tcgen05.ld 32 lanes x 8 columns per warp, + bias + residual (from the staged tile,
 //   optional 2x2 max-pool, zero channel pad) + ReLU/PReLU, float4 stores.
 //
+// The kernel is persistent and every tile of a layer has the same geometry, so all index
+// arithmetic is done once per CTA: a staging table (one entry per 16-byte chunk of the input tile:
+// global offset relative to the tile origin, shared-memory offset, tile-local coordinates for the
+// border test) and a depthwise table (one entry per work item: window origin, first output slot,
+// channel quad) live in shared memory, and each thread keeps its epilogue pixel in registers.  Per
+// tile a chunk then costs ~12 instructions and the depthwise loop is pure LDS / FFMA / STS.
+//
 // Precision: the detector weights are fp16-origin, hence exact in TF32; the activation is split as
 // a = hi + lo with hi = a & 0xFFFFE000 (exact) and lo = a - hi (exact in fp32, |lo| < 2^-10 |a|), so the
 // only loss is the hardware's truncation of lo to TF32: <= 2^-21 relative per product, i.e. fp32-grade
 // (measured 3e-7..9e-7 of max|ref| in tools/probe/tc_probe.cu vs 2e-7..3e-7 for an fp32 FMA chain).
+#include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <utility>
@@ -25,15 +34,9 @@ constexpr uint32_t kLBO = 128;   // bytes between the two 16-byte K chunks of on
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ float act1(float v, int act, float alpha) {
-  if (act == kActRelu) return fmaxf(v, 0.f);
-  if (act == kActPrelu) return v >= 0.f ? v : v * alpha;
-  return v;
-}
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
-  int sz = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(sz));
+__device__ __forceinline__ void cp_async16_u32(uint32_t smem_dst, const void* gmem_src, bool valid) {
+  int sz = valid ? 16 : 0;   // src-size 0 => 16 bytes of zeros (TFLite SAME zero padding)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_dst), "l"(gmem_src), "r"(sz));
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n" ::);
@@ -57,15 +60,24 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t 
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc));
 }
 
-__device__ __forceinline__ void split_store(float* sAhi, float* sAlo, size_t off, float4 a) {
+__device__ __forceinline__ void split_store(float* sAhi, float* sAlo, uint32_t off_floats, float4 a) {
   float4 hi, lo;
   hi.x = __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u); lo.x = a.x - hi.x;
   hi.y = __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u); lo.y = a.y - hi.y;
   hi.z = __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u); lo.z = a.z - hi.z;
   hi.w = __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u); lo.w = a.w - hi.w;
-  *reinterpret_cast<float4*>(sAhi + off) = hi;
-  *reinterpret_cast<float4*>(sAlo + off) = lo;
+  *reinterpret_cast<float4*>(sAhi + off_floats) = hi;
+  *reinterpret_cast<float4*>(sAlo + off_floats) = lo;
 }
+
+__device__ __forceinline__ void fma4(float4& a, const float4& v, const float4& w) {
+  a.x = fmaf(v.x, w.x, a.x); a.y = fmaf(v.y, w.y, a.y); a.z = fmaf(v.z, w.z, a.z); a.w = fmaf(v.w, w.w, a.w);
+}
+__device__ __forceinline__ float4 max4(const float4& a, const float4& b) {
+  return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+__device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
 #ifndef FDT_TC_MINB
 #define FDT_TC_MINB 1
@@ -77,21 +89,49 @@ __global__ void __launch_bounds__(kTcThreads, FDT_TC_MINB) k_dwpw_tc(DwPwTcP p, 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Q8 = p.K8 >> 2;                       // 16-byte K chunks per row
   const uint32_t SBO = (uint32_t)Q8 * 128u;       // bytes between 8-row groups
-  const int in_elems = p.G * p.IH * p.IW * p.KS;
   float* sB = smem;                               // [Npad x K8] canonical
   float* sBias = sB + (size_t)p.Npad * p.K8;      // [Npad]
   float* sAlpha = sBias + p.Npad;                 // [Npad]
-  float* sAhi = sAlpha + p.Npad;                  // [a_rows x K8] canonical
+  float* sDw = sAlpha + p.Npad;                   // [10][K8]: 9 taps + bias
+  float* sAhi = sDw + (p.has_dw ? 10 * p.K8 : 0); // [a_rows x K8] canonical
   float* sAlo = sAhi + (size_t)p.a_rows * p.K8;
   float* sIn = sAlo + (size_t)p.a_rows * p.K8;    // [G][IH][IW][KS]
+  uint2* stab = reinterpret_cast<uint2*>(sIn + p.in_floats);   // staging table [n_chunks]
+  uint2* dtab = stab + p.n_chunks;                              // depthwise table [n_items]
   const int thw = p.TH * p.TW;
   const int nslots = p.G * thw;
 
-  // ---- prologue: weights (already in canonical layout in global memory), bias, barrier, TMEM
-  for (int i = tid; i < p.Npad * Q8; i += kTcThreads) cp_async16(sB + 4 * (size_t)i, p.wB + 4 * (size_t)i, true);
+  // ---- prologue: weights, bias, tables, barrier, TMEM ------------------------------------------------
+  const uint32_t sB_u32 = smem_u32(sB);
+  for (int i = tid; i < p.Npad * Q8; i += kTcThreads) cp_async16_u32(sB_u32 + 16u * i, p.wB + 4 * (size_t)i, true);
   for (int i = tid; i < p.Npad; i += kTcThreads) {
     sBias[i] = p.bias[i];
     sAlpha[i] = p.alpha ? p.alpha[i] : 0.f;
+  }
+  if (p.has_dw)
+    for (int i = tid; i < 10 * p.K8; i += kTcThreads) sDw[i] = i < 9 * p.K8 ? p.dww[i] : p.dwb[i - 9 * p.K8];
+  // staging table: chunk i = ((g*IH + ly)*IW + lx)*Q8 + qq
+  for (int i = tid; i < p.n_chunks; i += kTcThreads) {
+    int pix, qq, gy, lx, g, ly;
+    p.fd_Q8.divmod(i, pix, qq);
+    p.fd_IW.divmod(pix, gy, lx);
+    p.fd_IH.divmod(gy, g, ly);
+    int goff = 4 * qq < p.CinS ? (int)(g * p.in_istride + ((long long)ly * p.W + lx) * p.CinS + 4 * qq) : -1;
+    uint32_t soff16 = (uint32_t)(((gy * p.IW + lx) * p.KS + 4 * qq) >> 2);
+    stab[i] = make_uint2((uint32_t)goff, soff16 | ((uint32_t)ly << 14) | ((uint32_t)lx << 20) | ((uint32_t)g << 26));
+  }
+  // depthwise table: item = (((g*Q8 + qq)*nstrips + st)*TW + tx)  (tx fastest => conflict-free LDS)
+  if (p.has_dw) {
+    for (int it = tid; it < p.n_items; it += kTcThreads) {
+      int tx, r, st, r2, qq, g;
+      p.fd_TW.divmod(it, r, tx);
+      p.fd_nstrips.divmod(r, r2, st);
+      p.fd_Q8.divmod(r2, g, qq);
+      const int tyb = st * p.RS;
+      uint32_t in_off = (uint32_t)(((g * p.IH + tyb * p.s) * p.IW + tx * p.s) * p.KS + 4 * qq);
+      uint32_t slot0 = (uint32_t)(g * thw + tyb * p.TW + tx);
+      dtab[it] = make_uint2(in_off, slot0 | ((uint32_t)qq << 8));
+    }
   }
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
@@ -101,6 +141,19 @@ __global__ void __launch_bounds__(kTcThreads, FDT_TC_MINB) k_dwpw_tc(DwPwTcP p, 
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)p.tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
+  // epilogue pixel of this thread (fixed for the whole kernel)
+  const int lq = warp & 3, half = warp >> 2;
+  const int slot = lq * 32 + lane;
+  int e_g, e_r, e_ty, e_tx;
+  p.fd_thw.divmod(slot, e_g, e_r);
+  p.fd_TW.divmod(e_r, e_ty, e_tx);
+  const bool slot_ok = slot < nslots;
+  const long long o_rel = slot_ok ? (long long)e_g * p.out_istride + ((long long)e_ty * p.OW + e_tx) * p.CoutS : 0;
+  const int rs = p.res_pool ? 2 : 1;
+  const float* res_s = sIn + (slot_ok ? (((size_t)e_g * p.IH + e_ty * rs + p.dpt) * p.IW + e_tx * rs + p.dpl) * p.KS : 0);
+  const uint32_t row_f = (uint32_t)p.IW * p.KS;          // floats per staged row
+  const uint32_t sIn_u32 = smem_u32(sIn);
+
   cp_async_wait_all();
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -117,106 +170,81 @@ __global__ void __launch_bounds__(kTcThreads, FDT_TC_MINB) k_dwpw_tc(DwPwTcP p, 
     const int ty0 = tyi * p.TH, tx0 = txi * p.TW;
     const int b0 = grp * p.G;
     const int iy0 = ty0 * p.s - p.dpt, ix0 = tx0 * p.s - p.dpl;
-    // ---- stage the input tile (+halo); zero outside the image and in the K padding lanes.
-    //      TPR threads share one tile row: the row's 64-bit base and the y / batch bounds are computed
-    //      once, each 16-byte chunk then costs one FastDiv, an x bound check and two adds.
+    // ---- stage the input tile (+halo): table-driven cp.async, zero fill outside the image
     {
-      const int nrows = p.G * p.IH;
-      const int lane_r = tid & (p.TPR - 1);
-      const int chunks = p.IW * Q8;
-      for (int r = tid >> p.TPR_log2; r < nrows; r += (kTcThreads >> p.TPR_log2)) {
-        int g, ly;
-        p.fd_IH.divmod(r, g, ly);
-        const int b = b0 + g, y = iy0 + ly;
-        const bool row_ok = b < B && y >= 0 && y < p.H;
-        const float* grow = p.in + (size_t)(row_ok ? b : 0) * p.in_istride + ((long long)(row_ok ? y : 0) * p.W + ix0) * p.CinS;
-        float* srow = sIn + (size_t)r * p.IW * p.KS;
-        for (int c = lane_r; c < chunks; c += p.TPR) {
-          int lx, qq;
-          p.fd_Q8.divmod(c, lx, qq);
-          const int x = ix0 + lx;
-          const bool ok = row_ok && x >= 0 && x < p.W && 4 * qq < p.CinS;
-          cp_async16(srow + lx * p.KS + 4 * qq, ok ? grow + lx * p.CinS + 4 * qq : p.in, ok);
-        }
+      const float* tbase = p.in + (long long)b0 * p.in_istride + ((long long)iy0 * p.W + ix0) * p.CinS;
+      const unsigned uH = (unsigned)p.H, uW = (unsigned)p.W;
+      const int nb = B - b0;
+      for (int i = tid; i < p.n_chunks; i += kTcThreads) {
+        const uint2 e = stab[i];
+        const int goff = (int)e.x;
+        const unsigned y = (unsigned)(iy0 + (int)((e.y >> 14) & 63u));
+        const unsigned x = (unsigned)(ix0 + (int)((e.y >> 20) & 63u));
+        const bool ok = goff >= 0 && y < uH && x < uW && (int)(e.y >> 26) < nb;
+        cp_async16_u32(sIn_u32 + ((e.y & 0x3FFFu) << 4), ok ? tbase + goff : p.in, ok);
       }
     }
     cp_async_wait_all();
     __syncthreads();
     // ---- A operand: depthwise 3x3 (or plain copy) -> hi/lo split -> canonical layout
     if (p.has_dw) {
-      // item = (g, qq, row strip of RS outputs, tx); tx fastest => conflict-free smem reads
-      const int nstrips = p.TH / p.RS;
-      const int nitems = p.G * Q8 * nstrips * p.TW;
-      for (int it = tid; it < nitems; it += kTcThreads) {
-        int tx, r, st, r2, qq, g;
-        p.fd_TW.divmod(it, r, tx);
-        p.fd_nstrips.divmod(r, r2, st);
-        p.fd_Q8.divmod(r2, g, qq);
+      for (int it = tid; it < p.n_items; it += kTcThreads) {
+        const uint2 e = dtab[it];
+        const uint32_t qq = e.y >> 8;
+        uint32_t sl = e.y & 0xFFu;
+        const float* wq = sDw + 4 * qq;
         float4 w[9];
 #pragma unroll
-        for (int t = 0; t < 9; ++t) w[t] = *reinterpret_cast<const float4*>(p.dww + (size_t)t * p.K8 + 4 * qq);
-        const float4 bias = *reinterpret_cast<const float4*>(p.dwb + 4 * qq);
-        const size_t rstride = (size_t)p.IW * p.KS;
-        const int tyb = st * p.RS;
-        const float* base = sIn + ((size_t)g * p.IH * p.IW + (size_t)tyb * p.s * p.IW + (size_t)tx * p.s) * p.KS + 4 * qq;
+        for (int t = 0; t < 9; ++t) w[t] = ld4(wq + t * p.K8);
+        const float4 bias = ld4(wq + 9 * p.K8);
+        const float* base = sIn + e.x;
+        const uint32_t aq = qq * kLBO;
         if (p.s == 1) {
           float4 r0[3], r1[3], rr[3];
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
-            r0[kx] = *reinterpret_cast<const float4*>(base + (size_t)kx * p.KS);
-            r1[kx] = *reinterpret_cast<const float4*>(base + rstride + (size_t)kx * p.KS);
+            r0[kx] = ld4(base + kx * p.KS);
+            r1[kx] = ld4(base + row_f + kx * p.KS);
           }
+          const float* nrow = base + 2 * row_f;
           for (int t = 0; t < p.RS; ++t) {
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx)
-              rr[kx] = *reinterpret_cast<const float4*>(base + (size_t)(t + 2) * rstride + (size_t)kx * p.KS);
+            for (int kx = 0; kx < 3; ++kx) rr[kx] = ld4(nrow + kx * p.KS);
             float4 a = bias;
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              a.x = fmaf(r0[kx].x, w[kx].x, a.x); a.y = fmaf(r0[kx].y, w[kx].y, a.y);
-              a.z = fmaf(r0[kx].z, w[kx].z, a.z); a.w = fmaf(r0[kx].w, w[kx].w, a.w);
-            }
+            for (int kx = 0; kx < 3; ++kx) fma4(a, r0[kx], w[kx]);
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              a.x = fmaf(r1[kx].x, w[3 + kx].x, a.x); a.y = fmaf(r1[kx].y, w[3 + kx].y, a.y);
-              a.z = fmaf(r1[kx].z, w[3 + kx].z, a.z); a.w = fmaf(r1[kx].w, w[3 + kx].w, a.w);
-            }
+            for (int kx = 0; kx < 3; ++kx) fma4(a, r1[kx], w[3 + kx]);
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              a.x = fmaf(rr[kx].x, w[6 + kx].x, a.x); a.y = fmaf(rr[kx].y, w[6 + kx].y, a.y);
-              a.z = fmaf(rr[kx].z, w[6 + kx].z, a.z); a.w = fmaf(rr[kx].w, w[6 + kx].w, a.w);
-            }
-            int slot = g * thw + (tyb + t) * p.TW + tx;
-            split_store(sAhi, sAlo, ((size_t)(slot >> 3) * SBO + (size_t)qq * kLBO + (size_t)(slot & 7) * 16) >> 2, a);
+            for (int kx = 0; kx < 3; ++kx) fma4(a, rr[kx], w[6 + kx]);
+            split_store(sAhi, sAlo, ((sl >> 3) * SBO + aq + (sl & 7u) * 16u) >> 2, a);
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) { r0[kx] = r1[kx]; r1[kx] = rr[kx]; }
+            nrow += row_f;
+            sl += p.TW;
           }
         } else {
+          const float* row = base;
           for (int t = 0; t < p.RS; ++t) {
             float4 a = bias;
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
-              const float* row = base + (size_t)(t * p.s + ky) * rstride;
 #pragma unroll
-              for (int kx = 0; kx < 3; ++kx) {
-                const float4 v = *reinterpret_cast<const float4*>(row + (size_t)kx * p.KS);
-                const float4 ww = w[ky * 3 + kx];
-                a.x = fmaf(v.x, ww.x, a.x); a.y = fmaf(v.y, ww.y, a.y);
-                a.z = fmaf(v.z, ww.z, a.z); a.w = fmaf(v.w, ww.w, a.w);
-              }
+              for (int kx = 0; kx < 3; ++kx) fma4(a, ld4(row + ky * row_f + kx * p.KS), w[ky * 3 + kx]);
             }
-            int slot = g * thw + (tyb + t) * p.TW + tx;
-            split_store(sAhi, sAlo, ((size_t)(slot >> 3) * SBO + (size_t)qq * kLBO + (size_t)(slot & 7) * 16) >> 2, a);
+            split_store(sAhi, sAlo, ((sl >> 3) * SBO + aq + (sl & 7u) * 16u) >> 2, a);
+            row += 2 * row_f;
+            sl += p.TW;
           }
         }
       }
     } else {
-      // pointwise only: slot s <-> staged pixel s (IH = TH, IW = TW)
+      // pointwise only: slot s <-> staged pixel s (IH = TH, IW = TW); slot fastest
       for (int it = tid; it < nslots * Q8; it += kTcThreads) {
-        int qq, slot;
-        p.fd_nslots.divmod(it, qq, slot);      // slot fastest
-        const float4 a = *reinterpret_cast<const float4*>(sIn + (size_t)slot * p.KS + 4 * qq);
-        split_store(sAhi, sAlo, ((size_t)(slot >> 3) * SBO + (size_t)qq * kLBO + (size_t)(slot & 7) * 16) >> 2, a);
+        int qq, sl;
+        p.fd_nslots.divmod(it, qq, sl);
+        const float4 a = ld4(sIn + (size_t)sl * p.KS + 4 * qq);
+        split_store(sAhi, sAlo, (((uint32_t)sl >> 3) * SBO + (uint32_t)qq * kLBO + ((uint32_t)sl & 7u) * 16u) >> 2, a);
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -224,10 +252,10 @@ __global__ void __launch_bounds__(kTcThreads, FDT_TC_MINB) k_dwpw_tc(DwPwTcP p, 
     // ---- tensor-core GEMM: D[128 x Npad] (TMEM) = (A_hi + A_lo)[128 x K8] * W[Npad x K8]^T
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_hi = smem_u32(sAhi), a_lo = smem_u32(sAlo), bb = smem_u32(sB);
+      const uint32_t a_hi = smem_u32(sAhi), a_lo = smem_u32(sAlo);
       const int ksteps = p.K8 >> 3;
       for (int ks = 0; ks < ksteps; ++ks) {
-        const uint64_t db = make_desc(bb + ks * 2 * kLBO, SBO);
+        const uint64_t db = make_desc(sB_u32 + ks * 2 * kLBO, SBO);
         mma_tf32(tmem_base, make_desc(a_hi + ks * 2 * kLBO, SBO), db, idesc, ks > 0 ? 1u : 0u);
         mma_tf32(tmem_base, make_desc(a_lo + ks * 2 * kLBO, SBO), db, idesc, 1u);
       }
@@ -244,15 +272,10 @@ __global__ void __launch_bounds__(kTcThreads, FDT_TC_MINB) k_dwpw_tc(DwPwTcP p, 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // ---- epilogue: warp w owns TMEM lanes 32*(w%4).., and the column half w/4
     {
-      const int lq = warp & 3, half = warp >> 2;
       const int ncol = p.Npad >> 1;
-      const int slot = lq * 32 + lane;
-      int g, r, ty, tx;
-      p.fd_thw.divmod(slot, g, r);
-      p.fd_TW.divmod(r, ty, tx);
-      const int oy = ty0 + ty, ox = tx0 + tx, b = b0 + g;
-      const bool valid = slot < nslots && b < B && oy < p.OH && ox < p.OW;
-      float* orow = p.out + (size_t)(valid ? b : 0) * p.out_istride + ((size_t)(valid ? oy : 0) * p.OW + (valid ? ox : 0)) * p.CoutS;
+      const int oy = ty0 + e_ty, ox = tx0 + e_tx, b = b0 + e_g;
+      const bool valid = slot_ok && b < B && oy < p.OH && ox < p.OW;
+      float* orow = p.out + (long long)b0 * p.out_istride + ((long long)ty0 * p.OW + tx0) * p.CoutS + o_rel;
       const float* rbase = p.res_mode == 2 ? p.res + (size_t)(valid ? b : 0) * p.res_istride : nullptr;
       for (int cc = 0; cc < ncol; cc += 8) {
         const int c = half * ncol + cc;
@@ -262,64 +285,65 @@ __global__ void __launch_bounds__(kTcThreads, FDT_TC_MINB) k_dwpw_tc(DwPwTcP p, 
                      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]) : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (!valid || c >= p.CoutS) continue;
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(u[j]) + sBias[c + j];
+        const float4 b0v = ld4(sBias + c), b1v = ld4(sBias + c + 4);
+        float4 v0 = make_float4(__uint_as_float(u[0]) + b0v.x, __uint_as_float(u[1]) + b0v.y, __uint_as_float(u[2]) + b0v.z, __uint_as_float(u[3]) + b0v.w);
+        float4 v1 = make_float4(__uint_as_float(u[4]) + b1v.x, __uint_as_float(u[5]) + b1v.y, __uint_as_float(u[6]) + b1v.z, __uint_as_float(u[7]) + b1v.w);
         if (p.res_mode == 1) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int ch = c + 4 * h;
-            if (ch >= p.res_lim) continue;      // channels >= Cin: zero channel pad of the residual
-            float4 rv;
-            if (p.res_pool) {
-              const float* rb = sIn + (((size_t)g * p.IH + 2 * ty + p.dpt) * p.IW + 2 * tx + p.dpl) * p.KS + ch;
-              const float4 m0 = *reinterpret_cast<const float4*>(rb);
-              const float4 m1 = *reinterpret_cast<const float4*>(rb + p.KS);
-              const float4 m2 = *reinterpret_cast<const float4*>(rb + (size_t)p.IW * p.KS);
-              const float4 m3 = *reinterpret_cast<const float4*>(rb + (size_t)p.IW * p.KS + p.KS);
-              rv.x = fmaxf(fmaxf(m0.x, m1.x), fmaxf(m2.x, m3.x)); rv.y = fmaxf(fmaxf(m0.y, m1.y), fmaxf(m2.y, m3.y));
-              rv.z = fmaxf(fmaxf(m0.z, m1.z), fmaxf(m2.z, m3.z)); rv.w = fmaxf(fmaxf(m0.w, m1.w), fmaxf(m2.w, m3.w));
-            } else {
-              rv = *reinterpret_cast<const float4*>(sIn + (((size_t)g * p.IH + ty + p.dpt) * p.IW + tx + p.dpl) * p.KS + ch);
-            }
-            v[4 * h + 0] += rv.x; v[4 * h + 1] += rv.y; v[4 * h + 2] += rv.z; v[4 * h + 3] += rv.w;
+          // residual straight from the staged tile (channels >= Cin are the zero channel pad)
+          if (p.res_pool) {
+            const float* r1p = res_s + p.KS;
+            const float* r2p = res_s + row_f;
+            const float* r3p = r2p + p.KS;
+            if (c < p.res_lim) add4(v0, max4(max4(ld4(res_s + c), ld4(r1p + c)), max4(ld4(r2p + c), ld4(r3p + c))));
+            if (c + 4 < p.res_lim) add4(v1, max4(max4(ld4(res_s + c + 4), ld4(r1p + c + 4)), max4(ld4(r2p + c + 4), ld4(r3p + c + 4))));
+          } else {
+            if (c < p.res_lim) add4(v0, ld4(res_s + c));
+            if (c + 4 < p.res_lim) add4(v1, ld4(res_s + c + 4));
           }
         } else if (p.res_mode == 2) {
+          float rv[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int ch = c + j;
+            rv[j] = 0.f;
             if (ch >= p.res_C) continue;
-            float rv;
             if (p.res_pool) {
-              rv = -INFINITY;
+              float m = -INFINITY;
 #pragma unroll
               for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
                 for (int dx = 0; dx < 2; ++dx) {
                   int ry = 2 * oy + dy, rx = 2 * ox + dx;
-                  if (ry < p.res_H && rx < p.res_W) rv = fmaxf(rv, rbase[((size_t)ry * p.res_W + rx) * p.res_Cs + ch]);
+                  if (ry < p.res_H && rx < p.res_W) m = fmaxf(m, rbase[((size_t)ry * p.res_W + rx) * p.res_Cs + ch]);
                 }
+              rv[j] = m;
             } else {
-              rv = rbase[((size_t)oy * p.res_W + ox) * p.res_Cs + ch];
+              rv[j] = rbase[((size_t)oy * p.res_W + ox) * p.res_Cs + ch];
             }
-            v[j] += rv;
           }
+          add4(v0, make_float4(rv[0], rv[1], rv[2], rv[3]));
+          add4(v1, make_float4(rv[4], rv[5], rv[6], rv[7]));
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = act1(v[j], p.act, sAlpha[c + j]);
+        if (p.act == kActRelu) {
+          v0 = max4(v0, make_float4(0.f, 0.f, 0.f, 0.f));
+          v1 = max4(v1, make_float4(0.f, 0.f, 0.f, 0.f));
+        } else if (p.act == kActPrelu) {
+          const float4 a0 = ld4(sAlpha + c), a1 = ld4(sAlpha + c + 4);
+          v0.x = v0.x >= 0.f ? v0.x : v0.x * a0.x; v0.y = v0.y >= 0.f ? v0.y : v0.y * a0.y;
+          v0.z = v0.z >= 0.f ? v0.z : v0.z * a0.z; v0.w = v0.w >= 0.f ? v0.w : v0.w * a0.w;
+          v1.x = v1.x >= 0.f ? v1.x : v1.x * a1.x; v1.y = v1.y >= 0.f ? v1.y : v1.y * a1.y;
+          v1.z = v1.z >= 0.f ? v1.z : v1.z * a1.z; v1.w = v1.w >= 0.f ? v1.w : v1.w * a1.w;
+        }
         if (p.vec_store) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int ch = c + 4 * h;
-            if (ch >= p.CoutS) continue;
-            float4 o = make_float4(ch + 0 < p.Cout ? v[4 * h] : 0.f, ch + 1 < p.Cout ? v[4 * h + 1] : 0.f,
-                                   ch + 2 < p.Cout ? v[4 * h + 2] : 0.f, ch + 3 < p.Cout ? v[4 * h + 3] : 0.f);
-            *reinterpret_cast<float4*>(orow + ch) = o;
-          }
+          // lanes >= Cout need no masking: their weights and bias are zero and the residual is the zero
+          // channel pad there, so they come out as exact zeros
+          *reinterpret_cast<float4*>(orow + c) = v0;
+          if (c + 4 < p.CoutS) *reinterpret_cast<float4*>(orow + c + 4) = v1;
         } else {
+          const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            if (c + j < p.CoutS) orow[c + j] = c + j < p.Cout ? v[j] : 0.f;
+            if (c + j < p.Cout) orow[c + j] = vv[j];
         }
       }
     }
@@ -335,10 +359,13 @@ __global__ void __launch_bounds__(kTcThreads, FDT_TC_MINB) k_dwpw_tc(DwPwTcP p, 
 }  // namespace
 
 void launch_dwpw_tc(const DwPwTcP& p, int B, cudaStream_t s, int max_ctas) {
+  // grid = resident CTAs: 148 SMs x the occupancy the kernel really gets at this shared-memory size
   static std::mutex mu;
+  static std::map<std::pair<int, size_t>, int> occ;
   static std::map<int, size_t> cur;
   int dev = 0;
   cudaGetDevice(&dev);
+  int per_sm = 1;
   {
     std::lock_guard<std::mutex> g(mu);
     size_t& c = cur[dev];
@@ -346,10 +373,20 @@ void launch_dwpw_tc(const DwPwTcP& p, int B, cudaStream_t s, int max_ctas) {
       cudaFuncSetAttribute(k_dwpw_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
       c = p.smem_bytes;
     }
+    auto key = std::make_pair(dev, p.smem_bytes);
+    auto it = occ.find(key);
+    if (it == occ.end()) {
+      int nb = 1;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_dwpw_tc, kTcThreads, p.smem_bytes) != cudaSuccess || nb < 1) nb = 1;
+      it = occ.emplace(key, nb).first;
+    }
+    per_sm = it->second;
   }
+  (void)max_ctas;
   int groups = (B + p.G - 1) / p.G;
   int ntiles = groups * p.tilesX * p.tilesY;
-  int grid = ntiles < max_ctas ? ntiles : max_ctas;
+  static const int mult = [] { const char* e = std::getenv("FDT_TC_GRIDMULT"); return e ? std::atoi(e) : 2; }();   // 2 waves of CTAs: measured best (de-synchronises the CTAs' load / compute phases)
+  int grid = std::min(ntiles, 148 * per_sm * (mult > 0 ? mult : 1));
   if (grid < 1) grid = 1;
   k_dwpw_tc<<<grid, kTcThreads, p.smem_bytes, s>>>(p, B, ntiles);
 }

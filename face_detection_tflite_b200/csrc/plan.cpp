@@ -328,11 +328,11 @@ struct Builder {
       s.TM = 1; s.NPG = Pn;                       // plan_spatial reads TM * NPG as the slot budget
       int bestTH = 0, bestTW = 0, bestG = 1;
       double best = -1;
-      if (OH * OW <= Pn) {
-        bestTH = OH; bestTW = OW; bestG = Pn / (OH * OW);
+      if (OH * OW <= Pn && OW <= 30) {
+        bestTH = OH; bestTW = OW; bestG = std::min(63, Pn / (OH * OW));
       } else {
-        for (int TW = std::min(OW, Pn); TW >= 1; --TW) {
-          int TH = std::min(OH, Pn / TW);
+        for (int TW = std::min(std::min(OW, Pn), 30); TW >= 1; --TW) {
+          int TH = std::min(std::min(OH, Pn / TW), 30);
           if (TH < 1) continue;
           double tiles = (double)((OH + TH - 1) / TH) * ((OW + TW - 1) / TW);
           double util = (double)OH * OW / (tiles * Pn);
@@ -350,13 +350,17 @@ struct Builder {
       s.a_rows = ru(nslots, 8);
       s.RS = 1;
       for (int rs : {8, 4, 2}) if (s.TH % rs == 0 && s.G * (s.K8 / 4) * (s.TH / rs) * s.TW >= 256) { s.RS = rs; break; }
-      size_t head = (size_t)s.Npad * s.K8 + 2 * (size_t)s.Npad;
+      if (s.IH > 63 || s.IW > 63 || s.G > 63 || nslots > 255) continue;     // staging-table field widths
+      size_t head = (size_t)s.Npad * s.K8 + 2 * (size_t)s.Npad + (s.has_dw ? 10 * (size_t)s.K8 : 0);
       size_t a = 2 * (size_t)s.a_rows * s.K8;
       size_t in = (size_t)s.G * s.IH * s.IW * s.KS;
       // the MMA always reads 128 rows of each A tile: keep those addresses inside the allocation
       size_t need_tail = (size_t)(128 - s.a_rows) * s.K8;      // floats past the end of A_lo
       if (in < need_tail) in = need_tail;
-      s.smem = (head + a + in) * 4 + 128;
+      in = (in + 3) / 4 * 4;
+      size_t n_chunks = (size_t)s.G * s.IH * s.IW * (s.K8 / 4);
+      size_t n_items = s.has_dw ? (size_t)s.G * (s.K8 / 4) * (s.TH / s.RS) * s.TW : 0;
+      s.smem = (head + a + in) * 4 + (n_chunks + n_items) * 8 + 128;
       if (s.smem <= 220 * 1024) { s.kind = kStepDwPwTc; *st = s; return true; }
     }
     return false;
