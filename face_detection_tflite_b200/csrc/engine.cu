@@ -94,6 +94,18 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         launch_stem(p, B, s, cta_cap(st.smem, 32 * (st.NC / 4)));
         break;
       }
+      case kStepStemTc: {
+        StemTcP p;
+        const PTensor& it = plan_.tensors[st.in];
+        p.in8 = in_u8; p.H = it.H; p.W = it.W; p.OH = out.H; p.OW = out.W;
+        p.kw = st.kw; p.pt = st.pt; p.pl = st.pl;
+        p.out = out.p; p.out_istride = out.istride; p.Cout = st.Cout; p.CoutS = out.Cs;
+        p.vec_store = (out.Cs % 4 == 0 && out.istride % 4 == 0 && ((size_t)out.p % 16 == 0)) ? 1 : 0;
+        p.wB = blob + st.w; p.bias = blob + st.bias; p.alpha = st.alpha >= 0 ? blob + st.alpha : nullptr;
+        p.act = st.act; p.Npad = st.Npad; p.tmem_cols = st.tmem_cols; p.smem_bytes = st.smem;
+        launch_stem_tc(p, B, s);
+        break;
+      }
       case kStepGemmConv: {
         GemmConvP p;
         const PTensor& it = plan_.tensors[st.in];

@@ -141,6 +141,18 @@ struct DwPwTcP {
 };
 void launch_dwpw_tc(const DwPwTcP& p, int B, cudaStream_t s, int max_ctas);
 
+// ---- stem on tensor cores: im2col GEMM from the u8x4 patch ----
+struct StemTcP {
+  const uint8_t* in8;       // [B][H][W][4] BGRX
+  int H, W, OH, OW, kw, pt, pl;
+  float* out; long long out_istride; int Cout, CoutS, vec_store;
+  const float* wB;          // [Npad x K8] UMMA K-major core-matrix layout, k = (ky*kw + kx)*3 + c
+  const float* bias; const float* alpha;
+  int act, Npad, tmem_cols;
+  size_t smem_bytes;
+};
+void launch_stem_tc(const StemTcP& p, int B, cudaStream_t s);
+
 // ---- detector post-processing: one block per image ----
 struct DecodeP {
   const float* boxes; long long boxes_istride;    // [B][N][16]

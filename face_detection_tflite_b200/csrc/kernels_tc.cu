@@ -356,6 +356,173 @@ __global__ void __launch_bounds__(kTcThreads, FDT_TC_MINB) k_dwpw_tc(DwPwTcP p, 
   }
 }
 
+
+// im2col gather of one half of the K chunks of pixel `prow` (patch origin of the pixel's receptive field)
+template <int KW, int HALF>
+__device__ __forceinline__ void stem_gather(const float* prow, float* sAhi, float* sAlo, uint32_t a_row) {
+  constexpr int PW3 = ((16 - 1) * 2 + KW) * 3, SEG = KW * 3, K = KW * SEG, K8 = (K + 7) / 8 * 8, Q8 = K8 / 4;
+#pragma unroll
+  for (int kk = 0; kk < Q8 / 2; ++kk) {
+    constexpr int dummy = 0; (void)dummy;
+    const int kq = HALF * (Q8 / 2) + kk;
+    float e[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = 4 * kq + j;                       // compile-time after unrolling
+      e[j] = k < K ? prow[(k / SEG) * PW3 + (k % SEG)] : 0.f;
+    }
+    split_store(sAhi, sAlo, a_row + (uint32_t)kq * (kLBO >> 2), make_float4(e[0], e[1], e[2], e[3]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_stem_tc — the KW x KW / stride-2 input convolution (3 channels) as an im2col GEMM on tcgen05:
+// D[128 px x Npad] = A[128 x K8] * W[Npad x K8]^T with K = KW*KW*3 (75 -> 80 for the 5x5 stem).
+// The u8x4 BGRX patch of a tile of 8 x 16 output pixels is normalised (fma(v, 1/127.5, -1), BGR->RGB) into
+// shared memory as dense RGB float triplets; an im2col row is then KW contiguous segments of KW*3
+// floats, gathered, split into TF32 hi + lo and written in the UMMA core-matrix layout.
+template <int KW>
+__global__ void __launch_bounds__(kTcThreads, 2) k_stem_tc(StemTcP p, int B, int ntiles) {
+  constexpr int TH = 8, TW = 16;
+  constexpr int PH = (TH - 1) * 2 + KW, PW = (TW - 1) * 2 + KW, PW3 = PW * 3;
+  constexpr int SEG = KW * 3, K = KW * SEG, K8 = (K + 7) / 8 * 8, Q8 = K8 / 4;
+  constexpr uint32_t SBO = (uint32_t)Q8 * 128u;
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* sB = smem;                               // [Npad x K8] canonical
+  float* sBias = sB + (size_t)p.Npad * K8;        // [Npad]
+  float* sAlpha = sBias + p.Npad;
+  float* sAhi = sAlpha + p.Npad;                  // [128 x K8] canonical
+  float* sAlo = sAhi + 128 * K8;
+  float* sP = sAlo + 128 * K8;                    // [PH][PW*3] normalised RGB patch
+
+  const uint32_t sB_u32 = smem_u32(sB);
+  for (int i = tid; i < p.Npad * Q8; i += kTcThreads) cp_async16_u32(sB_u32 + 16u * i, p.wB + 4 * (size_t)i, true);
+  for (int i = tid; i < p.Npad; i += kTcThreads) {
+    sBias[i] = p.bias[i];
+    sAlpha[i] = p.alpha ? p.alpha[i] : 0.f;
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)p.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  cp_async_wait_all();
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((128u >> 4) << 24);
+  uint32_t parity = 0;
+  const int tilesX = (p.OW + TW - 1) / TW, tilesY = (p.OH + TH - 1) / TH;
+  const int tiles_per_img = tilesX * tilesY;
+  // this thread's pixel for the im2col gather (slot r) and for the epilogue (slot e)
+  const int r = tid & 127, khalf = tid >> 7;
+  const int r_ty = r >> 4, r_tx = r & 15;
+  const float* prow = sP + (2 * r_ty) * PW3 + 6 * r_tx;
+  const uint32_t a_row = (((uint32_t)r >> 3) * SBO + ((uint32_t)r & 7u) * 16u) >> 2;
+  const int lq = warp & 3, half = warp >> 2;
+  const int eslot = lq * 32 + lane;
+  const int e_ty = eslot >> 4, e_tx = eslot & 15;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int b = tile / tiles_per_img;
+    const int trem = tile - b * tiles_per_img;
+    const int ty0 = (trem / tilesX) * TH, tx0 = (trem % tilesX) * TW;
+    const int iy0 = ty0 * 2 - p.pt, ix0 = tx0 * 2 - p.pl;
+    // ---- patch: u8x4 BGRX -> normalised RGB floats (bgrMatToSignedFloat32, helpers.dart:401-406)
+    const uchar4* img = reinterpret_cast<const uchar4*>(p.in8) + (size_t)b * p.H * p.W;
+    for (int i = tid; i < PH * PW; i += kTcThreads) {
+      const int ly = i / PW, lx = i - ly * PW;
+      const int y = iy0 + ly, x = ix0 + lx;
+      float3 v = make_float3(0.f, 0.f, 0.f);
+      if ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W) {
+        const uchar4 u = img[(size_t)y * p.W + x];
+        v.x = fmaf((float)u.z, 1.0f / 127.5f, -1.0f);
+        v.y = fmaf((float)u.y, 1.0f / 127.5f, -1.0f);
+        v.z = fmaf((float)u.x, 1.0f / 127.5f, -1.0f);
+      }
+      float* d = sP + ly * PW3 + lx * 3;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z;
+    }
+    __syncthreads();
+    // ---- im2col gather -> hi/lo split -> canonical A (thread = pixel r, one half of the K chunks)
+    if (khalf == 0) stem_gather<KW, 0>(prow, sAhi, sAlo, a_row);     // khalf is warp-uniform
+    else stem_gather<KW, 1>(prow, sAhi, sAlo, a_row);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_hi = smem_u32(sAhi), a_lo = smem_u32(sAlo);
+#pragma unroll 1
+      for (int ks = 0; ks < K8 / 8; ++ks) {
+        const uint64_t db = make_desc(sB_u32 + ks * 2 * kLBO, SBO);
+        mma_tf32(tmem_base, make_desc(a_hi + ks * 2 * kLBO, SBO), db, idesc, ks > 0 ? 1u : 0u);
+        mma_tf32(tmem_base, make_desc(a_lo + ks * 2 * kLBO, SBO), db, idesc, 1u);
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
+    }
+    {
+      uint32_t ok = 0;
+      while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(smem_u32(&mbar)), "r"(parity) : "memory");
+      }
+      parity ^= 1u;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+      const int ncol = p.Npad >> 1;
+      const int oy = ty0 + e_ty, ox = tx0 + e_tx;
+      const bool valid = oy < p.OH && ox < p.OW;
+      float* orow = p.out + (size_t)b * p.out_istride + ((size_t)(valid ? oy : 0) * p.OW + (valid ? ox : 0)) * p.CoutS;
+      for (int cc = 0; cc < ncol; cc += 8) {
+        const int c = half * ncol + cc;
+        uint32_t u[8];
+        const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)c;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]) : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (!valid || c >= p.CoutS) continue;
+        const float4 b0v = ld4(sBias + c), b1v = ld4(sBias + c + 4);
+        float4 v0 = make_float4(__uint_as_float(u[0]) + b0v.x, __uint_as_float(u[1]) + b0v.y, __uint_as_float(u[2]) + b0v.z, __uint_as_float(u[3]) + b0v.w);
+        float4 v1 = make_float4(__uint_as_float(u[4]) + b1v.x, __uint_as_float(u[5]) + b1v.y, __uint_as_float(u[6]) + b1v.z, __uint_as_float(u[7]) + b1v.w);
+        if (p.act == kActRelu) {
+          v0 = max4(v0, make_float4(0.f, 0.f, 0.f, 0.f));
+          v1 = max4(v1, make_float4(0.f, 0.f, 0.f, 0.f));
+        } else if (p.act == kActPrelu) {
+          const float4 a0 = ld4(sAlpha + c), a1 = ld4(sAlpha + c + 4);
+          v0.x = v0.x >= 0.f ? v0.x : v0.x * a0.x; v0.y = v0.y >= 0.f ? v0.y : v0.y * a0.y;
+          v0.z = v0.z >= 0.f ? v0.z : v0.z * a0.z; v0.w = v0.w >= 0.f ? v0.w : v0.w * a0.w;
+          v1.x = v1.x >= 0.f ? v1.x : v1.x * a1.x; v1.y = v1.y >= 0.f ? v1.y : v1.y * a1.y;
+          v1.z = v1.z >= 0.f ? v1.z : v1.z * a1.z; v1.w = v1.w >= 0.f ? v1.w : v1.w * a1.w;
+        }
+        if (p.vec_store) {
+          *reinterpret_cast<float4*>(orow + c) = v0;
+          if (c + 4 < p.CoutS) *reinterpret_cast<float4*>(orow + c + 4) = v1;
+        } else {
+          const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (c + j < p.Cout) orow[c + j] = vv[j];
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols));
+  }
+}
+
 }  // namespace
 
 void launch_dwpw_tc(const DwPwTcP& p, int B, cudaStream_t s, int max_ctas) {
@@ -389,6 +556,36 @@ void launch_dwpw_tc(const DwPwTcP& p, int B, cudaStream_t s, int max_ctas) {
   int grid = std::min(ntiles, 148 * per_sm * (mult > 0 ? mult : 1));
   if (grid < 1) grid = 1;
   k_dwpw_tc<<<grid, kTcThreads, p.smem_bytes, s>>>(p, B, ntiles);
+}
+
+template <int KW>
+static void launch_stem_tc_kw(const StemTcP& p, int B, cudaStream_t s) {
+  static std::mutex mu;
+  static std::map<int, int> occ;     // device -> resident CTAs per SM
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int per_sm = 1;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = occ.find(dev);
+    if (it == occ.end()) {
+      cudaFuncSetAttribute(k_stem_tc<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
+      int nb = 1;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_stem_tc<KW>, kTcThreads, p.smem_bytes) != cudaSuccess || nb < 1) nb = 1;
+      it = occ.emplace(dev, nb).first;
+    }
+    per_sm = it->second;
+  }
+  const int tiles = ((p.OW + 15) / 16) * ((p.OH + 7) / 8);
+  const int ntiles = tiles * B;
+  int grid = std::min(ntiles, 148 * per_sm * 2);
+  if (grid < 1) grid = 1;
+  k_stem_tc<KW><<<grid, kTcThreads, p.smem_bytes, s>>>(p, B, ntiles);
+}
+
+void launch_stem_tc(const StemTcP& p, int B, cudaStream_t s) {
+  if (p.kw == 5) launch_stem_tc_kw<5>(p, B, s);
+  else launch_stem_tc_kw<3>(p, B, s);
 }
 
 }  // namespace fdt

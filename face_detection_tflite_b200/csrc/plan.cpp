@@ -455,13 +455,32 @@ struct Builder {
     if (!m.const_f32(conv.in[1], &w)) return fail("conv weights are not constant");
     if (conv.in.size() > 2 && conv.in[2] >= 0) { if (!m.const_f32(conv.in[2], &b)) return fail("conv bias is not constant"); }
     b.resize(st.Cout, 0.f);
-    std::vector<float> wk((size_t)st.KP * st.CoutP, 0.f);
-    for (int co = 0; co < st.Cout; ++co)
-      for (int k = 0; k < st.K; ++k) wk[(size_t)k * st.CoutP + co] = w[(size_t)co * st.K + k];
-    size_t padded = (size_t)st.nchunks * st.NC + 8;
-    st.w = push(wk, wk.size());
-    st.bias = push(b, padded);
-    if (alpha_tf >= 0 && !pack_alpha(alpha_tf, padded, &st.alpha)) return false;
+    if (st.kind == kStepStem && use_tc && tf32_exact(w) && ru(st.Cout, 16) <= 128) {
+      // tensor-core stem: B operand [Npad x K8] in the UMMA K-major core-matrix layout
+      st.kind = kStepStemTc;
+      st.K8 = ru(st.K, 8);
+      st.Npad = ru(st.Cout, 16);
+      st.tmem_cols = 32;
+      while (st.tmem_cols < st.Npad) st.tmem_cols *= 2;
+      const size_t SBO = (size_t)(st.K8 / 4) * 128, LBO = 128;
+      std::vector<float> wb((size_t)st.Npad * st.K8, 0.f);
+      for (int n = 0; n < st.Cout; ++n)
+        for (int k = 0; k < st.K; ++k)
+          wb[((size_t)(n >> 3) * SBO + (size_t)(k >> 2) * LBO + (size_t)(n & 7) * 16 + (size_t)(k & 3) * 4) / 4] = w[(size_t)n * st.K + k];
+      int PH = 14 + st.kw, PW = 30 + st.kw;
+      st.smem = ((size_t)st.Npad * st.K8 + 2 * (size_t)st.Npad + 2 * 128 * (size_t)st.K8 + (size_t)PH * PW * 3) * 4 + 128;
+      st.w = push(wb, wb.size());
+      st.bias = push(b, (size_t)st.Npad + 8);
+      if (alpha_tf >= 0 && !pack_alpha(alpha_tf, (size_t)st.Npad + 8, &st.alpha)) return false;
+    } else {
+      std::vector<float> wk((size_t)st.KP * st.CoutP, 0.f);
+      for (int co = 0; co < st.Cout; ++co)
+        for (int k = 0; k < st.K; ++k) wk[(size_t)k * st.CoutP + co] = w[(size_t)co * st.K + k];
+      size_t padded = (size_t)st.nchunks * st.NC + 8;
+      st.w = push(wk, wk.size());
+      st.bias = push(b, padded);
+      if (alpha_tf >= 0 && !pack_alpha(alpha_tf, padded, &st.alpha)) return false;
+    }
     st.macs = (double)ot.dim(1) * ot.dim(2) * st.K * st.Cout;
     st.name = m.tensors[cur].name;
     F->ok = true;
@@ -675,7 +694,7 @@ bool Plan::build(const TfModel& m, int fuse, std::string* err, bool use_tc) {
 }
 
 std::string Plan::describe() const {
-  static const char* kn[] = {"normalize", "naive_conv", "gemm_conv", "dwpw", "add", "act", "padc", "maxpool", "resize", "stem", "dwpw_tc"};
+  static const char* kn[] = {"normalize", "naive_conv", "gemm_conv", "dwpw", "add", "act", "padc", "maxpool", "resize", "stem", "dwpw_tc", "stem_tc"};
   std::string s;
   char buf[512];
   double macs = 0;

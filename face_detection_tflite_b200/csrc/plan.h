@@ -25,7 +25,7 @@ struct PTensor {
 };
 
 enum StepKind { kStepNormalize, kStepNaiveConv, kStepGemmConv, kStepDwPw, kStepAdd, kStepAct, kStepPadC,
-                kStepMaxPool, kStepResize, kStepStem, kStepDwPwTc };
+                kStepMaxPool, kStepResize, kStepStem, kStepDwPwTc, kStepStemTc };
 
 struct PStep {
   StepKind kind = kStepAct;
