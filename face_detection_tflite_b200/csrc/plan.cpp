@@ -424,17 +424,31 @@ struct Builder {
     st.KP = ru(st.K, 4);
     st.KS = smem_stride(st.KP);
     plan_columns(&st);
-    // shrink the weight chunk until A (128 x KS) + W (KP x NC) fit
-    for (;;) {
-      st.smem = ((size_t)st.TM * st.NPG * st.KS + (size_t)st.KP * st.NC) * 4;
-      if (st.smem <= kSmemLimit) break;
-      int nq = st.NC / 4;
-      if (nq <= 1) return false;
-      nq = (nq + 1) / 2;
-      st.NC = nq * 4;
-      st.nchunks = (st.CoutP + st.NC - 1) / st.NC;
-      st.TM = nq <= 12 ? 4 : 8;
-      st.NPG = 128 / st.TM;
+    // A (P x KS) + W (KP x NC) must fit in shared memory: every weight chunk re-stages the im2col tile,
+    // so shrink the pixel tile (128 -> 64 -> 32) before splitting the output channels any further.
+    {
+      bool fit = false;
+      PStep best = st;
+      int best_chunks = 1 << 30;
+      for (int P = 128; P >= 32; P /= 2) {
+        PStep c = st;
+        plan_columns(&c);
+        for (;;) {
+          c.TM = (c.NC / 4) <= 12 && P >= 128 ? 4 : (P >= 128 ? 8 : 4);
+          c.NPG = P / c.TM;
+          c.smem = ((size_t)P * c.KS + (size_t)c.KP * c.NC) * 4;
+          if (c.smem <= kSmemLimit && c.NPG * (c.NC / 4) <= 384) break;
+          int nq = c.NC / 4;
+          if (nq <= 1) { c.smem = 0; break; }
+          nq = (nq + 1) / 2;
+          c.NC = nq * 4;
+          c.nchunks = (c.CoutP + c.NC - 1) / c.NC;
+        }
+        if (c.smem == 0) continue;
+        if (c.nchunks < best_chunks) { best_chunks = c.nchunks; best = c; fit = true; }
+      }
+      if (!fit) return false;
+      st = best;
     }
     std::vector<int> absorbed;
     int cur = conv.out[0], alpha_tf = -1;
