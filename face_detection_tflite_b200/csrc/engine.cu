@@ -102,7 +102,7 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         p.out = out.p; p.out_istride = out.istride; p.Cout = st.Cout; p.CoutS = out.Cs;
         p.vec_store = (out.Cs % 4 == 0 && out.istride % 4 == 0 && ((size_t)out.p % 16 == 0)) ? 1 : 0;
         p.wB = blob + st.w; p.bias = blob + st.bias; p.alpha = st.alpha >= 0 ? blob + st.alpha : nullptr;
-        p.act = st.act; p.Npad = st.Npad; p.tmem_cols = st.tmem_cols; p.smem_bytes = st.smem;
+        p.act = st.act; p.Npad = st.Npad; p.tmem_cols = st.tmem_cols; p.w_parts = st.w_parts; p.smem_bytes = st.smem;
         launch_stem_tc(p, B, s);
         break;
       }
@@ -125,6 +125,10 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         p.w = blob + st.w; p.bias = blob + st.bias; p.alpha = st.alpha >= 0 ? blob + st.alpha : nullptr;
         p.act = st.act; p.CoutP = st.CoutP; p.NC = st.NC; p.nchunks = st.nchunks;
         p.NPG = st.NPG; p.TM = st.TM; p.smem_bytes = st.smem;
+        p.flat = (!st.in_u8 && out.H == 1 && out.W == 1 && st.pt == 0 && st.pl == 0 && st.kh == it.H && st.kw == it.W &&
+                  it.Cs == it.C && (st.K % 4) == 0 && it.istride % 4 == 0) ? 1 : 0;
+        p.fd_KP = FastDiv(st.KP); p.fd_kwc = FastDiv(st.kw * p.Cin); p.fd_Cin = FastDiv(p.Cin);
+        p.fd_OW = FastDiv(out.W); p.fd_OH = FastDiv(out.H); p.fd_NQ = FastDiv(st.NC / 4);
         launch_gemm_conv(p, B, s, cta_cap(st.smem, st.NPG * (st.NC / 4)));
         break;
       }
@@ -168,7 +172,7 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         p.out = out.p; p.out_istride = out.istride; p.Cout = st.Cout; p.CoutS = out.Cs;
         p.vec_store = (out.Cs % 4 == 0 && out.istride % 4 == 0 && ((size_t)out.p % 16 == 0)) ? 1 : 0;
         p.wB = blob + st.w; p.bias = blob + st.bias; p.alpha = st.alpha >= 0 ? blob + st.alpha : nullptr;
-        p.act = st.act; p.Npad = st.Npad; p.tmem_cols = st.tmem_cols; p.a_rows = st.a_rows; p.RS = st.RS;
+        p.act = st.act; p.Npad = st.Npad; p.tmem_cols = st.tmem_cols; p.a_rows = st.a_rows; p.RS = st.RS; p.w_parts = st.w_parts;
         p.res_mode = st.in2 >= 0 ? st.res_mode : 0;
         if (st.in2 >= 0) {
           TV rv = view(ctx, st.in2);

@@ -263,7 +263,24 @@ int mesh_stage(fdt_handle* h, cudaStream_t s, const uint8_t* d_frames, long long
     }
     {
       StageTimer t(h, 4, s);
-      t.launches = h->mesh.run(h->mesh_ctx, h->d_crops, nf, s);
+      static const bool dump = [] { const char* e = std::getenv("FDT_DUMP_MESH_STEPS"); return e && e[0] == '1'; }();
+      if (dump) {
+        // diagnostic: per-kernel device time of the mesh plan on stderr
+        const size_t S = h->mesh.plan().steps.size();
+        std::vector<cudaEvent_t> ev(S + 1);
+        for (auto& e : ev) cudaEventCreate(&e);
+        t.launches = h->mesh.run(h->mesh_ctx, h->d_crops, nf, s, ev.data());
+        cudaStreamSynchronize(s);
+        for (size_t i = 0; i < S; ++i) {
+          float ms = 0;
+          cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+          std::fprintf(stderr, "mesh step %2zu kind %2d %-28s %8.3f ms (%d faces)\n", i, (int)h->mesh.plan().steps[i].kind,
+                       h->mesh.plan().steps[i].name.c_str(), ms, nf);
+        }
+        for (auto& e : ev) cudaEventDestroy(e);
+      } else {
+        t.launches = h->mesh.run(h->mesh_ctx, h->d_crops, nf, s);
+      }
     }
     {
       StageTimer t(h, 5, s);

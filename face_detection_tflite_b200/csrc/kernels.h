@@ -99,6 +99,8 @@ struct GemmConvP {
   const float* bias;        // [CoutP]
   const float* alpha;       // [CoutP] or nullptr
   int act, CoutP, NC, nchunks, NPG, TM;
+  int flat;                 // 1: the kernel window is the whole (dense) input image -> im2col row = plain copy
+  FastDiv fd_KP, fd_kwc, fd_Cin, fd_OW, fd_OH, fd_NQ;
   size_t smem_bytes;
 };
 void launch_gemm_conv(const GemmConvP& p, int B, cudaStream_t s, int max_ctas);
@@ -134,6 +136,7 @@ struct DwPwTcP {
   const float* bias; const float* alpha;   // [Npad]
   int act, Npad, tmem_cols, a_rows, RS;
   int in_floats, n_chunks, n_items;   // staged tile size (floats), staging-table / depthwise-table entries
+  int w_parts;              // 1: weights exact in TF32; 2: W = W_hi + W_lo (fp32 weights), wB holds both
   const float* res; long long res_istride; int res_H, res_W, res_C, res_Cs, res_pool, res_mode, res_lim;
   int TH, TW, G, IH, IW, tilesX, tilesY;
   FastDiv fd_Q8, fd_IW, fd_IH, fd_TW, fd_thw, fd_tpg, fd_tilesX, fd_nstrips, fd_nslots;
@@ -148,7 +151,7 @@ struct StemTcP {
   float* out; long long out_istride; int Cout, CoutS, vec_store;
   const float* wB;          // [Npad x K8] UMMA K-major core-matrix layout, k = (ky*kw + kx)*3 + c
   const float* bias; const float* alpha;
-  int act, Npad, tmem_cols;
+  int act, Npad, tmem_cols, w_parts;
   size_t smem_bytes;
 };
 void launch_stem_tc(const StemTcP& p, int B, cudaStream_t s);

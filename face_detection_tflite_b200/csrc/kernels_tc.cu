@@ -89,8 +89,8 @@ __global__ void __launch_bounds__(kTcThreads, FDT_TC_MINB) k_dwpw_tc(DwPwTcP p, 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Q8 = p.K8 >> 2;                       // 16-byte K chunks per row
   const uint32_t SBO = (uint32_t)Q8 * 128u;       // bytes between 8-row groups
-  float* sB = smem;                               // [Npad x K8] canonical
-  float* sBias = sB + (size_t)p.Npad * p.K8;      // [Npad]
+  float* sB = smem;                               // [w_parts][Npad x K8] canonical (hi [, lo] parts of W)
+  float* sBias = sB + (size_t)p.w_parts * p.Npad * p.K8;   // [Npad]
   float* sAlpha = sBias + p.Npad;                 // [Npad]
   float* sDw = sAlpha + p.Npad;                   // [10][K8]: 9 taps + bias
   float* sAhi = sDw + (p.has_dw ? 10 * p.K8 : 0); // [a_rows x K8] canonical
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kTcThreads, FDT_TC_MINB) k_dwpw_tc(DwPwTcP p, 
 
   // ---- prologue: weights, bias, tables, barrier, TMEM ------------------------------------------------
   const uint32_t sB_u32 = smem_u32(sB);
-  for (int i = tid; i < p.Npad * Q8; i += kTcThreads) cp_async16_u32(sB_u32 + 16u * i, p.wB + 4 * (size_t)i, true);
+  for (int i = tid; i < p.w_parts * p.Npad * Q8; i += kTcThreads) cp_async16_u32(sB_u32 + 16u * i, p.wB + 4 * (size_t)i, true);
   for (int i = tid; i < p.Npad; i += kTcThreads) {
     sBias[i] = p.bias[i];
     sAlpha[i] = p.alpha ? p.alpha[i] : 0.f;
@@ -254,10 +254,14 @@ __global__ void __launch_bounds__(kTcThreads, FDT_TC_MINB) k_dwpw_tc(DwPwTcP p, 
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t a_hi = smem_u32(sAhi), a_lo = smem_u32(sAlo);
       const int ksteps = p.K8 >> 3;
+      const uint32_t b_lo = sB_u32 + (uint32_t)p.Npad * p.K8 * 4u;
       for (int ks = 0; ks < ksteps; ++ks) {
         const uint64_t db = make_desc(sB_u32 + ks * 2 * kLBO, SBO);
-        mma_tf32(tmem_base, make_desc(a_hi + ks * 2 * kLBO, SBO), db, idesc, ks > 0 ? 1u : 0u);
+        const uint64_t dah = make_desc(a_hi + ks * 2 * kLBO, SBO);
+        mma_tf32(tmem_base, dah, db, idesc, ks > 0 ? 1u : 0u);
         mma_tf32(tmem_base, make_desc(a_lo + ks * 2 * kLBO, SBO), db, idesc, 1u);
+        // fp32 weights (face_landmark): W = W_hi + W_lo, third product A_hi * W_lo (A_lo * W_lo ~ 2^-22, dropped)
+        if (p.w_parts > 1) mma_tf32(tmem_base, dah, make_desc(b_lo + ks * 2 * kLBO, SBO), idesc, 1u);
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
     }
@@ -391,15 +395,15 @@ __global__ void __launch_bounds__(kTcThreads, 2) k_stem_tc(StemTcP p, int B, int
   __shared__ __align__(8) uint64_t mbar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  float* sB = smem;                               // [Npad x K8] canonical
-  float* sBias = sB + (size_t)p.Npad * K8;        // [Npad]
+  float* sB = smem;                               // [w_parts][Npad x K8] canonical
+  float* sBias = sB + (size_t)p.w_parts * p.Npad * K8;   // [Npad]
   float* sAlpha = sBias + p.Npad;
   float* sAhi = sAlpha + p.Npad;                  // [128 x K8] canonical
   float* sAlo = sAhi + 128 * K8;
   float* sP = sAlo + 128 * K8;                    // [PH][PW*3] normalised RGB patch
 
   const uint32_t sB_u32 = smem_u32(sB);
-  for (int i = tid; i < p.Npad * Q8; i += kTcThreads) cp_async16_u32(sB_u32 + 16u * i, p.wB + 4 * (size_t)i, true);
+  for (int i = tid; i < p.w_parts * p.Npad * Q8; i += kTcThreads) cp_async16_u32(sB_u32 + 16u * i, p.wB + 4 * (size_t)i, true);
   for (int i = tid; i < p.Npad; i += kTcThreads) {
     sBias[i] = p.bias[i];
     sAlpha[i] = p.alpha ? p.alpha[i] : 0.f;
@@ -461,10 +465,13 @@ __global__ void __launch_bounds__(kTcThreads, 2) k_stem_tc(StemTcP p, int B, int
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t a_hi = smem_u32(sAhi), a_lo = smem_u32(sAlo);
 #pragma unroll 1
+      const uint32_t b_lo = sB_u32 + (uint32_t)p.Npad * K8 * 4u;
       for (int ks = 0; ks < K8 / 8; ++ks) {
         const uint64_t db = make_desc(sB_u32 + ks * 2 * kLBO, SBO);
-        mma_tf32(tmem_base, make_desc(a_hi + ks * 2 * kLBO, SBO), db, idesc, ks > 0 ? 1u : 0u);
+        const uint64_t dah = make_desc(a_hi + ks * 2 * kLBO, SBO);
+        mma_tf32(tmem_base, dah, db, idesc, ks > 0 ? 1u : 0u);
         mma_tf32(tmem_base, make_desc(a_lo + ks * 2 * kLBO, SBO), db, idesc, 1u);
+        if (p.w_parts > 1) mma_tf32(tmem_base, dah, make_desc(b_lo + ks * 2 * kLBO, SBO), idesc, 1u);
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
     }

@@ -196,9 +196,9 @@ __global__ void __launch_bounds__(384, FDT_MINB) k_gemm_conv(GemmConvP p, int B,
   float* sW = smem + (size_t)P * p.KS;       // [KP][NC]
   const int tid = threadIdx.x, nt = blockDim.x;
   const int NQ = p.NC >> 2;
-  const int q = tid % NQ, pg = tid / NQ;
+  int q, pg;
+  p.fd_NQ.divmod(tid, pg, q);          // threads beyond NPG*NQ only help with the im2col staging
   const long long total_px = (long long)B * p.OH * p.OW;
-  const int kwc = p.kw * p.Cin;
 
   for (int chunk = 0; chunk < p.nchunks; ++chunk) {
     const int c0 = chunk * p.NC;
@@ -207,32 +207,45 @@ __global__ void __launch_bounds__(384, FDT_MINB) k_gemm_conv(GemmConvP p, int B,
     cp_async_wait_all();
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       __syncthreads();  // previous tile's GEMM done with sA (and weights visible on first pass)
-      // ---- im2col: sA[slot][k], k = (ky*kw + kx)*Cin + c
       const long long px0 = (long long)tile * P;
-      for (int i = tid; i < P * p.KP; i += nt) {
-        int slot = i / p.KP, k = i - slot * p.KP;
-        float v = 0.f;
-        long long px = px0 + slot;
-        if (k < p.K && px < total_px) {
-          int ox = (int)(px % p.OW);
-          long long r = px / p.OW;
-          int oy = (int)(r % p.OH);
-          int b = (int)(r / p.OH);
-          int ky = k / kwc, rem = k - ky * kwc;
-          int kx = rem / p.Cin, c = rem - kx * p.Cin;
-          int iy = oy * p.sh + ky - p.pt, ix = ox * p.sw + kx - p.pl;
-          if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
-            if (p.in8) {
-              unsigned char u = p.in8[(size_t)b * p.in_istride + ((size_t)iy * p.W + ix) * 4 + (2 - c)];
-              v = fmaf((float)u, 1.0f / 127.5f, -1.0f);
-            } else {
-              v = p.in[(size_t)b * p.in_istride + ((size_t)iy * p.W + ix) * p.CinS + c];
+      if (p.flat) {
+        // the window is the whole dense input: row = the image itself, copied 16 bytes at a time
+        const int kq = p.KP >> 2;
+        for (int i = tid; i < P * kq; i += nt) {
+          int slot = i / kq, k4 = i - slot * kq;
+          long long px = px0 + slot;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (px < total_px && 4 * k4 < p.K) v = *reinterpret_cast<const float4*>(p.in + (size_t)px * p.in_istride + 4 * k4);
+          *reinterpret_cast<float4*>(sA + (size_t)slot * p.KS + 4 * k4) = v;
+        }
+      } else {
+        // ---- im2col: sA[slot][k], k = (ky*kw + kx)*Cin + c
+        for (int i = tid; i < P * p.KP; i += nt) {
+          int slot, k;
+          p.fd_KP.divmod(i, slot, k);
+          float v = 0.f;
+          long long px = px0 + slot;
+          if (k < p.K && px < total_px) {
+            int r, ox, b, oy, ky, rem, kx, c;
+            p.fd_OW.divmod((int)px, r, ox);
+            p.fd_OH.divmod(r, b, oy);
+            p.fd_kwc.divmod(k, ky, rem);
+            p.fd_Cin.divmod(rem, kx, c);
+            int iy = oy * p.sh + ky - p.pt, ix = ox * p.sw + kx - p.pl;
+            if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+              if (p.in8) {
+                unsigned char u = p.in8[(size_t)b * p.in_istride + ((size_t)iy * p.W + ix) * 4 + (2 - c)];
+                v = fmaf((float)u, 1.0f / 127.5f, -1.0f);
+              } else {
+                v = p.in[(size_t)b * p.in_istride + ((size_t)iy * p.W + ix) * p.CinS + c];
+              }
             }
           }
+          sA[(size_t)slot * p.KS + k] = v;
         }
-        sA[(size_t)slot * p.KS + k] = v;
       }
       __syncthreads();
+      if (pg >= p.NPG) continue;      // staging helper threads (no barrier below inside this tile)
       float acc[TM][4];
 #pragma unroll
       for (int i = 0; i < TM; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
@@ -477,6 +490,8 @@ void launch_gemm_conv(const GemmConvP& p, int B, cudaStream_t s, int max_ctas) {
   int grid = ntiles < max_ctas ? ntiles : max_ctas;
   if (grid < 1) grid = 1;
   int nt = p.NPG * (p.NC >> 2);
+  if (nt < 128) nt = 128;               // extra threads help with the im2col staging
+  nt = (nt + 31) / 32 * 32;
   if (p.TM == 8) {
     set_smem((const void*)k_gemm_conv<8>, p.smem_bytes);
     k_gemm_conv<8><<<grid, nt, p.smem_bytes, s>>>(p, B, ntiles);

@@ -269,15 +269,18 @@ struct Builder {
     if (!m.const_f32(conv.in[1], &w)) return fail("conv weights are not constant");
     if (conv.in.size() > 2 && conv.in[2] >= 0) { if (!m.const_f32(conv.in[2], &b)) return fail("conv bias is not constant"); }
     b.resize(st.Cout, 0.f);
-    bool tc = use_tc && tf32_exact(w) && (st.res_mode != 1 || st.has_dw) && plan_tc(&F->st, Cin, OH, OW);
+    const int w_parts = tf32_exact(w) ? 1 : 2;
+    bool tc = use_tc && plan_tc(&F->st, Cin, OH, OW, w_parts);
     const PStep& fs = F->st;
     if (tc) {
       // B operand [Npad x K8] in the UMMA K-major core-matrix layout (8 rows x 16 bytes per core matrix)
       const size_t SBO = (size_t)(fs.K8 / 4) * 128, LBO = 128;
-      std::vector<float> wb((size_t)fs.Npad * fs.K8, 0.f);
+      std::vector<float> wb((size_t)w_parts * fs.Npad * fs.K8, 0.f);
       for (int n = 0; n < fs.Cout; ++n)
-        for (int k = 0; k < Cin; ++k)
-          wb[((size_t)(n >> 3) * SBO + (size_t)(k >> 2) * LBO + (size_t)(n & 7) * 16 + (size_t)(k & 3) * 4) / 4] = w[(size_t)n * Cin + k];
+        for (int k = 0; k < Cin; ++k) {
+          size_t o = ((size_t)(n >> 3) * SBO + (size_t)(k >> 2) * LBO + (size_t)(n & 7) * 16 + (size_t)(k & 3) * 4) / 4;
+          split_w(w[(size_t)n * Cin + k], w_parts, &wb[o], &wb[o + (w_parts > 1 ? (size_t)fs.Npad * fs.K8 : 0)]);
+        }
       F->st.w = push(wb, wb.size());
       F->st.bias = push(b, (size_t)fs.Npad + 8);
       if (alpha_tf >= 0 && !pack_alpha(alpha_tf, (size_t)fs.Npad + 8, &F->st.alpha)) return false;
@@ -306,6 +309,18 @@ struct Builder {
   }
 
   // ---- tensor-core variant of a fused pointwise step -------------------------------------------
+  // W = hi + lo with hi exactly representable in TF32 (low 13 mantissa bits cleared)
+  static void split_w(float v, int parts, float* hi, float* lo) {
+    if (parts == 1) { *hi = v; return; }
+    uint32_t u;
+    std::memcpy(&u, &v, 4);
+    u &= 0xFFFFE000u;
+    float h;
+    std::memcpy(&h, &u, 4);
+    *hi = h;
+    *lo = v - h;
+  }
+
   static bool tf32_exact(const std::vector<float>& w) {
     for (float v : w) {
       uint32_t u;
@@ -316,8 +331,9 @@ struct Builder {
   }
 
   // Re-plans `st` (a kStepDwPw) for k_dwpw_tc: M = 128 pixel slots, N = Cout padded to 16, K padded to 8.
-  bool plan_tc(PStep* st, int Cin, int OH, int OW) {
+  bool plan_tc(PStep* st, int Cin, int OH, int OW, int w_parts) {
     PStep s = *st;
+    s.w_parts = w_parts;
     s.K8 = ru(Cin, 8);
     s.Npad = ru(s.Cout, 16);
     if (s.Npad > 128 || s.K8 > 256) return false;
@@ -351,7 +367,7 @@ struct Builder {
       s.RS = 1;
       for (int rs : {8, 4, 2}) if (s.TH % rs == 0 && s.G * (s.K8 / 4) * (s.TH / rs) * s.TW >= 256) { s.RS = rs; break; }
       if (s.IH > 63 || s.IW > 63 || s.G > 63 || nslots > 255) continue;     // staging-table field widths
-      size_t head = (size_t)s.Npad * s.K8 + 2 * (size_t)s.Npad + (s.has_dw ? 10 * (size_t)s.K8 : 0);
+      size_t head = (size_t)s.w_parts * s.Npad * s.K8 + 2 * (size_t)s.Npad + (s.has_dw ? 10 * (size_t)s.K8 : 0);
       size_t a = 2 * (size_t)s.a_rows * s.K8;
       size_t in = (size_t)s.G * s.IH * s.IW * s.KS;
       // the MMA always reads 128 rows of each A tile: keep those addresses inside the allocation
@@ -469,7 +485,8 @@ struct Builder {
     if (!m.const_f32(conv.in[1], &w)) return fail("conv weights are not constant");
     if (conv.in.size() > 2 && conv.in[2] >= 0) { if (!m.const_f32(conv.in[2], &b)) return fail("conv bias is not constant"); }
     b.resize(st.Cout, 0.f);
-    if (st.kind == kStepStem && use_tc && tf32_exact(w) && ru(st.Cout, 16) <= 128) {
+    if (st.kind == kStepStem && use_tc && ru(st.Cout, 16) <= 128) {
+      st.w_parts = tf32_exact(w) ? 1 : 2;
       // tensor-core stem: B operand [Npad x K8] in the UMMA K-major core-matrix layout
       st.kind = kStepStemTc;
       st.K8 = ru(st.K, 8);
@@ -477,12 +494,14 @@ struct Builder {
       st.tmem_cols = 32;
       while (st.tmem_cols < st.Npad) st.tmem_cols *= 2;
       const size_t SBO = (size_t)(st.K8 / 4) * 128, LBO = 128;
-      std::vector<float> wb((size_t)st.Npad * st.K8, 0.f);
+      std::vector<float> wb((size_t)st.w_parts * st.Npad * st.K8, 0.f);
       for (int n = 0; n < st.Cout; ++n)
-        for (int k = 0; k < st.K; ++k)
-          wb[((size_t)(n >> 3) * SBO + (size_t)(k >> 2) * LBO + (size_t)(n & 7) * 16 + (size_t)(k & 3) * 4) / 4] = w[(size_t)n * st.K + k];
+        for (int k = 0; k < st.K; ++k) {
+          size_t o = ((size_t)(n >> 3) * SBO + (size_t)(k >> 2) * LBO + (size_t)(n & 7) * 16 + (size_t)(k & 3) * 4) / 4;
+          split_w(w[(size_t)n * st.K + k], st.w_parts, &wb[o], &wb[o + (st.w_parts > 1 ? (size_t)st.Npad * st.K8 : 0)]);
+        }
       int PH = 14 + st.kw, PW = 30 + st.kw;
-      st.smem = ((size_t)st.Npad * st.K8 + 2 * (size_t)st.Npad + 2 * 128 * (size_t)st.K8 + (size_t)PH * PW * 3) * 4 + 128;
+      st.smem = ((size_t)st.w_parts * st.Npad * st.K8 + 2 * (size_t)st.Npad + 2 * 128 * (size_t)st.K8 + (size_t)PH * PW * 3) * 4 + 128;
       st.w = push(wb, wb.size());
       st.bias = push(b, (size_t)st.Npad + 8);
       if (alpha_tf >= 0 && !pack_alpha(alpha_tf, (size_t)st.Npad + 8, &st.alpha)) return false;

@@ -17,7 +17,8 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 
 
 def run(model, w, h, mode, batch, min_side, max_side):
-    det = fdt.FaceDetector.create(fdt.FaceDetectionModel[model], withMesh=(mode == "standard"))
+    # standard mode: 4 result slots per frame (BASELINE config 4: "up to 4 faces/frame") keeps the mesh output buffer small
+    det = fdt.FaceDetector.create(fdt.FaceDetectionModel[model], withMesh=(mode == "standard"), maxFaces=(4 if mode == "standard" else 0))
     base = np.concatenate([synth.face_frames(56, w, h, min_side=min_side, max_side=max_side), synth.noise_frames(8, w, h)])
     dev = torch.from_numpy(base).cuda().repeat(batch // 64, 1, 1, 1).contiguous()
     m = fdt.FaceDetectionMode[mode]
