@@ -172,7 +172,7 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         p.out = out.p; p.out_istride = out.istride; p.Cout = st.Cout; p.CoutS = out.Cs;
         p.vec_store = (out.Cs % 4 == 0 && out.istride % 4 == 0 && ((size_t)out.p % 16 == 0)) ? 1 : 0;
         p.wB = blob + st.w; p.bias = blob + st.bias; p.alpha = st.alpha >= 0 ? blob + st.alpha : nullptr;
-        p.act = st.act; p.Npad = st.Npad; p.tmem_cols = st.tmem_cols; p.a_rows = st.a_rows; p.RS = st.RS; p.w_parts = st.w_parts;
+        p.act = st.act; p.Npad = st.Npad; p.tmem_cols = st.tmem_cols; p.a_rows = st.a_rows; p.RS = st.RS; p.w_parts = st.w_parts; p.nbuf = st.nbuf;
         p.res_mode = st.in2 >= 0 ? st.res_mode : 0;
         if (st.in2 >= 0) {
           TV rv = view(ctx, st.in2);

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kTcThreads, FDT_TC_MINB) k_dwpw_tc(DwPwTcP p, 
   float* sAhi = sDw + (p.has_dw ? 10 * p.K8 : 0); // [a_rows x K8] canonical
   float* sAlo = sAhi + (size_t)p.a_rows * p.K8;
   float* sIn = sAlo + (size_t)p.a_rows * p.K8;    // [G][IH][IW][KS]
-  uint2* stab = reinterpret_cast<uint2*>(sIn + p.in_floats);   // staging table [n_chunks]
+  uint2* stab = reinterpret_cast<uint2*>(sIn + (size_t)p.nbuf * p.in_floats);   // staging table [n_chunks]
   uint2* dtab = stab + p.n_chunks;                              // depthwise table [n_items]
   const int thw = p.TH * p.TW;
   const int nslots = p.G * thw;
@@ -150,9 +150,10 @@ __global__ void __launch_bounds__(kTcThreads, FDT_TC_MINB) k_dwpw_tc(DwPwTcP p, 
   const bool slot_ok = slot < nslots;
   const long long o_rel = slot_ok ? (long long)e_g * p.out_istride + ((long long)e_ty * p.OW + e_tx) * p.CoutS : 0;
   const int rs = p.res_pool ? 2 : 1;
-  const float* res_s = sIn + (slot_ok ? (((size_t)e_g * p.IH + e_ty * rs + p.dpt) * p.IW + e_tx * rs + p.dpl) * p.KS : 0);
+  const uint32_t res_off = slot_ok ? (uint32_t)((((size_t)e_g * p.IH + e_ty * rs + p.dpt) * p.IW + e_tx * rs + p.dpl) * p.KS) : 0u;
   const uint32_t row_f = (uint32_t)p.IW * p.KS;          // floats per staged row
-  const uint32_t sIn_u32 = smem_u32(sIn);
+  float* const sInA = sIn;
+  float* const sInB = p.nbuf > 1 ? sIn + p.in_floats : sIn;
 
   cp_async_wait_all();
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -163,29 +164,41 @@ __global__ void __launch_bounds__(kTcThreads, FDT_TC_MINB) k_dwpw_tc(DwPwTcP p, 
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((128u >> 4) << 24);
   uint32_t parity = 0;
 
+  // Stages the input tile (+halo) of `t` into `dst`: table-driven cp.async, zero fill outside the image.
+  auto stage = [&](int t, float* dst) {
+    int grp, trem, tyi, txi;
+    p.fd_tpg.divmod(t, grp, trem);
+    p.fd_tilesX.divmod(trem, tyi, txi);
+    const int b0 = grp * p.G;
+    const int iy0 = tyi * p.TH * p.s - p.dpt, ix0 = txi * p.TW * p.s - p.dpl;
+    const float* tbase = p.in + (long long)b0 * p.in_istride + ((long long)iy0 * p.W + ix0) * p.CinS;
+    const unsigned uH = (unsigned)p.H, uW = (unsigned)p.W;
+    const int nb = B - b0;
+    const uint32_t dst_u32 = smem_u32(dst);
+    for (int i = tid; i < p.n_chunks; i += kTcThreads) {
+      const uint2 e = stab[i];
+      const int goff = (int)e.x;
+      const unsigned y = (unsigned)(iy0 + (int)((e.y >> 14) & 63u));
+      const unsigned x = (unsigned)(ix0 + (int)((e.y >> 20) & 63u));
+      const bool ok = goff >= 0 && y < uH && x < uW && (int)(e.y >> 26) < nb;
+      cp_async16_u32(dst_u32 + ((e.y & 0x3FFFu) << 4), ok ? tbase + goff : p.in, ok);
+    }
+  };
+  int cur = 0;
+  if ((int)blockIdx.x < ntiles) stage(blockIdx.x, sInA);
+
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     int grp, trem, tyi, txi;
     p.fd_tpg.divmod(tile, grp, trem);
     p.fd_tilesX.divmod(trem, tyi, txi);
     const int ty0 = tyi * p.TH, tx0 = txi * p.TW;
     const int b0 = grp * p.G;
-    const int iy0 = ty0 * p.s - p.dpt, ix0 = tx0 * p.s - p.dpl;
-    // ---- stage the input tile (+halo): table-driven cp.async, zero fill outside the image
-    {
-      const float* tbase = p.in + (long long)b0 * p.in_istride + ((long long)iy0 * p.W + ix0) * p.CinS;
-      const unsigned uH = (unsigned)p.H, uW = (unsigned)p.W;
-      const int nb = B - b0;
-      for (int i = tid; i < p.n_chunks; i += kTcThreads) {
-        const uint2 e = stab[i];
-        const int goff = (int)e.x;
-        const unsigned y = (unsigned)(iy0 + (int)((e.y >> 14) & 63u));
-        const unsigned x = (unsigned)(ix0 + (int)((e.y >> 20) & 63u));
-        const bool ok = goff >= 0 && y < uH && x < uW && (int)(e.y >> 26) < nb;
-        cp_async16_u32(sIn_u32 + ((e.y & 0x3FFFu) << 4), ok ? tbase + goff : p.in, ok);
-      }
-    }
-    cp_async_wait_all();
+    sIn = cur ? sInB : sInA;
+    const float* res_s = sIn + res_off;
+    cp_async_wait_all();          // this tile's input (issued one iteration ago, or in the prologue)
     __syncthreads();
+    // software pipeline: the next tile's input streams into the other buffer while this tile is computed
+    if (p.nbuf > 1 && tile + (int)gridDim.x < ntiles) stage(tile + gridDim.x, cur ? sInA : sInB);
     // ---- A operand: depthwise 3x3 (or plain copy) -> hi/lo split -> canonical layout
     if (p.has_dw) {
       for (int it = tid; it < p.n_items; it += kTcThreads) {
@@ -353,6 +366,8 @@ __global__ void __launch_bounds__(kTcThreads, FDT_TC_MINB) k_dwpw_tc(DwPwTcP p, 
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();   // TMEM, sIn and the A tiles are free again
+    if (p.nbuf > 1) cur ^= 1;
+    else if (tile + (int)gridDim.x < ntiles) stage(tile + gridDim.x, sInA);
   }
   if (warp == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

@@ -376,7 +376,16 @@ struct Builder {
       in = (in + 3) / 4 * 4;
       size_t n_chunks = (size_t)s.G * s.IH * s.IW * (s.K8 / 4);
       size_t n_items = s.has_dw ? (size_t)s.G * (s.K8 / 4) * (s.TH / s.RS) * s.TW : 0;
-      s.smem = (head + a + in) * 4 + (n_chunks + n_items) * 8 + 128;
+      // double-buffer the input tile when that does not cost residency: the kernel's ~110 registers allow
+      // two CTAs per SM, i.e. <= 113 KB each; a CTA that is alone on its SM anyway may use up to 220 KB
+      size_t smem1 = (head + a + in) * 4 + (n_chunks + n_items) * 8 + 128;
+      size_t smem2 = smem1 + in * 4;
+      static const int want_nbuf = [] { const char* e = std::getenv("FDT_TC_NBUF"); return e ? std::atoi(e) : 0; }();
+      bool dbl = want_nbuf == 2 ? smem2 <= 220 * 1024
+               : want_nbuf == 1 ? false
+               : (smem2 <= 113 * 1024 || (smem1 > 113 * 1024 && smem2 <= 220 * 1024));
+      s.nbuf = dbl ? 2 : 1;
+      s.smem = dbl ? smem2 : smem1;
       if (s.smem <= 220 * 1024) { s.kind = kStepDwPwTc; *st = s; return true; }
     }
     return false;

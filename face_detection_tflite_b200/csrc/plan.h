@@ -39,7 +39,7 @@ struct PStep {
   int K = 0, KP = 0, KS = 0, Cout = 0, CoutP = 0, NC = 0, nchunks = 0, NPG = 0, TM = 0;
   int TH = 0, TW = 0, G = 1, IH = 0, IW = 0, tilesX = 1, tilesY = 1;
   size_t smem = 0;
-  int K8 = 0, Npad = 0, a_rows = 0, RS = 1, tmem_cols = 0, w_parts = 1;   // tensor-core variant
+  int K8 = 0, Npad = 0, a_rows = 0, RS = 1, tmem_cols = 0, w_parts = 1, nbuf = 1;   // tensor-core variant
   int fh = 1, fw = 1, align = 0, half = 0;
   double macs = 0;  // per image
 };
