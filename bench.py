@@ -270,11 +270,28 @@ def main():
                                 "tflops": 2 * macs.value * n / (arr[i] * 1e-3) / 1e12 if arr[i] > 0 else None})
             top = max(kernels, key=lambda k: k["ms"])
             peak, how = peaks()
+            total_ms = sum(k["ms"] for k in kernels)
+            # DRAM traffic of the same launch from the committed ncu --set full capture (profiles/), when the kernel matches
+            traffic, traffic_src = None, None
+            tfile = sorted((ROOT / "profiles").glob("r*_traffic.json"))
+            if tfile:
+                tj = json.loads(tfile[-1].read_text())
+                ent = [e for e in tj["launches"] if e["launch"] == top["launch"]]
+                if ent and ent[0]["kernel"].split("<")[0] == top["kernel"] and ent[0]["images_per_launch"] == n:
+                    traffic, traffic_src = ent[0]["dram_bytes_per_launch"], "profiles/" + tfile[-1].name
             roofline = {"kernel": "%s[%s]" % (top["kernel"], top["tensor"]), "bound": "hbm", "achieved": top["gbs"], "peak": peak,
-                        "unit": "GB/s", "frac": top["gbs"] / peak, "traffic": None, "peak_source": how,
-                        "share_of_step": top["ms"] / sum(k["ms"] for k in kernels), "images_per_launch": n,
-                        "fp32_tflops": top["tflops"],
-                        "conv_stack_tflops": 2 * sum(k["macs_per_image"] for k in kernels) * n / (sum(k["ms"] for k in kernels) * 1e-3) / 1e12}
+                        "unit": "GB/s", "frac": top["gbs"] / peak, "traffic": traffic, "traffic_source": traffic_src,
+                        "algorithmic_bytes_per_launch": top["bytes_per_image"] * n, "peak_source": how,
+                        "share_of_step": top["ms"] / total_ms, "images_per_launch": n,
+                        "note": "dominant kernel by device time; achieved = algorithmic activation bytes (input read once + output written "
+                                "once, fp32 NHWC) / CUDA-event duration of that launch",
+                        "stages": {
+                            "letterbox": {"ms": kernels[0]["ms"], "gbs": kernels[0]["gbs"], "frac_hbm": kernels[0]["gbs"] / peak},
+                            "conv_stack": {"ms": sum(k["ms"] for k in kernels[1:-1]),
+                                           "gbs": sum(k["bytes_per_image"] for k in kernels[1:-1]) * n / (sum(k["ms"] for k in kernels[1:-1]) * 1e-3) / 1e9,
+                                           "tflops": 2 * sum(k["macs_per_image"] for k in kernels[1:-1]) * n / (sum(k["ms"] for k in kernels[1:-1]) * 1e-3) / 1e12},
+                            "decode_nms": {"ms": kernels[-1]["ms"], "gbs": kernels[-1]["gbs"], "frac_hbm": kernels[-1]["gbs"] / peak}}}
+            roofline["stages"]["conv_stack"]["frac_hbm"] = roofline["stages"]["conv_stack"]["gbs"] / peak
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
