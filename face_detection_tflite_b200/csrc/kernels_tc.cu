@@ -574,8 +574,12 @@ void launch_dwpw_tc(const DwPwTcP& p, int B, cudaStream_t s, int max_ctas) {
   (void)max_ctas;
   int groups = (B + p.G - 1) / p.G;
   int ntiles = groups * p.tilesX * p.tilesY;
-  static const int mult = [] { const char* e = std::getenv("FDT_TC_GRIDMULT"); return e ? std::atoi(e) : 2; }();   // 2 waves of CTAs: measured best (de-synchronises the CTAs' load / compute phases)
-  int grid = std::min(ntiles, 148 * per_sm * (mult > 0 ? mult : 1));
+  // Grid = resident CTAs, doubled for layers with many tiles (measured: a second wave de-synchronises the
+  // CTAs' load / compute phases; for small layers the smaller grid leaves room for the other stream's kernel).
+  static const int force = [] { const char* e = std::getenv("FDT_TC_GRIDMULT"); return e ? std::atoi(e) : 0; }();
+  const int resident = 148 * per_sm;
+  const int mult = force > 0 ? force : (ntiles >= 6 * resident ? 2 : 1);
+  int grid = std::min(ntiles, resident * mult);
   if (grid < 1) grid = 1;
   k_dwpw_tc<<<grid, kTcThreads, p.smem_bytes, s>>>(p, B, ntiles);
 }
