@@ -416,6 +416,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) k_stem_tc(StemTcP p, int B, int
   float* sAhi = sAlpha + p.Npad;                  // [128 x K8] canonical
   float* sAlo = sAhi + 128 * K8;
   float* sP = sAlo + 128 * K8;                    // [PH][PW*3] normalised RGB patch
+  uint32_t* sRaw = reinterpret_cast<uint32_t*>(sP + PH * PW3);   // [2][PH*PW] raw BGRX pixels (cp.async, double-buffered)
 
   const uint32_t sB_u32 = smem_u32(sB);
   for (int i = tid; i < p.w_parts * p.Npad * Q8; i += kTcThreads) cp_async16_u32(sB_u32 + 16u * i, p.wB + 4 * (size_t)i, true);
@@ -450,26 +451,51 @@ __global__ void __launch_bounds__(kTcThreads, 2) k_stem_tc(StemTcP p, int B, int
   const int eslot = lq * 32 + lane;
   const int e_ty = eslot >> 4, e_tx = eslot & 15;
 
+  // raw BGRX patch of tile `t` -> sRaw[buf] with 4-byte cp.async (zero fill outside the image = SAME padding;
+  // a zero pixel must become 0.0, not -1.0, so validity is re-derived when converting)
+  auto stage_raw = [&](int t, int buf) {
+    const int b = t / tiles_per_img;
+    const int trem = t - b * tiles_per_img;
+    const int iy0 = (trem / tilesX) * TH * 2 - p.pt, ix0 = (trem % tilesX) * TW * 2 - p.pl;
+    const uint32_t* img = reinterpret_cast<const uint32_t*>(p.in8) + (size_t)b * p.H * p.W;
+    const uint32_t dst = smem_u32(sRaw + buf * (PH * PW));
+    for (int i = tid; i < PH * PW; i += kTcThreads) {
+      const int ly = i / PW, lx = i - ly * PW;
+      const int y = iy0 + ly, x = ix0 + lx;
+      const bool ok = (unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W;
+      const int sz = ok ? 4 : 0;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst + 4u * i), "l"(ok ? img + (size_t)y * p.W + x : img), "r"(sz));
+    }
+  };
+  int cur = 0;
+  if ((int)blockIdx.x < ntiles) stage_raw(blockIdx.x, 0);
+
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int b = tile / tiles_per_img;
     const int trem = tile - b * tiles_per_img;
     const int ty0 = (trem / tilesX) * TH, tx0 = (trem % tilesX) * TW;
     const int iy0 = ty0 * 2 - p.pt, ix0 = tx0 * 2 - p.pl;
+    cp_async_wait_all();
+    __syncthreads();
+    if (tile + (int)gridDim.x < ntiles) stage_raw(tile + gridDim.x, cur ^ 1);   // prefetch the next patch
     // ---- patch: u8x4 BGRX -> normalised RGB floats (bgrMatToSignedFloat32, helpers.dart:401-406)
-    const uchar4* img = reinterpret_cast<const uchar4*>(p.in8) + (size_t)b * p.H * p.W;
-    for (int i = tid; i < PH * PW; i += kTcThreads) {
-      const int ly = i / PW, lx = i - ly * PW;
-      const int y = iy0 + ly, x = ix0 + lx;
-      float3 v = make_float3(0.f, 0.f, 0.f);
-      if ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W) {
-        const uchar4 u = img[(size_t)y * p.W + x];
-        v.x = fmaf((float)u.z, 1.0f / 127.5f, -1.0f);
-        v.y = fmaf((float)u.y, 1.0f / 127.5f, -1.0f);
-        v.z = fmaf((float)u.x, 1.0f / 127.5f, -1.0f);
+    {
+      const uint32_t* raw = sRaw + cur * (PH * PW);
+      for (int i = tid; i < PH * PW; i += kTcThreads) {
+        const int ly = i / PW, lx = i - ly * PW;
+        const int y = iy0 + ly, x = ix0 + lx;
+        float3 v = make_float3(0.f, 0.f, 0.f);
+        if ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W) {
+          const uint32_t u = raw[i];
+          v.x = fmaf((float)((u >> 16) & 0xFFu), 1.0f / 127.5f, -1.0f);
+          v.y = fmaf((float)((u >> 8) & 0xFFu), 1.0f / 127.5f, -1.0f);
+          v.z = fmaf((float)(u & 0xFFu), 1.0f / 127.5f, -1.0f);
+        }
+        float* d = sP + ly * PW3 + lx * 3;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z;
       }
-      float* d = sP + ly * PW3 + lx * 3;
-      d[0] = v.x; d[1] = v.y; d[2] = v.z;
     }
+    cur ^= 1;
     __syncthreads();
     // ---- im2col gather -> hi/lo split -> canonical A (thread = pixel r, one half of the K chunks)
     if (khalf == 0) stem_gather<KW, 0>(prow, sAhi, sAlo, a_row);     // khalf is warp-uniform

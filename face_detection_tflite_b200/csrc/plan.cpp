@@ -510,7 +510,7 @@ struct Builder {
           split_w(w[(size_t)n * st.K + k], st.w_parts, &wb[o], &wb[o + (st.w_parts > 1 ? (size_t)st.Npad * st.K8 : 0)]);
         }
       int PH = 14 + st.kw, PW = 30 + st.kw;
-      st.smem = ((size_t)st.w_parts * st.Npad * st.K8 + 2 * (size_t)st.Npad + 2 * 128 * (size_t)st.K8 + (size_t)PH * PW * 3) * 4 + 128;
+      st.smem = ((size_t)st.w_parts * st.Npad * st.K8 + 2 * (size_t)st.Npad + 2 * 128 * (size_t)st.K8 + (size_t)PH * PW * 3 + 2 * (size_t)PH * PW) * 4 + 128;
       st.w = push(wb, wb.size());
       st.bias = push(b, (size_t)st.Npad + 8);
       if (alpha_tf >= 0 && !pack_alpha(alpha_tf, (size_t)st.Npad + 8, &st.alpha)) return false;
