@@ -340,8 +340,13 @@ struct Builder {
     s.KS = s.K8 + (((s.K8 / 4) % 2 == 0) ? 4 : 0);
     s.tmem_cols = 32;
     while (s.tmem_cols < s.Npad) s.tmem_cols *= 2;
+    // First choice: the largest tile within the preferred footprint (FDT_TC_SMEMCAP KB, tuning knob);
+    // fallback: the largest tile that fits at all.
+    static const size_t pref_cap = [] { const char* e = std::getenv("FDT_TC_SMEMCAP"); return (size_t)(e ? std::atoi(e) : 220) * 1024; }();
+    for (int pass = 0; pass < 2; ++pass)
     for (int Pn = 128; Pn >= 32; Pn /= 2) {
-      s.TM = 1; s.NPG = Pn;                       // plan_spatial reads TM * NPG as the slot budget
+      const size_t cap = pass == 0 ? pref_cap : (size_t)220 * 1024;
+      s.TM = 1; s.NPG = Pn;                       // slot budget of this candidate
       int bestTH = 0, bestTW = 0, bestG = 1;
       double best = -1;
       if (OH * OW <= Pn && OW <= 30) {
@@ -386,7 +391,7 @@ struct Builder {
                : (smem2 <= 113 * 1024 || (smem1 > 113 * 1024 && smem2 <= 220 * 1024));
       s.nbuf = dbl ? 2 : 1;
       s.smem = dbl ? smem2 : smem1;
-      if (s.smem <= 220 * 1024) { s.kind = kStepDwPwTc; *st = s; return true; }
+      if (s.smem <= cap) { s.kind = kStepDwPwTc; *st = s; return true; }
     }
     return false;
   }
