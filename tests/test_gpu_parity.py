@@ -369,3 +369,97 @@ def test_full_size_c2_properties(fdt, model_bytes):
     o = get_oracle(model_bytes, "shortRange", "cv2dnn")
     for k in (1, 7, 18, 33, 49):
         assert c1[k] == len(o.detect(base[k]))
+
+
+# ---- more coverage of the boundary ------------------------------------------------------------------
+def test_mat_types_give_same_detections(fdt, sample_images):
+    """matType 24 (BGRA) and 0 (GRAY) are colour-converted like bgrMatToSignedFloat32 does (helpers.dart:386-392)."""
+    import cv2
+    d = get_detector(fdt, "backCamera")
+    img = sample_images["landmark-ex1.jpg"]
+    fast = fdt.FaceDetectionMode.fast
+    base = d.detectFacesFromMat(img, mode=fast)
+    bgra = cv2.cvtColor(img, cv2.COLOR_BGR2BGRA)
+    assert [f.detectionData for f in d.detectFacesFromMat(bgra, mode=fast)] == [f.detectionData for f in base]
+    gray = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)
+    g3 = cv2.cvtColor(gray, cv2.COLOR_GRAY2BGR)
+    assert [f.detectionData for f in d.detectFacesFromMat(gray, mode=fast)] == [f.detectionData for f in d.detectFacesFromMat(g3, mode=fast)]
+    # standard mode on BGRA: the warp reads the 4-channel frame directly
+    a = d.detectFacesFromMat(bgra, mode=fdt.FaceDetectionMode.standard)
+    b = d.detectFacesFromMat(img, mode=fdt.FaceDetectionMode.standard)
+    assert len(a) == len(b) == 1 and np.array_equal(a[0].mesh.packed, b[0].mesh.packed)
+
+
+def test_random_frame_sizes_letterbox_bit_exact(fdt):
+    rng = np.random.default_rng(42)
+    d = get_detector(fdt, "full", mesh=False)
+    for _ in range(12):
+        h, w = int(rng.integers(1, 900)), int(rng.integers(1, 1400))
+        frame = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        d.detectBatchRaw(frame, count=1, width=w, height=h)
+        want, _ = co.letterbox_u8(frame, 192, 192)
+        assert np.array_equal(d.debugLetterboxed(1)[0], want), (h, w)
+
+
+def test_max_faces_truncation_and_device_frames_standard_mode(fdt, sample_images):
+    import torch
+    img = sample_images["group-shot-bounding-box-ex1.jpeg"]
+    h, w = img.shape[:2]
+    full = get_detector(fdt, "backCamera").detectFacesFromMat(img, mode=fdt.FaceDetectionMode.fast)
+    two = get_detector(fdt, "backCamera", maxFaces=2)
+    t = two.detectFacesFromMat(img, mode=fdt.FaceDetectionMode.fast)
+    assert [f.detectionData for f in t] == [f.detectionData for f in full[:2]]
+    # device-resident frames in standard mode: same meshes as host frames
+    frames = np.stack([img, img])
+    dev = torch.from_numpy(frames).cuda()
+    fa, ca, ma = two.detectBatchRaw(dev.data_ptr(), count=2, width=w, height=h, mode=fdt.FaceDetectionMode.standard, memKind=1)
+    fb, cb, mb = two.detectBatchRaw(frames, count=2, width=w, height=h, mode=fdt.FaceDetectionMode.standard)
+    assert list(ca) == list(cb) == [2, 2] and np.array_equal(ma, mb)
+
+
+def test_two_handles_in_threads_are_independent_and_deterministic(fdt, sample_images):
+    """concurrency_stress_test.dart:130-162 (parallel detectors) and
+    face_detection_integration_test.dart:929-955 (identical results across instances)."""
+    import threading
+    img = sample_images["landmark-ex1.jpg"]
+    dets = [fdt.FaceDetector.create(fdt.FaceDetectionModel.shortRange, maxBatch=8) for _ in range(2)]
+    out = [None, None]
+
+    def work(i):
+        res = []
+        for _ in range(10):
+            res.append(dets[i].detectFacesFromMat(img, mode=fdt.FaceDetectionMode.standard))
+        out[i] = res
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    ref = out[0][0]
+    assert len(ref) == 1
+    for res in out:
+        for r in res:
+            assert [f.detectionData for f in r] == [f.detectionData for f in ref]
+            assert np.array_equal(r[0].mesh.packed, ref[0].mesh.packed)
+    [d.dispose() for d in dets]
+
+
+def test_c_abi_status_codes(fdt, lib):
+    import ctypes as C
+    from face_detection_tflite_b200 import _ffi
+    d = get_detector(fdt, "shortRange")
+    h = d._h
+    faces = (_ffi.FdtFace * 100)()
+    cnt = C.c_int32()
+    buf = np.zeros(48, np.uint8)
+    assert lib.fdt_detect_one(h, buf.ctypes.data, 47, 4, 4, 16, 0, faces, C.byref(cnt), None) == _ffi.FDT_ERR_SIZE_MISMATCH
+    assert b"length" in lib.fdt_last_error(h)
+    assert lib.fdt_detect_one(h, buf.ctypes.data, 48, 4, 4, 17, 0, faces, C.byref(cnt), None) == _ffi.FDT_ERR_BAD_ARG      # unknown matType
+    assert lib.fdt_detect_one(h, buf.ctypes.data, 48, 4, 4, 16, 2, faces, C.byref(cnt), None) == _ffi.FDT_ERR_UNSUPPORTED  # mode full
+    assert lib.fdt_detect_one(h, buf.ctypes.data, 48, 4, 4, 16, 7, faces, C.byref(cnt), None) == _ffi.FDT_ERR_BAD_ARG
+    assert lib.fdt_detect_batch(h, buf.ctypes.data, 1, 4, 4, 8, 16, 0, 0, faces, C.byref(cnt), None) == _ffi.FDT_ERR_SIZE_MISMATCH  # row_stride < w*3
+    assert lib.fdt_detect_batch(h, buf.ctypes.data, 1, 4, 4, 12, 16, 0, 0, None, None, None) == _ffi.FDT_ERR_BAD_ARG
+    assert lib.fdt_detect_one(h, buf.ctypes.data, 48, 4, 4, 16, 0, faces, C.byref(cnt), None) == _ffi.FDT_OK and cnt.value == 0
+    iw, ih, na, mf, mb = (C.c_int32() for _ in range(5))
+    assert lib.fdt_get_info(h, C.byref(iw), C.byref(ih), C.byref(na), C.byref(mf), C.byref(mb)) == 0
+    assert (iw.value, ih.value, na.value, mf.value) == (128, 128, 896, 100)
+    assert lib.fdt_last_h2d_bytes(h) == 48 and lib.fdt_last_launch_count(h) == 23
