@@ -26,7 +26,10 @@ static_assert(sizeof(fdt_config) == 48, "fdt_config layout");
 
 namespace {
 
-constexpr int kStreams = 2;
+#ifndef FDT_STREAMS
+#define FDT_STREAMS 2
+#endif
+constexpr int kStreams = FDT_STREAMS;   // chunks alternate over this many streams (each with its own arena)
 constexpr int kMeshInput = 192;
 constexpr double kMinScore = 0.5;         // lib/src/shared/face_model_config.dart:53
 constexpr double kMinSuppression = 0.3;   // lib/src/shared/face_model_config.dart:77
