@@ -26,6 +26,7 @@ SOURCES = {
     "kernels_naive.cu": [],
     "kernels_tiled.cu": [],
     "kernels_tc.cu": [],
+    "kernels_ws.cu": [],
     "kernels_pre.cu": [],
     # f64 geometry must be evaluated operation by operation (no fused multiply-add contraction)
     "kernels_post.cu": ["-fmad=false"],

@@ -161,7 +161,7 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         launch_dwpw(p, B, s, cta_cap(st.smem, st.NPG * (st.NC / 4)));
         break;
       }
-      case kStepDwPwTc: {
+      case kStepDwPwTc: case kStepBlockWs: {
         DwPwTcP p;
         TV iv = view(ctx, st.in);
         p.in = iv.p; p.in_istride = iv.istride; p.H = iv.H; p.W = iv.W; p.Cin = iv.C; p.CinS = iv.Cs;
@@ -192,7 +192,13 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
           p.in_floats = (int)((std::max(in, tail) + 3) / 4 * 4);
         }
         p.smem_bytes = st.smem;
-        launch_dwpw_tc(p, B, s, cta_cap(st.smem, 256));
+        p.ns = st.ns; p.na = st.na; p.nd = st.nd;
+        if (st.kind == kStepBlockWs) {
+          p.in_floats = st.in_stage_floats;
+          if (!launch_block_ws(p, B, ctx.cap, s)) fprintf(stderr, "fdt: cuTensorMapEncodeTiled failed for step '%s'\n", st.name.c_str());
+        } else {
+          launch_dwpw_tc(p, B, s, cta_cap(st.smem, 256));
+        }
         break;
       }
       case kStepAdd: case kStepAct: case kStepPadC: {

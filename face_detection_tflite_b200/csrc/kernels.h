@@ -138,12 +138,16 @@ struct DwPwTcP {
   int in_floats, n_chunks, n_items;   // staged tile size (floats), staging-table / depthwise-table entries
   int w_parts;              // 1: weights exact in TF32; 2: W = W_hi + W_lo (fp32 weights), wB holds both
   int nbuf;                 // 2: double-buffered input tile (the next tile is prefetched during compute)
+  int ns, na, nd;           // k_block_ws: input ring stages, A-operand buffers, depthwise warps
   const float* res; long long res_istride; int res_H, res_W, res_C, res_Cs, res_pool, res_mode, res_lim;
   int TH, TW, G, IH, IW, tilesX, tilesY;
   FastDiv fd_Q8, fd_IW, fd_IH, fd_TW, fd_thw, fd_tpg, fd_tilesX, fd_nstrips, fd_nslots;
   size_t smem_bytes;
 };
 void launch_dwpw_tc(const DwPwTcP& p, int B, cudaStream_t s, int max_ctas);
+// warp-specialised TMA / mbarrier pipeline version (kernels_ws.cu); `cap` = images the input tensor is allocated for.
+// Returns false when the tensor map could not be encoded (nothing launched).
+bool launch_block_ws(const DwPwTcP& p, int B, int cap, cudaStream_t s);
 
 // ---- stem on tensor cores: im2col GEMM from the u8x4 patch ----
 struct StemTcP {

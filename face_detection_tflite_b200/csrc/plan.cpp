@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cstdint>
 
@@ -271,6 +272,7 @@ struct Builder {
     b.resize(st.Cout, 0.f);
     const int w_parts = tf32_exact(w) ? 1 : 2;
     bool tc = use_tc && plan_tc(&F->st, Cin, OH, OW, w_parts);
+    if (tc) plan_ws(&F->st, OH, OW);
     const PStep& fs = F->st;
     if (tc) {
       // B operand [Npad x K8] in the UMMA K-major core-matrix layout (8 rows x 16 bytes per core matrix)
@@ -392,6 +394,67 @@ struct Builder {
       s.nbuf = dbl ? 2 : 1;
       s.smem = dbl ? smem2 : smem1;
       if (s.smem <= cap) { s.kind = kStepDwPwTc; *st = s; return true; }
+    }
+    return false;
+  }
+
+  // Re-plans a kStepDwPwTc step for k_block_ws (kernels_ws.cu): one CTA per SM, the input tile arrives by TMA
+  // into a ring of `ns` stages, the A operand (hi + lo, always 128 rows) is double-buffered when it fits.
+  // Shared-memory formula mirrors the kernel's carve-up.
+  bool plan_ws(PStep* st, int OH, int OW) {
+    static const int want = [] { const char* e = std::getenv("FDT_WS"); return e ? std::atoi(e) : 1; }();
+    static const int want_nd = [] { const char* e = std::getenv("FDT_WS_ND"); return e ? std::atoi(e) : 8; }();
+    static const int max_ns = [] { const char* e = std::getenv("FDT_WS_NS"); return e ? std::atoi(e) : 4; }();
+    static const int max_na = [] { const char* e = std::getenv("FDT_WS_NA"); return e ? std::atoi(e) : 2; }();
+    if (!want) return false;
+    PStep s = *st;
+    s.nd = want_nd == 12 ? 12 : 8;
+    s.tmem_cols = 32;
+    while (s.tmem_cols < 2 * s.Npad) s.tmem_cols *= 2;
+    if (s.tmem_cols > 512) return false;
+    const size_t cap = (size_t)225 * 1024;
+    for (int Pn = 128; Pn >= 32; Pn /= 2) {
+      s.TM = 1; s.NPG = Pn;
+      int bestTH = 0, bestTW = 0, bestG = 1;
+      double best = -1;
+      if (OH * OW <= Pn) {
+        bestTH = OH; bestTW = OW; bestG = Pn / (OH * OW);
+      } else {
+        for (int TW = std::min(OW, Pn); TW >= 1; --TW) {
+          int TH = std::min(OH, Pn / TW);
+          if (TH < 1) continue;
+          double tiles = (double)((OH + TH - 1) / TH) * ((OW + TW - 1) / TW);
+          double util = (double)OH * OW / (tiles * Pn);
+          double halo = (double)((TH - 1) * s.dws + 3) * ((TW - 1) * s.dws + 3) / ((double)TH * TW * s.dws * s.dws);
+          double score = util / (s.has_dw ? halo : 1.0);
+          if (score > best + 1e-9) { best = score; bestTH = TH; bestTW = TW; }
+        }
+      }
+      s.TH = bestTH; s.TW = bestTW; s.G = bestG;
+      s.IH = s.has_dw ? (s.TH - 1) * s.dws + 3 : s.TH;
+      s.IW = s.has_dw ? (s.TW - 1) * s.dws + 3 : s.TW;
+      s.tilesY = (OH + s.TH - 1) / s.TH;
+      s.tilesX = (OW + s.TW - 1) / s.TW;
+      if (s.IH > 256 || s.IW > 256 || s.G > 256 || s.KS > 256) continue;      // TMA box limits
+      s.a_rows = 128;
+      s.RS = 1;
+      for (int rs : {8, 4, 2}) if (s.TH % rs == 0 && s.G * (s.K8 / 4) * (s.TH / rs) * s.TW >= s.nd * 32) { s.RS = rs; break; }
+      size_t n_items = s.has_dw ? (size_t)s.G * (s.K8 / 4) * (s.TH / s.RS) * s.TW : 0;
+      size_t head = ((size_t)s.w_parts * s.Npad * s.K8 + 2 * (size_t)s.Npad + (s.has_dw ? 10 * (size_t)s.K8 : 0)) * 4 + n_items * 8 + 16 * 8 + 128;
+      size_t a_bytes = (size_t)2 * 128 * s.K8 * 4;
+      size_t in_bytes = ((size_t)s.G * s.IH * s.IW * s.KS * 4 + 127) / 128 * 128;
+      static const int combos[5][2] = {{2, 4}, {2, 3}, {2, 2}, {1, 2}, {1, 1}};
+      for (const auto& c : combos) {
+        if (c[0] > max_na || c[1] > max_ns) continue;
+        size_t total = head + c[0] * a_bytes + c[1] * in_bytes;
+        if (total > cap) continue;
+        s.na = c[0]; s.ns = c[1];
+        s.in_stage_floats = (int)(in_bytes / 4);
+        s.smem = total;
+        s.kind = kStepBlockWs;
+        *st = s;
+        return true;
+      }
     }
     return false;
   }
@@ -741,7 +804,7 @@ bool Plan::build(const TfModel& m, int fuse, std::string* err, bool use_tc) {
 }
 
 std::string Plan::describe() const {
-  static const char* kn[] = {"normalize", "naive_conv", "gemm_conv", "dwpw", "add", "act", "padc", "maxpool", "resize", "stem", "dwpw_tc", "stem_tc"};
+  static const char* kn[] = {"normalize", "naive_conv", "gemm_conv", "dwpw", "add", "act", "padc", "maxpool", "resize", "stem", "dwpw_tc", "stem_tc", "block_ws"};
   std::string s;
   char buf[512];
   double macs = 0;
@@ -750,10 +813,10 @@ std::string Plan::describe() const {
     const PTensor& o = tensors[st.out];
     macs += st.macs;
     snprintf(buf, sizeof buf,
-             "%3zu %-10s in=%d res=%d%s/m%d out=%d[%dx%dx%d Cs%d %s] act=%d dw=%d/s%d K=%d NC=%dx%d TM=%d NPG=%d tile=%dx%dx%d smem=%zu  %s\n",
+             "%3zu %-10s in=%d res=%d%s/m%d out=%d[%dx%dx%d Cs%d %s] act=%d dw=%d/s%d K=%d NC=%dx%d TM=%d NPG=%d tile=%dx%dx%d ns=%d na=%d smem=%zu  %s\n",
              i, kn[st.kind], st.in >= 0 ? tensors[st.in].tf : -1, st.in2 >= 0 ? tensors[st.in2].tf : -1,
              st.res_pool ? "(pool)" : "", st.res_mode, o.tf, o.H, o.W, o.C, o.Cs, o.root >= 0 ? "view" : "arena", st.act,
-             (int)st.has_dw, st.dws, st.K, st.NC, st.nchunks, st.TM, st.NPG, st.TH, st.TW, st.G, st.smem, st.name.c_str());
+             (int)st.has_dw, st.dws, st.K, st.NC, st.nchunks, st.TM, st.NPG, st.TH, st.TW, st.G, st.ns, st.na, st.smem, st.name.c_str());
     s += buf;
   }
   snprintf(buf, sizeof buf, "steps=%zu  MACs/image=%.3fM  arena/image=%.1f KB  weights=%.1f KB\n", steps.size(),
