@@ -100,10 +100,156 @@ __device__ __forceinline__ float4 max4(const float4& a, const float4& b) {
 __device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
-// Shared-memory carve-up (must match ws_smem_bytes in plan.cpp):
+__device__ __forceinline__ float4 lds4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// a >= 0 ? a : alpha * a   with alpha = 0 (ReLU), 1 (none) or the PReLU slope: max(a,0) + alpha * min(a,0), exact in all three cases
+__device__ __forceinline__ float4 leaky4(const float4& a, const float4& al) {
+  return make_float4(fmaf(al.x, fminf(a.x, 0.f), fmaxf(a.x, 0.f)), fmaf(al.y, fminf(a.y, 0.f), fmaxf(a.y, 0.f)),
+                     fmaf(al.z, fminf(a.z, 0.f), fmaxf(a.z, 0.f)), fmaf(al.w, fminf(a.w, 0.f), fmaxf(a.w, 0.f)));
+}
+
+// ---- depthwise 3x3 of one work item: RS output rows of one channel quad at one tile column -------------------
+// Row-streaming form: every staged input row is loaded once (3 LDS.128) and scattered into the accumulators of the
+// up to three output rows it feeds, so only the accumulators stay live (no 3-row window in registers).  Each output
+// still sums bias, then taps (ky, kx) in row-major order - the same order as the per-output form.
+template <int S, int RS>
+__device__ __forceinline__ void dw_item(uint32_t base, uint32_t row_b, uint32_t ks_b, const float4 (&w)[9], const float4& bias,
+                                        float* sAhi, float* sAlo, uint32_t sl, uint32_t aq, uint32_t SBO, uint32_t TW) {
+  constexpr int NR = S == 1 ? RS + 2 : 2 * RS + 1;     // staged rows this item reads
+  float4 acc[3];                                        // acc[t % 3] = output row t
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    float4 v[3];
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) v[kx] = lds4(base + (uint32_t)r * row_b + kx * ks_b);
+    if (S == 1) {
+      if (r >= 2) {                                     // ky = 2 of output r-2: complete
+        float4& a = acc[(r - 2) % 3];
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) fma4(a, v[kx], w[6 + kx]);
+        split_store(sAhi, sAlo, ((sl >> 3) * SBO + aq + (sl & 7u) * 16u) >> 2, a);
+        sl += TW;
+      }
+      if (r >= 1 && r - 1 < RS) {                       // ky = 1 of output r-1
+        float4& a = acc[(r - 1) % 3];
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) fma4(a, v[kx], w[3 + kx]);
+      }
+      if (r < RS) {                                     // ky = 0 of output r
+        float4& a = acc[r % 3];
+        a = bias;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) fma4(a, v[kx], w[kx]);
+      }
+    } else {
+      const int t = r >> 1;
+      if ((r & 1) == 0) {
+        if (t >= 1) {                                   // ky = 2 of output t-1: complete
+          float4& a = acc[(t - 1) % 3];
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) fma4(a, v[kx], w[6 + kx]);
+          split_store(sAhi, sAlo, ((sl >> 3) * SBO + aq + (sl & 7u) * 16u) >> 2, a);
+          sl += TW;
+        }
+        if (t < RS) {                                   // ky = 0 of output t
+          float4& a = acc[t % 3];
+          a = bias;
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) fma4(a, v[kx], w[kx]);
+        }
+      } else {                                          // ky = 1 of output t
+        float4& a = acc[t % 3];
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) fma4(a, v[kx], w[3 + kx]);
+      }
+    }
+  }
+}
+
+// ---- epilogue of one tile for the thread's pixel: TMEM -> + bias + residual -> activation -> HBM --------------
+// RES: 0 none, 1 from the staged input tile, 2 from the staged tile with 2x2 max-pool, 3 from HBM (generic path).
+// LEAKY: 0 = ReLU (max only), 1 = slope from sAlpha (1 = identity, PReLU slopes otherwise).
+// Loads of an 8-column group (bias, slopes, residual) are issued before tcgen05.wait::ld so they overlap the TMEM read.
+template <int RES, int LEAKY>
+__device__ __forceinline__ void epi_tile(const DwPwTcP& p, uint32_t tcol0, uint32_t res_a, uint32_t bias_a, uint32_t alpha_a,
+                                         float* orow, bool valid, const float* rbase, int oy, int ox) {
+  const uint32_t ks_b = (uint32_t)p.KS * 4u, row_b = (uint32_t)p.IW * ks_b;
+  for (int c0 = 0; c0 < p.Npad; c0 += 8) {
+    uint32_t u[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                 : "r"(tcol0 + (uint32_t)c0));
+    float4 bv[2], al[2], rv[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int c = c0 + 4 * q;
+      bv[q] = lds4(bias_a + 4u * c);
+      if (LEAKY) al[q] = lds4(alpha_a + 4u * c);
+      rv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (RES == 1) {
+        if (c < p.res_lim) rv[q] = lds4(res_a + 4u * c);
+      } else if (RES == 2) {
+        if (c < p.res_lim)
+          rv[q] = max4(max4(lds4(res_a + 4u * c), lds4(res_a + ks_b + 4u * c)), max4(lds4(res_a + row_b + 4u * c), lds4(res_a + row_b + ks_b + 4u * c)));
+      } else if (RES == 3) {
+        if (valid) {
+          float r4[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ch = c + j;
+            r4[j] = 0.f;
+            if (ch >= p.res_C) continue;
+            if (p.res_pool) {
+              float m = -INFINITY;
+#pragma unroll
+              for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                  int ry = 2 * oy + dy, rx = 2 * ox + dx;
+                  if (ry < p.res_H && rx < p.res_W) m = fmaxf(m, rbase[((size_t)ry * p.res_W + rx) * p.res_Cs + ch]);
+                }
+              r4[j] = m;
+            } else {
+              r4[j] = rbase[((size_t)oy * p.res_W + ox) * p.res_Cs + ch];
+            }
+          }
+          rv[q] = make_float4(r4[0], r4[1], r4[2], r4[3]);
+        }
+      }
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (!valid) continue;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int c = c0 + 4 * q;
+      if (c >= p.CoutS) break;
+      float4 v = make_float4(__uint_as_float(u[4 * q]) + bv[q].x, __uint_as_float(u[4 * q + 1]) + bv[q].y,
+                             __uint_as_float(u[4 * q + 2]) + bv[q].z, __uint_as_float(u[4 * q + 3]) + bv[q].w);
+      add4(v, rv[q]);
+      if (LEAKY) v = leaky4(v, al[q]);
+      else v = max4(v, make_float4(0.f, 0.f, 0.f, 0.f));
+      if (p.vec_store) {
+        // lanes >= Cout need no masking: their weights and bias are zero and the residual is the zero
+        // channel pad there, so they come out as exact zeros
+        *reinterpret_cast<float4*>(orow + c) = v;
+      } else {
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (c + j < p.Cout) orow[c + j] = vv[j];
+      }
+    }
+  }
+}
+
+// Shared-memory carve-up (must match plan_ws in plan.cpp):
 //   [W (w_parts x Npad x K8)] [bias Npad] [alpha Npad] [dw taps+bias 10 x K8] [dtab n_items x 8 B] [barriers 128 B]
 //   | 128-byte aligned: [A ring: NA x (hi, lo) x 128 x K8] [input ring: NS x in_stage_bytes]
-template <int ND>
+// S: depthwise stride (0 = no depthwise, pointwise only); RS: output rows per depthwise work item.
+template <int ND, int S, int RS>
 __global__ void __launch_bounds__((ND + kEpiWarps + 2) * 32, 1)
 k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntiles) {
   extern __shared__ __align__(128) float smem[];
@@ -118,7 +264,7 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
   float* sBias = sB + (size_t)p.w_parts * p.Npad * p.K8;
   float* sAlpha = sBias + p.Npad;
   float* sDw = sAlpha + p.Npad;
-  uint2* dtab = reinterpret_cast<uint2*>(sDw + (p.has_dw ? 10 * p.K8 : 0));
+  uint2* dtab = reinterpret_cast<uint2*>(sDw + (S ? 10 * p.K8 : 0));
   uint64_t* bars = reinterpret_cast<uint64_t*>(dtab + p.n_items);
   const uint32_t a_stage_floats = 2u * 128u * (uint32_t)p.K8;
   float* sA = reinterpret_cast<float*>(((uintptr_t)(bars + 16) + 127) & ~(uintptr_t)127);
@@ -137,9 +283,9 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
   for (int i = tid; i < p.w_parts * p.Npad * Q8; i += kThreads) cp_async16_u32(sB_u32 + 16u * i, p.wB + 4 * (size_t)i);
   for (int i = tid; i < p.Npad; i += kThreads) {
     sBias[i] = p.bias[i];
-    sAlpha[i] = p.alpha ? p.alpha[i] : 0.f;
+    sAlpha[i] = p.act == kActPrelu ? p.alpha[i] : 1.f;   // ReLU takes the max-only epilogue
   }
-  if (p.has_dw) {
+  if (S) {
     for (int i = tid; i < 10 * p.K8; i += kThreads) sDw[i] = i < 9 * p.K8 ? p.dww[i] : p.dwb[i - 9 * p.K8];
     // depthwise table: item = (((g*Q8 + qq)*nstrips + st)*TW + tx)  (tx fastest => conflict-free LDS)
     for (int it = tid; it < p.n_items; it += kThreads) {
@@ -147,10 +293,10 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
       p.fd_TW.divmod(it, r, tx);
       p.fd_nstrips.divmod(r, r2, st);
       p.fd_Q8.divmod(r2, g, qq);
-      const int tyb = st * p.RS;
-      uint32_t in_off = (uint32_t)(((g * p.IH + tyb * p.s) * p.IW + tx * p.s) * p.KS + 4 * qq);
+      const int tyb = st * RS;
+      uint32_t in_off = (uint32_t)(((g * p.IH + tyb * S) * p.IW + tx * S) * p.KS + 4 * qq);
       uint32_t slot0 = (uint32_t)(g * thw + tyb * p.TW + tx);
-      dtab[it] = make_uint2(in_off, slot0 | ((uint32_t)qq << 8));
+      dtab[it] = make_uint2(in_off * 4u, slot0 | ((uint32_t)qq << 8));
     }
   }
   if (tid == 0) {
@@ -190,7 +336,8 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
     const long long o_rel = slot_ok ? (long long)e_g * p.out_istride + ((long long)e_ty * p.OW + e_tx) * p.CoutS : 0;
     const int rs = p.res_pool ? 2 : 1;
     const uint32_t res_off = slot_ok ? (uint32_t)((((size_t)e_g * p.IH + e_ty * rs + p.dpt) * p.IW + e_tx * rs + p.dpl) * p.KS) : 0u;
-    const uint32_t row_f = (uint32_t)p.IW * p.KS;
+    const uint32_t sIn0_a = smem_u32(sIn0), bias_a = smem_u32(sBias), alpha_a = smem_u32(sAlpha);
+    const int res_kind = p.res_mode == 1 ? (p.res_pool ? 2 : 1) : (p.res_mode == 2 ? 3 : 0);
     int si = 0, sph = 0, di = 0, dph = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       int grp, trem, tyi, txi;
@@ -198,7 +345,7 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
       p.fd_tilesX.divmod(trem, tyi, txi);
       const int ty0 = tyi * p.TH, tx0 = txi * p.TW;
       const int b0 = grp * p.G;
-      const float* res_s = sIn0 + (size_t)si * in_stage_floats + res_off;
+      const uint32_t res_a = sIn0_a + ((uint32_t)si * in_stage_floats + res_off) * 4u;
       if (epi_reads_stage) mbar_wait(full_in + 8u * si, (uint32_t)sph);   // visibility of the TMA writes to this thread
       mbar_wait(d_full + 8u * di, (uint32_t)dph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -207,75 +354,16 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
       float* orow = p.out + (long long)b0 * p.out_istride + ((long long)ty0 * p.OW + tx0) * p.CoutS + o_rel;
       const float* rbase = p.res_mode == 2 ? p.res + (size_t)(valid ? b : 0) * p.res_istride : nullptr;
       const uint32_t tcol0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(di * p.Npad);
-      for (int c0 = 0; c0 < p.Npad; c0 += 16) {
-        uint32_t u[16];
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-            : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
-              "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
-            : "r"(tcol0 + (uint32_t)c0));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (!valid) continue;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int c = c0 + 4 * q;
-          if (c >= p.CoutS) break;
-          const float4 bv = ld4(sBias + c);
-          float4 v = make_float4(__uint_as_float(u[4 * q]) + bv.x, __uint_as_float(u[4 * q + 1]) + bv.y,
-                                 __uint_as_float(u[4 * q + 2]) + bv.z, __uint_as_float(u[4 * q + 3]) + bv.w);
-          if (p.res_mode == 1) {
-            // residual straight from the staged tile (channels >= Cin are the zero channel pad)
-            if (c < p.res_lim) {
-              if (p.res_pool) {
-                const float* r1p = res_s + p.KS;
-                const float* r2p = res_s + row_f;
-                const float* r3p = r2p + p.KS;
-                add4(v, max4(max4(ld4(res_s + c), ld4(r1p + c)), max4(ld4(r2p + c), ld4(r3p + c))));
-              } else {
-                add4(v, ld4(res_s + c));
-              }
-            }
-          } else if (p.res_mode == 2) {
-            float rv[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int ch = c + j;
-              rv[j] = 0.f;
-              if (ch >= p.res_C) continue;
-              if (p.res_pool) {
-                float m = -INFINITY;
-#pragma unroll
-                for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-                  for (int dx = 0; dx < 2; ++dx) {
-                    int ry = 2 * oy + dy, rx = 2 * ox + dx;
-                    if (ry < p.res_H && rx < p.res_W) m = fmaxf(m, rbase[((size_t)ry * p.res_W + rx) * p.res_Cs + ch]);
-                  }
-                rv[j] = m;
-              } else {
-                rv[j] = rbase[((size_t)oy * p.res_W + ox) * p.res_Cs + ch];
-              }
-            }
-            add4(v, make_float4(rv[0], rv[1], rv[2], rv[3]));
-          }
-          if (p.act == kActRelu) {
-            v = max4(v, make_float4(0.f, 0.f, 0.f, 0.f));
-          } else if (p.act == kActPrelu) {
-            const float4 a0 = ld4(sAlpha + c);
-            v.x = v.x >= 0.f ? v.x : v.x * a0.x; v.y = v.y >= 0.f ? v.y : v.y * a0.y;
-            v.z = v.z >= 0.f ? v.z : v.z * a0.z; v.w = v.w >= 0.f ? v.w : v.w * a0.w;
-          }
-          if (p.vec_store) {
-            // lanes >= Cout need no masking: their weights and bias are zero and the residual is the zero
-            // channel pad there, so they come out as exact zeros
-            *reinterpret_cast<float4*>(orow + c) = v;
-          } else {
-            const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (c + j < p.Cout) orow[c + j] = vv[j];
-          }
-        }
+      if (p.act == kActRelu) {
+        if (res_kind == 1) epi_tile<1, 0>(p, tcol0, res_a, bias_a, alpha_a, orow, valid, rbase, oy, ox);
+        else if (res_kind == 2) epi_tile<2, 0>(p, tcol0, res_a, bias_a, alpha_a, orow, valid, rbase, oy, ox);
+        else if (res_kind == 3) epi_tile<3, 0>(p, tcol0, res_a, bias_a, alpha_a, orow, valid, rbase, oy, ox);
+        else epi_tile<0, 0>(p, tcol0, res_a, bias_a, alpha_a, orow, valid, rbase, oy, ox);
+      } else {
+        if (res_kind == 1) epi_tile<1, 1>(p, tcol0, res_a, bias_a, alpha_a, orow, valid, rbase, oy, ox);
+        else if (res_kind == 2) epi_tile<2, 1>(p, tcol0, res_a, bias_a, alpha_a, orow, valid, rbase, oy, ox);
+        else if (res_kind == 3) epi_tile<3, 1>(p, tcol0, res_a, bias_a, alpha_a, orow, valid, rbase, oy, ox);
+        else epi_tile<0, 1>(p, tcol0, res_a, bias_a, alpha_a, orow, valid, rbase, oy, ox);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -289,63 +377,41 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
   } else if (warp < kEpiWarps + ND) {
     // =============================== depthwise / A-operand warps ====================================
     const int dtid = tid - kEpiWarps * 32;
-    const uint32_t row_f = (uint32_t)p.IW * p.KS;
+    const uint32_t ks_b = (uint32_t)p.KS * 4u, row_b = (uint32_t)p.IW * ks_b;
+    const uint32_t sIn0_a = smem_u32(sIn0), sDw_a = smem_u32(sDw);
+    // one work item per thread: its taps stay in registers for the whole kernel
+    const bool hoist = S != 0 && p.n_items <= kDwThreads;
+    const bool mine = hoist && dtid < p.n_items;
+    uint2 e0 = make_uint2(0u, 0u);
+    float4 w0[9], bias0 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) w0[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (S != 0 && mine) {
+      e0 = dtab[dtid];
+      const uint32_t wq = sDw_a + 16u * (e0.y >> 8);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) w0[t] = lds4(wq + (uint32_t)(t * p.K8) * 4u);
+      bias0 = lds4(wq + (uint32_t)(9 * p.K8) * 4u);
+    }
     int si = 0, sph = 0, ai = 0, aph = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const float* sIn = sIn0 + (size_t)si * in_stage_floats;
+      const uint32_t sIn_a = sIn0_a + (uint32_t)si * in_stage_floats * 4u;
       float* sAhi = sA + (size_t)ai * a_stage_floats;
       float* sAlo = sAhi + 128 * p.K8;
       mbar_wait(full_in + 8u * si, (uint32_t)sph);
       mbar_wait(a_empty + 8u * ai, (uint32_t)(aph ^ 1));
-      if (p.has_dw) {
-        for (int it = dtid; it < p.n_items; it += kDwThreads) {
-          const uint2 e = dtab[it];
-          const uint32_t qq = e.y >> 8;
-          uint32_t sl = e.y & 0xFFu;
-          const float* wq = sDw + 4 * qq;
-          float4 w[9];
+      if (S != 0) {
+        if (hoist) {
+          if (mine) dw_item<S ? S : 1, RS>(sIn_a + e0.x, row_b, ks_b, w0, bias0, sAhi, sAlo, e0.y & 0xFFu, (e0.y >> 8) * kLBO, SBO, (uint32_t)p.TW);
+        } else {
+          for (int it = dtid; it < p.n_items; it += kDwThreads) {
+            const uint2 e = dtab[it];
+            const uint32_t wq = sDw_a + 16u * (e.y >> 8);
+            float4 w[9];
 #pragma unroll
-          for (int t = 0; t < 9; ++t) w[t] = ld4(wq + t * p.K8);
-          const float4 bias = ld4(wq + 9 * p.K8);
-          const float* base = sIn + e.x;
-          const uint32_t aq = qq * kLBO;
-          if (p.s == 1) {
-            float4 r0[3], r1[3], rr[3];
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              r0[kx] = ld4(base + kx * p.KS);
-              r1[kx] = ld4(base + row_f + kx * p.KS);
-            }
-            const float* nrow = base + 2 * row_f;
-            for (int t = 0; t < p.RS; ++t) {
-#pragma unroll
-              for (int kx = 0; kx < 3; ++kx) rr[kx] = ld4(nrow + kx * p.KS);
-              float4 a = bias;
-#pragma unroll
-              for (int kx = 0; kx < 3; ++kx) fma4(a, r0[kx], w[kx]);
-#pragma unroll
-              for (int kx = 0; kx < 3; ++kx) fma4(a, r1[kx], w[3 + kx]);
-#pragma unroll
-              for (int kx = 0; kx < 3; ++kx) fma4(a, rr[kx], w[6 + kx]);
-              split_store(sAhi, sAlo, ((sl >> 3) * SBO + aq + (sl & 7u) * 16u) >> 2, a);
-#pragma unroll
-              for (int kx = 0; kx < 3; ++kx) { r0[kx] = r1[kx]; r1[kx] = rr[kx]; }
-              nrow += row_f;
-              sl += p.TW;
-            }
-          } else {
-            const float* row = base;
-            for (int t = 0; t < p.RS; ++t) {
-              float4 a = bias;
-#pragma unroll
-              for (int ky = 0; ky < 3; ++ky) {
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx) fma4(a, ld4(row + ky * row_f + kx * p.KS), w[ky * 3 + kx]);
-              }
-              split_store(sAhi, sAlo, ((sl >> 3) * SBO + aq + (sl & 7u) * 16u) >> 2, a);
-              row += 2 * row_f;
-              sl += p.TW;
-            }
+            for (int t = 0; t < 9; ++t) w[t] = lds4(wq + (uint32_t)(t * p.K8) * 4u);
+            const float4 bias = lds4(wq + (uint32_t)(9 * p.K8) * 4u);
+            dw_item<S ? S : 1, RS>(sIn_a + e.x, row_b, ks_b, w, bias, sAhi, sAlo, e.y & 0xFFu, (e.y >> 8) * kLBO, SBO, (uint32_t)p.TW);
           }
         }
       } else {
@@ -353,7 +419,7 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
         for (int it = dtid; it < nslots * Q8; it += kDwThreads) {
           int qq, sl;
           p.fd_nslots.divmod(it, qq, sl);
-          const float4 a = ld4(sIn + (size_t)sl * p.KS + 4 * qq);
+          const float4 a = lds4(sIn_a + ((uint32_t)sl * (uint32_t)p.KS + 4u * qq) * 4u);
           split_store(sAhi, sAlo, (((uint32_t)sl >> 3) * SBO + (uint32_t)qq * kLBO + ((uint32_t)sl & 7u) * 16u) >> 2, a);
         }
       }
@@ -465,8 +531,8 @@ bool input_tensor_map(const DwPwTcP& p, int cap, CUtensorMap* out) {
   return true;
 }
 
-template <int ND>
-void launch_ws_nd(const CUtensorMap& tm, const DwPwTcP& p, int B, int ntiles, cudaStream_t s) {
+template <int ND, int S, int RS>
+void launch_ws_k(const CUtensorMap& tm, const DwPwTcP& p, int B, int ntiles, cudaStream_t s) {
   static std::mutex mu;
   static std::map<int, size_t> cur;
   int dev = 0;
@@ -475,13 +541,30 @@ void launch_ws_nd(const CUtensorMap& tm, const DwPwTcP& p, int B, int ntiles, cu
     std::lock_guard<std::mutex> g(mu);
     size_t& c = cur[dev];
     if (p.smem_bytes > c) {
-      cudaFuncSetAttribute(k_block_ws<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
+      cudaFuncSetAttribute(k_block_ws<ND, S, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
       c = p.smem_bytes;
     }
   }
   int grid = std::min(ntiles, 148);
   if (grid < 1) grid = 1;
-  k_block_ws<ND><<<grid, (ND + kEpiWarps + 2) * 32, p.smem_bytes, s>>>(tm, p, B, ntiles);
+  k_block_ws<ND, S, RS><<<grid, (ND + kEpiWarps + 2) * 32, p.smem_bytes, s>>>(tm, p, B, ntiles);
+}
+
+template <int ND>
+void launch_ws_nd(const CUtensorMap& tm, const DwPwTcP& p, int B, int ntiles, cudaStream_t s) {
+  const int S = p.has_dw ? p.s : 0;
+  switch (S * 16 + (S ? p.RS : 1)) {
+    case 1: launch_ws_k<ND, 0, 1>(tm, p, B, ntiles, s); break;
+    case 16 + 1: launch_ws_k<ND, 1, 1>(tm, p, B, ntiles, s); break;
+    case 16 + 2: launch_ws_k<ND, 1, 2>(tm, p, B, ntiles, s); break;
+    case 16 + 4: launch_ws_k<ND, 1, 4>(tm, p, B, ntiles, s); break;
+    case 16 + 8: launch_ws_k<ND, 1, 8>(tm, p, B, ntiles, s); break;
+    case 32 + 1: launch_ws_k<ND, 2, 1>(tm, p, B, ntiles, s); break;
+    case 32 + 2: launch_ws_k<ND, 2, 2>(tm, p, B, ntiles, s); break;
+    case 32 + 4: launch_ws_k<ND, 2, 4>(tm, p, B, ntiles, s); break;
+    case 32 + 8: launch_ws_k<ND, 2, 8>(tm, p, B, ntiles, s); break;
+    default: break;
+  }
 }
 
 }  // namespace

@@ -403,12 +403,11 @@ struct Builder {
   // Shared-memory formula mirrors the kernel's carve-up.
   bool plan_ws(PStep* st, int OH, int OW) {
     static const int want = [] { const char* e = std::getenv("FDT_WS"); return e ? std::atoi(e) : 1; }();
-    static const int want_nd = [] { const char* e = std::getenv("FDT_WS_ND"); return e ? std::atoi(e) : 8; }();
+    static const int want_nd = [] { const char* e = std::getenv("FDT_WS_ND"); return e ? std::atoi(e) : 0; }();
     static const int max_ns = [] { const char* e = std::getenv("FDT_WS_NS"); return e ? std::atoi(e) : 4; }();
     static const int max_na = [] { const char* e = std::getenv("FDT_WS_NA"); return e ? std::atoi(e) : 2; }();
     if (!want) return false;
     PStep s = *st;
-    s.nd = want_nd == 12 ? 12 : 8;
     s.tmem_cols = 32;
     while (s.tmem_cols < 2 * s.Npad) s.tmem_cols *= 2;
     if (s.tmem_cols > 512) return false;
@@ -437,8 +436,25 @@ struct Builder {
       s.tilesX = (OW + s.TW - 1) / s.TW;
       if (s.IH > 256 || s.IW > 256 || s.G > 256 || s.KS > 256) continue;      // TMA box limits
       s.a_rows = 128;
-      s.RS = 1;
-      for (int rs : {8, 4, 2}) if (s.TH % rs == 0 && s.G * (s.K8 / 4) * (s.TH / rs) * s.TW >= s.nd * 32) { s.RS = rs; break; }
+      // Depthwise work split: ND warps (8 with 128 registers, 12 with 96) and RS output rows per item, chosen by an
+      // instruction-count estimate per thread and tile; one item per thread lets the taps stay in registers.
+      s.RS = 1; s.nd = 8;
+      if (s.has_dw) {
+        double best_cost = 1e30;
+        for (int nd : {12, 8}) {
+          if (want_nd && nd != want_nd) continue;
+          for (int rs : {1, 2, 4}) {
+            if (s.TH % rs || rs > (nd == 12 ? 2 : 4)) continue;
+            int items = s.G * (s.K8 / 4) * (s.TH / rs) * s.TW;
+            int m = (items + nd * 32 - 1) / (nd * 32);
+            int rows = s.dws == 1 ? rs + 2 : 2 * rs + 1;
+            double cost = m * ((m > 1 ? 14 : 0) + 3.0 * rows + 50.0 * rs + 10);
+            if (cost < best_cost - 1e-9) { best_cost = cost; s.RS = rs; s.nd = nd; }
+          }
+        }
+      } else if (want_nd == 12) {
+        s.nd = 12;
+      }
       size_t n_items = s.has_dw ? (size_t)s.G * (s.K8 / 4) * (s.TH / s.RS) * s.TW : 0;
       size_t head = ((size_t)s.w_parts * s.Npad * s.K8 + 2 * (size_t)s.Npad + (s.has_dw ? 10 * (size_t)s.K8 : 0)) * 4 + n_items * 8 + 16 * 8 + 128;
       size_t a_bytes = (size_t)2 * 128 * s.K8 * 4;
@@ -813,10 +829,10 @@ std::string Plan::describe() const {
     const PTensor& o = tensors[st.out];
     macs += st.macs;
     snprintf(buf, sizeof buf,
-             "%3zu %-10s in=%d res=%d%s/m%d out=%d[%dx%dx%d Cs%d %s] act=%d dw=%d/s%d K=%d NC=%dx%d TM=%d NPG=%d tile=%dx%dx%d ns=%d na=%d smem=%zu  %s\n",
+             "%3zu %-10s in=%d res=%d%s/m%d out=%d[%dx%dx%d Cs%d %s] act=%d dw=%d/s%d K=%d NC=%dx%d TM=%d NPG=%d tile=%dx%dx%d RS=%d nd=%d ns=%d na=%d smem=%zu  %s\n",
              i, kn[st.kind], st.in >= 0 ? tensors[st.in].tf : -1, st.in2 >= 0 ? tensors[st.in2].tf : -1,
              st.res_pool ? "(pool)" : "", st.res_mode, o.tf, o.H, o.W, o.C, o.Cs, o.root >= 0 ? "view" : "arena", st.act,
-             (int)st.has_dw, st.dws, st.K, st.NC, st.nchunks, st.TM, st.NPG, st.TH, st.TW, st.G, st.ns, st.na, st.smem, st.name.c_str());
+             (int)st.has_dw, st.dws, st.K, st.NC, st.nchunks, st.TM, st.NPG, st.TH, st.TW, st.G, st.RS, st.nd, st.ns, st.na, st.smem, st.name.c_str());
     s += buf;
   }
   snprintf(buf, sizeof buf, "steps=%zu  MACs/image=%.3fM  arena/image=%.1f KB  weights=%.1f KB\n", steps.size(),
