@@ -169,6 +169,41 @@ __device__ __forceinline__ void dw_item(uint32_t base, uint32_t row_b, uint32_t 
   }
 }
 
+// ---- fast epilogue (float4 stores, residual none / staged / staged + 2x2 max-pool, staged pixel stride KS >= CoutS) ----
+// Straight-line per 8-column group: TMEM load, bias and residual LDS issued before tcgen05.wait::ld, add, activation,
+// two float4 stores.  Channels >= Cout inside CoutS come out as exact zeros (zero weights, bias and TMA zero fill).
+template <int RES, int LEAKY>
+__device__ __forceinline__ void epi_fast(uint32_t tcol0, uint32_t res_a, uint32_t bias_a, uint32_t alpha_a, float* orow, bool valid,
+                                         int cout_s, uint32_t ks_b, uint32_t row_b) {
+#pragma unroll 1
+  for (int c0 = 0; c0 < cout_s; c0 += 8) {
+    uint32_t u[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                 : "r"(tcol0 + (uint32_t)c0));
+    const uint32_t cb = 4u * (uint32_t)c0;
+    float4 b0 = lds4(bias_a + cb), b1 = lds4(bias_a + cb + 16u);
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, a0 = r0, a1 = r0;
+    if (LEAKY) { a0 = lds4(alpha_a + cb); a1 = lds4(alpha_a + cb + 16u); }
+    if (RES == 1) {
+      r0 = lds4(res_a + cb); r1 = lds4(res_a + cb + 16u);
+    } else if (RES == 2) {
+      r0 = max4(max4(lds4(res_a + cb), lds4(res_a + ks_b + cb)), max4(lds4(res_a + row_b + cb), lds4(res_a + row_b + ks_b + cb)));
+      r1 = max4(max4(lds4(res_a + cb + 16u), lds4(res_a + ks_b + cb + 16u)), max4(lds4(res_a + row_b + cb + 16u), lds4(res_a + row_b + ks_b + cb + 16u)));
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    float4 v0 = make_float4(__uint_as_float(u[0]) + b0.x, __uint_as_float(u[1]) + b0.y, __uint_as_float(u[2]) + b0.z, __uint_as_float(u[3]) + b0.w);
+    float4 v1 = make_float4(__uint_as_float(u[4]) + b1.x, __uint_as_float(u[5]) + b1.y, __uint_as_float(u[6]) + b1.z, __uint_as_float(u[7]) + b1.w);
+    if (RES) { add4(v0, r0); add4(v1, r1); }
+    if (LEAKY) { v0 = leaky4(v0, a0); v1 = leaky4(v1, a1); }
+    else { v0 = max4(v0, make_float4(0.f, 0.f, 0.f, 0.f)); v1 = max4(v1, make_float4(0.f, 0.f, 0.f, 0.f)); }
+    if (valid) {
+      *reinterpret_cast<float4*>(orow + c0) = v0;
+      if (c0 + 4 < cout_s) *reinterpret_cast<float4*>(orow + c0 + 4) = v1;
+    }
+  }
+}
+
 // ---- epilogue of one tile for the thread's pixel: TMEM -> + bias + residual -> activation -> HBM --------------
 // RES: 0 none, 1 from the staged input tile, 2 from the staged tile with 2x2 max-pool, 3 from HBM (generic path).
 // LEAKY: 0 = ReLU (max only), 1 = slope from sAlpha (1 = identity, PReLU slopes otherwise).
@@ -283,7 +318,7 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
   for (int i = tid; i < p.w_parts * p.Npad * Q8; i += kThreads) cp_async16_u32(sB_u32 + 16u * i, p.wB + 4 * (size_t)i);
   for (int i = tid; i < p.Npad; i += kThreads) {
     sBias[i] = p.bias[i];
-    sAlpha[i] = p.act == kActPrelu ? p.alpha[i] : 1.f;   // ReLU takes the max-only epilogue
+    sAlpha[i] = p.act == kActPrelu ? p.alpha[i] : (p.act == kActRelu ? 0.f : 1.f);
   }
   if (S) {
     for (int i = tid; i < 10 * p.K8; i += kThreads) sDw[i] = i < 9 * p.K8 ? p.dww[i] : p.dwb[i - 9 * p.K8];
@@ -338,6 +373,8 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
     const uint32_t res_off = slot_ok ? (uint32_t)((((size_t)e_g * p.IH + e_ty * rs + p.dpt) * p.IW + e_tx * rs + p.dpl) * p.KS) : 0u;
     const uint32_t sIn0_a = smem_u32(sIn0), bias_a = smem_u32(sBias), alpha_a = smem_u32(sAlpha);
     const int res_kind = p.res_mode == 1 ? (p.res_pool ? 2 : 1) : (p.res_mode == 2 ? 3 : 0);
+    const bool fast = p.vec_store && res_kind != 3 && (res_kind == 0 || p.KS >= p.CoutS);
+    const uint32_t ks_b = (uint32_t)p.KS * 4u, row_b = (uint32_t)p.IW * ks_b;
     int si = 0, sph = 0, di = 0, dph = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       int grp, trem, tyi, txi;
@@ -354,11 +391,16 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
       float* orow = p.out + (long long)b0 * p.out_istride + ((long long)ty0 * p.OW + tx0) * p.CoutS + o_rel;
       const float* rbase = p.res_mode == 2 ? p.res + (size_t)(valid ? b : 0) * p.res_istride : nullptr;
       const uint32_t tcol0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(di * p.Npad);
-      if (p.act == kActRelu) {
-        if (res_kind == 1) epi_tile<1, 0>(p, tcol0, res_a, bias_a, alpha_a, orow, valid, rbase, oy, ox);
-        else if (res_kind == 2) epi_tile<2, 0>(p, tcol0, res_a, bias_a, alpha_a, orow, valid, rbase, oy, ox);
-        else if (res_kind == 3) epi_tile<3, 0>(p, tcol0, res_a, bias_a, alpha_a, orow, valid, rbase, oy, ox);
-        else epi_tile<0, 0>(p, tcol0, res_a, bias_a, alpha_a, orow, valid, rbase, oy, ox);
+      if (fast) {
+        if (p.act == kActRelu) {
+          if (res_kind == 1) epi_fast<1, 0>(tcol0, res_a, bias_a, alpha_a, orow, valid, p.CoutS, ks_b, row_b);
+          else if (res_kind == 2) epi_fast<2, 0>(tcol0, res_a, bias_a, alpha_a, orow, valid, p.CoutS, ks_b, row_b);
+          else epi_fast<0, 0>(tcol0, res_a, bias_a, alpha_a, orow, valid, p.CoutS, ks_b, row_b);
+        } else {
+          if (res_kind == 1) epi_fast<1, 1>(tcol0, res_a, bias_a, alpha_a, orow, valid, p.CoutS, ks_b, row_b);
+          else if (res_kind == 2) epi_fast<2, 1>(tcol0, res_a, bias_a, alpha_a, orow, valid, p.CoutS, ks_b, row_b);
+          else epi_fast<0, 1>(tcol0, res_a, bias_a, alpha_a, orow, valid, p.CoutS, ks_b, row_b);
+        }
       } else {
         if (res_kind == 1) epi_tile<1, 1>(p, tcol0, res_a, bias_a, alpha_a, orow, valid, rbase, oy, ox);
         else if (res_kind == 2) epi_tile<2, 1>(p, tcol0, res_a, bias_a, alpha_a, orow, valid, rbase, oy, ox);
@@ -558,11 +600,9 @@ void launch_ws_nd(const CUtensorMap& tm, const DwPwTcP& p, int B, int ntiles, cu
     case 16 + 1: launch_ws_k<ND, 1, 1>(tm, p, B, ntiles, s); break;
     case 16 + 2: launch_ws_k<ND, 1, 2>(tm, p, B, ntiles, s); break;
     case 16 + 4: launch_ws_k<ND, 1, 4>(tm, p, B, ntiles, s); break;
-    case 16 + 8: launch_ws_k<ND, 1, 8>(tm, p, B, ntiles, s); break;
     case 32 + 1: launch_ws_k<ND, 2, 1>(tm, p, B, ntiles, s); break;
     case 32 + 2: launch_ws_k<ND, 2, 2>(tm, p, B, ntiles, s); break;
     case 32 + 4: launch_ws_k<ND, 2, 4>(tm, p, B, ntiles, s); break;
-    case 32 + 8: launch_ws_k<ND, 2, 8>(tm, p, B, ntiles, s); break;
     default: break;
   }
 }

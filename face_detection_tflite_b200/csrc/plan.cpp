@@ -408,6 +408,14 @@ struct Builder {
     static const int max_na = [] { const char* e = std::getenv("FDT_WS_NA"); return e ? std::atoi(e) : 2; }();
     if (!want) return false;
     PStep s = *st;
+    // staged pixel stride: >= K8 (and >= CoutS when the residual is read from the stage, so the epilogue needs no
+    // channel guard: the TMA zero-fills everything past CinS), an odd number of 16-byte quads (conflict-free LDS.128)
+    {
+      int ks = s.K8;
+      if (s.res_mode == 1 && ru(s.Cout, 4) > ks) ks = ru(s.Cout, 4);
+      if ((ks / 4) % 2 == 0) ks += 4;
+      s.KS = ks;
+    }
     s.tmem_cols = 32;
     while (s.tmem_cols < 2 * s.Npad) s.tmem_cols *= 2;
     if (s.tmem_cols > 512) return false;
