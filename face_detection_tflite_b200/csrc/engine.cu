@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 namespace fdt {
 
@@ -104,6 +105,20 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         p.wB = blob + st.w; p.bias = blob + st.bias; p.alpha = st.alpha >= 0 ? blob + st.alpha : nullptr;
         p.act = st.act; p.Npad = st.Npad; p.tmem_cols = st.tmem_cols; p.w_parts = st.w_parts; p.smem_bytes = st.smem;
         launch_stem_tc(p, B, s);
+        break;
+      }
+      case kStepStemWs: {
+        StemWsP p;
+        const PTensor& it = plan_.tensors[st.in];
+        p.in8 = in_u8; p.H = it.H; p.W = it.W; p.OH = out.H; p.OW = out.W;
+        p.kw = st.kw; p.pt = st.pt; p.pl = st.pl;
+        p.out = out.p; p.out_istride = out.istride; p.Cout = st.Cout; p.CoutS = out.Cs;
+        p.vec_store = (out.Cs % 4 == 0 && out.istride % 4 == 0 && ((size_t)out.p % 16 == 0)) ? 1 : 0;
+        p.wB = blob + st.w; p.bias = blob + st.bias; p.alpha = st.alpha >= 0 ? blob + st.alpha : nullptr;
+        p.act = st.act; p.Npad = st.Npad; p.K8 = st.K8; p.tmem_cols = st.tmem_cols; p.w_parts = st.w_parts;
+        p.out_scale = (float)st.out_scale; p.smem_bytes = st.smem;
+        { static const int dbg = [] { const char* e = std::getenv("FDT_STEM_DBG"); return e ? std::atoi(e) : 0; }(); p.dbg = dbg; }
+        if (!launch_stem_ws(p, B, ctx.cap, s)) fprintf(stderr, "fdt: cuTensorMapEncodeTiled failed for step '%s'\n", st.name.c_str());
         break;
       }
       case kStepGemmConv: {

@@ -901,7 +901,7 @@ int32_t fdt_get_step_info(fdt_handle* h, int32_t launch, char* kernel, char* ten
   const Plan& p = h->det.plan();
   const int S = (int)p.steps.size();
   if (launch < 0 || launch > S + 1) return fail(h, FDT_ERR_BAD_ARG, "launch index out of range");
-  static const char* kn[] = {"k_normalize", "k_naive_conv", "k_gemm_conv", "k_dwpw", "k_add", "k_act", "k_padc", "k_maxpool", "k_resize_bilinear", "k_stem", "k_dwpw_tc", "k_stem_tc", "k_block_ws"};
+  static const char* kn[] = {"k_normalize", "k_naive_conv", "k_gemm_conv", "k_dwpw", "k_add", "k_act", "k_padc", "k_maxpool", "k_resize_bilinear", "k_stem", "k_dwpw_tc", "k_stem_tc", "k_block_ws", "k_stem_ws"};
   std::string kname, tname;
   double macs = 0, bytes = 0;
   const int S_w = h->det.in_w(), S_h = h->det.in_h();

@@ -161,6 +161,20 @@ struct StemTcP {
 };
 void launch_stem_tc(const StemTcP& p, int B, cudaStream_t s);
 
+// ---- stem, warp-specialised: TMA patch ring -> exact fp16 im2col (16-byte copies) -> tcgen05 kind::f16 ----
+struct StemWsP {
+  const uint8_t* in8;       // [cap][H][W][4] BGRX
+  int H, W, OH, OW, kw, pt, pl;
+  float* out; long long out_istride; int Cout, CoutS, vec_store;
+  const float* wB;          // w_parts x [Npad x K8] fp16, UMMA K-major core-matrix layout (see plan.cpp)
+  const float* bias; const float* alpha;
+  int act, Npad, K8, tmem_cols, w_parts;
+  float out_scale;
+  int dbg;                  // FDT_STEM_DBG bisect switches (0 in production)
+  size_t smem_bytes;
+};
+bool launch_stem_ws(const StemWsP& p, int B, int cap, cudaStream_t s);
+
 // ---- detector post-processing: one block per image ----
 struct DecodeP {
   const float* boxes; long long boxes_istride;    // [B][N][16]

@@ -19,6 +19,7 @@
 //
 // All hand-offs are mbarriers (full/empty per ring slot); there is no __syncthreads in the steady state.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cstdlib>
@@ -533,6 +534,246 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_stem_ws — the KW x KW / stride-2 input convolution as an exact fp16 im2col GEMM.
+//
+// u8 pixel values minus 127.5 are half-integers in [-127.5, 127.5]: exact in fp16, as are the fp16-origin weights,
+// so one tcgen05.mma.kind::f16 per K step reproduces the fp32 convolution of the normalised image up to the
+// accumulation order (fp32 weights: three fp16 terms).  The im2col matrix costs no arithmetic at all: the converted
+// patch keeps 4 halves {B,G,R,0} per pixel, so the KW taps of one kernel row are SEGP consecutive pixels = CPK
+// 16-byte chunks that are copied verbatim (LDS.128 -> STS.128) into the UMMA K-major core-matrix layout.
+//
+//   warp 16 (1 lane) producer: TMA of the raw u8x4 patch [PH][40] (zero fill outside the image) into a 4-stage ring
+//   warps 8..15     builders : raw -> fp16 patch (PRMT + 2 HSUB2 per pixel pair, 0 outside the image), then im2col
+//   warp 17 (1 lane) MMA     : K8/16 x w_parts tcgen05.mma into one of two TMEM accumulators
+//   warps 0..7      epilogue : two groups of four warps alternate tiles: D * out_scale + bias, ReLU/PReLU, float4 stores
+template <int KW>
+__global__ void __launch_bounds__(576, 1) k_stem_ws(const __grid_constant__ CUtensorMap tmap, StemWsP p, int B, int ntiles) {
+  constexpr int TH = 8, TW = 16, PWP = 36;
+  constexpr int PH = (TH - 1) * 2 + KW;
+  constexpr int SEGP = KW == 5 ? 6 : 4, CPK = SEGP / 2;
+  constexpr int NCH = (KW * CPK + 1) / 2 * 2;          // 16-byte K chunks per row (even)
+  constexpr int K8 = NCH * 8;                          // halves
+  constexpr uint32_t SBO = (uint32_t)NCH * 128u;
+  constexpr int NS = 4, NA = 2;
+  constexpr int RAWW = 40;                             // raw patch row: the TMA box must start 16-byte aligned in x, so it
+                                                       // begins up to 3 pixels left of the patch (offset rx_off) and is 40 wide
+  constexpr uint32_t RAW_STAGE = (PH * RAWW * 4 + 127) / 128 * 128;
+  constexpr uint32_t HP_BYTES = PH * PWP * 8;
+  constexpr uint32_t A_BYTES = 128u * K8 * 2u;
+  extern __shared__ __align__(128) float smem[];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* sW = reinterpret_cast<uint8_t*>(smem);
+  const uint32_t w_bytes = (uint32_t)p.w_parts * p.Npad * K8 * 2u;
+  float* sBias = reinterpret_cast<float*>(sW + w_bytes);
+  float* sAlpha = sBias + p.Npad;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sAlpha + p.Npad);
+  uint8_t* sA = reinterpret_cast<uint8_t*>(((uintptr_t)(bars + 16) + 127) & ~(uintptr_t)127);
+  uint8_t* sHp = sA + NA * A_BYTES;
+  uint8_t* sRaw = sHp + 2 * ((HP_BYTES + 127) / 128 * 128);
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t full_raw = bar0, empty_raw = bar0 + 8u * 4, a_full = bar0 + 8u * 8, a_empty = bar0 + 8u * 10,
+                 d_full = bar0 + 8u * 12, d_empty = bar0 + 8u * 14;
+
+  // ---- prologue ----
+  const uint32_t sW_u32 = smem_u32(sW);
+  for (int i = tid; i < (int)(w_bytes >> 4); i += 576) cp_async16_u32(sW_u32 + 16u * i, reinterpret_cast<const uint8_t*>(p.wB) + 16 * (size_t)i);
+  for (int i = tid; i < p.Npad; i += 576) {
+    sBias[i] = p.bias[i];
+    sAlpha[i] = p.act == kActPrelu ? p.alpha[i] : (p.act == kActRelu ? 0.f : 1.f);
+  }
+  for (int i = tid; i < (int)(NA * A_BYTES / 16); i += 576) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);   // pad chunks stay zero
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(full_raw + 8u * i, 1); mbar_init(empty_raw + 8u * i, 8); }
+    for (int i = 0; i < NA; ++i) { mbar_init(a_full + 8u * i, 8); mbar_init(a_empty + 8u * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(d_full + 8u * i, 1); mbar_init(d_empty + 8u * i, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+  }
+  if (warp == 17) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)p.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  cp_async_wait_all();
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  const int tilesX = (p.OW + TW - 1) / TW, tilesY = (p.OH + TH - 1) / TH;
+  const int tiles_per_img = tilesX * tilesY;
+  const int rx_off = (4 - (p.pl & 3)) & 3;             // ix0 = 32*txi - pl  ->  aligned start ix0 - rx_off
+
+  if (warp < 8) {
+    // =============================== epilogue: group g takes every second tile of this CTA =============
+    const int g = warp >> 2, quarter = warp & 3;
+    const int slot = quarter * 32 + lane;
+    const int e_ty = slot >> 4, e_tx = slot & 15;
+    const uint32_t bias_a = smem_u32(sBias), alpha_a = smem_u32(sAlpha);
+    const float scale = p.out_scale;
+    const bool relu = p.act == kActRelu;
+    int k = 0;
+    for (int tile = blockIdx.x + g * gridDim.x; tile < ntiles; tile += 2 * gridDim.x, ++k) {
+      const int b = tile / tiles_per_img;
+      const int trem = tile - b * tiles_per_img;
+      const int ty0 = (trem / tilesX) * TH, tx0 = (trem % tilesX) * TW;
+      const int oy = ty0 + e_ty, ox = tx0 + e_tx;
+      const bool valid = oy < p.OH && ox < p.OW;
+      float* orow = p.out + (size_t)b * p.out_istride + ((size_t)(valid ? oy : 0) * p.OW + (valid ? ox : 0)) * p.CoutS;
+      mbar_wait(d_full + 8u * g, (uint32_t)(k & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tcol0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * p.Npad);
+#pragma unroll 1
+      for (int c0 = 0; c0 < p.CoutS; c0 += 8) {
+        uint32_t u[8];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                     : "r"(tcol0 + (uint32_t)c0));
+        const uint32_t cb = 4u * (uint32_t)c0;
+        const float4 b0 = lds4(bias_a + cb), b1 = lds4(bias_a + cb + 16u);
+        const float4 a0 = lds4(alpha_a + cb), a1 = lds4(alpha_a + cb + 16u);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float4 v0 = make_float4(fmaf(__uint_as_float(u[0]), scale, b0.x), fmaf(__uint_as_float(u[1]), scale, b0.y),
+                                fmaf(__uint_as_float(u[2]), scale, b0.z), fmaf(__uint_as_float(u[3]), scale, b0.w));
+        float4 v1 = make_float4(fmaf(__uint_as_float(u[4]), scale, b1.x), fmaf(__uint_as_float(u[5]), scale, b1.y),
+                                fmaf(__uint_as_float(u[6]), scale, b1.z), fmaf(__uint_as_float(u[7]), scale, b1.w));
+        if (relu) { v0 = max4(v0, make_float4(0.f, 0.f, 0.f, 0.f)); v1 = max4(v1, make_float4(0.f, 0.f, 0.f, 0.f)); }
+        else { v0 = leaky4(v0, a0); v1 = leaky4(v1, a1); }
+        if (valid) {
+          if (p.vec_store) {
+            *reinterpret_cast<float4*>(orow + c0) = v0;
+            if (c0 + 4 < p.CoutS) *reinterpret_cast<float4*>(orow + c0 + 4) = v1;
+          } else {
+            const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (c0 + j < p.Cout) orow[c0 + j] = vv[j];
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d_empty + 8u * g);
+    }
+  } else if (warp < 16) {
+    // =============================== builders: raw patch -> fp16 patch -> im2col A =======================
+    const int bt = tid - 256;
+    const int r = bt & 127, part = bt >> 7;
+    const int r_ty = r >> 4, r_tx = r & 15;
+    const uint32_t a_row = ((uint32_t)r >> 3) * SBO + ((uint32_t)r & 7u) * 16u;
+    const uint32_t src_px = (uint32_t)((2 * r_ty) * PWP + 2 * r_tx) * 8u;
+    constexpr int KY0 = KW == 5 ? 3 : 2;                 // part 0: ky < KY0, part 1: the rest
+    const int ky_lo = part == 0 ? 0 : KY0, ky_hi = part == 0 ? KY0 : KW;
+    const uint32_t sA_a = smem_u32(sA), sHp_a = smem_u32(sHp), sRaw_a = smem_u32(sRaw);
+    constexpr uint32_t HP_STRIDE = (HP_BYTES + 127) / 128 * 128;
+    int si = 0, sph = 0, ai = 0, aph = 0, hb = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_img;
+      const int trem = tile - b * tiles_per_img;
+      const int iy0 = (trem / tilesX) * TH * 2 - p.pt, ix0 = (trem % tilesX) * TW * 2 - p.pl;
+      mbar_wait(full_raw + 8u * si, (uint32_t)sph);
+      // ---- convert: u8x4 BGRX -> {B,G,R,0} - 127.5 as halves; pixels outside the image (SAME padding) -> 0
+      const uint32_t raw_a = sRaw_a + (uint32_t)si * RAW_STAGE, hp_a = sHp_a + (uint32_t)hb * HP_STRIDE;
+      for (int i = bt; i < PH * PWP; i += 256) {
+        const int ly = i / PWP, lx = i - ly * PWP;
+        uint32_t raw;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw) : "r"(raw_a + 4u * (uint32_t)(ly * RAWW + lx + rx_off)));
+        const bool ok = (unsigned)(iy0 + ly) < (unsigned)p.H && (unsigned)(ix0 + lx) < (unsigned)p.W;
+        uint32_t lo = __byte_perm(raw, 0x64646464u, 0x4140), hi = __byte_perm(raw, 0x64646464u, 0x4342);   // halves 1024 + byte
+        __half2 l = *reinterpret_cast<__half2*>(&lo), h = *reinterpret_cast<__half2*>(&hi);
+        const __half2 k1024 = __floats2half2_rn(1024.f, 1024.f), k127 = __floats2half2_rn(127.5f, 127.5f);
+        l = __hsub2(__hsub2(l, k1024), k127);
+        h = __hsub2(__hsub2(h, k1024), k127);
+        uint32_t lo2 = *reinterpret_cast<uint32_t*>(&l), hi2 = *reinterpret_cast<uint32_t*>(&h) & 0x0000FFFFu;
+        if (!ok) { lo2 = 0u; hi2 = 0u; }
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(hp_a + 8u * i), "r"(lo2), "r"(hi2) : "memory");
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_raw + 8u * si);   // raw stage consumed
+      asm volatile("bar.sync 1, 256;" ::: "memory");      // patch complete (also: every builder has finished the previous gather)
+      mbar_wait(a_empty + 8u * ai, (uint32_t)(aph ^ 1));
+      // ---- im2col: CPK 16-byte chunks per (pixel, ky), copied verbatim
+      const uint32_t dst = sA_a + (uint32_t)ai * A_BYTES + a_row;
+#pragma unroll
+      for (int ky = 0; ky < KW; ++ky) {
+        if (ky < ky_lo || ky >= ky_hi) continue;
+#pragma unroll
+        for (int j = 0; j < CPK; ++j) {
+          uint32_t x0, x1, x2, x3;
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
+                       : "r"(hp_a + src_px + (uint32_t)(ky * PWP * 8 + j * 16)));
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)((ky * CPK + j) * 128)), "r"(x0), "r"(x1), "r"(x2), "r"(x3) : "memory");
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full + 8u * ai);
+      hb ^= 1;
+      if (++si == NS) { si = 0; sph ^= 1; }
+      if (++ai == NA) { ai = 0; aph ^= 1; }
+    }
+  } else if (warp == 16) {
+    // =============================== TMA producer ===================================================
+    if (lane == 0) {
+      int si = 0, sph = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_img;
+        const int trem = tile - b * tiles_per_img;
+        const int iy0 = (trem / tilesX) * TH * 2 - p.pt, ix0 = (trem % tilesX) * TW * 2 - p.pl;
+        mbar_wait(empty_raw + 8u * si, (uint32_t)(sph ^ 1));
+        const uint32_t bar = full_raw + 8u * si;
+        if (p.dbg & 1) { mbar_arrive(bar); } else {
+        mbar_expect_tx(bar, (uint32_t)(PH * RAWW * 4));
+        const uint32_t dst = smem_u32(sRaw) + (uint32_t)si * RAW_STAGE;
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"(dst), "l"(&tmap), "r"(ix0 - rx_off), "r"(iy0), "r"(b), "r"(bar) : "memory");
+        }
+        if (++si == NS) { si = 0; sph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== MMA issuer =====================================================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Npad >> 3) << 17) | ((128u >> 4) << 24);   // D f32, A/B f16, K-major
+      const uint32_t part_bytes = (uint32_t)p.Npad * K8 * 2u;
+      int ai = 0, aph = 0, k = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
+        const int di = k & 1;
+        mbar_wait(a_full + 8u * ai, (uint32_t)aph);
+        mbar_wait(d_empty + 8u * di, (uint32_t)(((k >> 1) & 1) ^ 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_base = smem_u32(sA) + (uint32_t)ai * A_BYTES;
+        const uint32_t dcol = tmem_base + (uint32_t)(di * p.Npad);
+        uint32_t acc = 0u;
+#pragma unroll 1
+        for (int ks = 0; ks < K8 / 16; ++ks) {
+          const uint64_t da = make_desc(a_base + ks * 2 * kLBO, SBO);
+          for (int t = 0; t < p.w_parts; ++t) {
+            const uint64_t db = make_desc(sW_u32 + (uint32_t)t * part_bytes + ks * 2 * kLBO, SBO);
+            if (!(p.dbg & 2)) asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(dcol), "l"(da), "l"(db), "r"(idesc), "r"(acc));
+            acc = 1u;
+          }
+        }
+        mma_commit(a_empty + 8u * ai);
+        mma_commit(d_full + 8u * di);
+        if (++ai == NA) { ai = 0; aph ^= 1; }
+      }
+    }
+    __syncwarp();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 17) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols));
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -607,6 +848,63 @@ void launch_ws_nd(const CUtensorMap& tm, const DwPwTcP& p, int B, int ntiles, cu
   }
 }
 
+// Tensor map of the letterboxed u8x4 image: u32 [cap][H][W], box {40, PH, 1} (x start 16-byte aligned)
+bool stem_tensor_map(const StemWsP& p, int cap, int PH, CUtensorMap* out) {
+  typedef std::tuple<const void*, int, int, int, int> Key;
+  static std::mutex mu;
+  static std::map<Key, CUtensorMap> cache;
+  Key key(p.in8, cap, p.H, p.W, PH);
+  std::lock_guard<std::mutex> g(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return true; }
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t gdim[3] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)cap};
+  cuuint64_t gstr[2] = {(cuuint64_t)p.W * 4, (cuuint64_t)p.W * p.H * 4};
+  cuuint32_t box[3] = {40u, (cuuint32_t)PH, 1u};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap tm;
+  static const int ty = [] { const char* e = std::getenv("FDT_STEM_TMTYPE"); return e ? std::atoi(e) : 0; }();
+  const CUtensorMapDataType dt = ty == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (ty == 2 ? CU_TENSOR_MAP_DATA_TYPE_INT32 : CU_TENSOR_MAP_DATA_TYPE_UINT32);
+  CUresult r = enc(&tm, dt, 3, const_cast<uint8_t*>(p.in8), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  cache[key] = tm;
+  *out = tm;
+  return true;
+}
+
+template <int KW>
+void launch_stem_ws_kw(const CUtensorMap& tm, const StemWsP& p, int B, cudaStream_t s) {
+  static std::mutex mu;
+  static std::map<int, size_t> cur;                       // device -> opted-in dynamic shared memory
+  static std::map<std::pair<int, size_t>, int> occ;       // (device, smem) -> resident CTAs per SM
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int per_sm = 1;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    size_t& c = cur[dev];
+    if (p.smem_bytes > c) {
+      cudaFuncSetAttribute(k_stem_ws<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
+      c = p.smem_bytes;
+    }
+    auto key = std::make_pair(dev, p.smem_bytes);
+    auto it = occ.find(key);
+    if (it == occ.end()) {
+      int nb = 1;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_stem_ws<KW>, 576, p.smem_bytes) != cudaSuccess || nb < 1) nb = 1;
+      it = occ.emplace(key, nb).first;
+    }
+    per_sm = it->second;
+  }
+  const int ntiles = ((p.OW + 15) / 16) * ((p.OH + 7) / 8) * B;
+  int grid = std::min(ntiles, 148 * per_sm);
+  if (grid < 1) grid = 1;
+  k_stem_ws<KW><<<grid, 576, p.smem_bytes, s>>>(tm, p, B, ntiles);
+}
+
 }  // namespace
 
 bool launch_block_ws(const DwPwTcP& p, int B, int cap, cudaStream_t s) {
@@ -619,4 +917,15 @@ bool launch_block_ws(const DwPwTcP& p, int B, int cap, cudaStream_t s) {
   return true;
 }
 
+}  // namespace fdt
+
+namespace fdt {
+bool launch_stem_ws(const StemWsP& p, int B, int cap, cudaStream_t s) {
+  CUtensorMap tm;
+  const int PH = 14 + p.kw;
+  if (!stem_tensor_map(p, cap, PH, &tm)) return false;
+  if (p.kw == 5) launch_stem_ws_kw<5>(tm, p, B, s);
+  else launch_stem_ws_kw<3>(tm, p, B, s);
+  return true;
+}
 }  // namespace fdt

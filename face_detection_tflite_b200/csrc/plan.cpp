@@ -1,6 +1,7 @@
 #include "plan.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -20,6 +21,46 @@ void same_pad(int in, int k, int s, int* before) {
   int total = (out - 1) * s + k - in;
   if (total < 0) total = 0;
   *before = total / 2;
+}
+
+
+// fp32 -> fp16 bit pattern, round to nearest even, subnormals handled; |v| must be below the fp16 overflow threshold
+uint16_t f32_to_f16(float v) {
+  uint32_t x;
+  std::memcpy(&x, &v, 4);
+  const uint32_t sign = (x >> 16) & 0x8000u;
+  const int32_t e = (int32_t)((x >> 23) & 0xFF) - 127 + 15;
+  uint32_t mant = x & 0x7FFFFFu;
+  if (((x >> 23) & 0xFF) == 0) return (uint16_t)sign;          // fp32 zero / subnormal -> 0
+  if (e >= 31) return (uint16_t)(sign | 0x7BFFu);              // clamp (callers scale weights to avoid this)
+  if (e <= 0) {
+    if (e < -10) return (uint16_t)sign;
+    mant |= 0x800000u;
+    const int shift = 14 - e;                                   // 14..24
+    uint32_t h = mant >> shift;
+    const uint32_t rem = mant & ((1u << shift) - 1), half = 1u << (shift - 1);
+    if (rem > half || (rem == half && (h & 1))) ++h;
+    return (uint16_t)(sign | h);
+  }
+  uint32_t h = ((uint32_t)e << 10) | (mant >> 13);
+  const uint32_t rem = mant & 0x1FFFu;
+  if (rem > 0x1000u || (rem == 0x1000u && (h & 1))) ++h;       // may carry into the exponent: still correct
+  return (uint16_t)(sign | h);
+}
+float f16_to_f32(uint16_t h) {
+  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+  int e = (h >> 10) & 0x1F;
+  uint32_t mant = h & 0x3FFu;
+  float out;
+  uint32_t x;
+  if (e == 0) {
+    if (mant == 0) { x = sign; std::memcpy(&out, &x, 4); return out; }
+    float f = (float)mant * 5.9604644775390625e-8f;            // 2^-24
+    return (h & 0x8000u) ? -f : f;
+  }
+  x = sign | ((uint32_t)(e - 15 + 127) << 23) | (mant << 13);
+  std::memcpy(&out, &x, 4);
+  return out;
 }
 
 struct View { int root = -1; long long off = 0; };
@@ -586,7 +627,57 @@ struct Builder {
     if (!m.const_f32(conv.in[1], &w)) return fail("conv weights are not constant");
     if (conv.in.size() > 2 && conv.in[2] >= 0) { if (!m.const_f32(conv.in[2], &b)) return fail("conv bias is not constant"); }
     b.resize(st.Cout, 0.f);
-    if (st.kind == kStepStem && use_tc && ru(st.Cout, 16) <= 128) {
+    static const int want_stem_ws = [] { const char* e = std::getenv("FDT_STEM_WS"); return e ? std::atoi(e) : 1; }();
+    if (st.kind == kStepStem && use_tc && want_stem_ws && ru(st.Cout, 16) <= 64) {
+      // k_stem_ws: im2col GEMM with exact fp16 operands.  A holds (u8 - 127.5) (half-integers, exact in fp16), laid out
+      // per tap row ky as SEGP pixels x {B,G,R,X} halves; W is scaled by a power of two and split into w_parts fp16
+      // terms (1 when the weights are fp16-origin, 3 for fp32 weights); out = D * out_scale + bias.
+      st.kind = kStepStemWs;
+      const int SEGP = st.kw == 5 ? 6 : 4, CPK = SEGP / 2;       // pixels / 16-byte chunks per tap row
+      const int nchunk = ru(st.kw * CPK, 2);                       // K chunks of 8 halves, even (MMA K = 16)
+      st.K8 = nchunk * 8;
+      st.Npad = ru(st.Cout, 16);
+      st.tmem_cols = 32;
+      while (st.tmem_cols < 2 * st.Npad) st.tmem_cols *= 2;
+      float wmax = 0.f;
+      for (float v : w) wmax = std::max(wmax, std::fabs(v));
+      float wscale = 1.f;
+      while (wmax * wscale * 2.f <= 16384.f && wscale < 65536.f) wscale *= 2.f;
+      // parts: how many fp16 terms reproduce every scaled weight exactly (up to 3)
+      int parts = 1;
+      for (float v : w) {
+        float r = v * wscale;
+        int need = 0;
+        for (int t = 0; t < 3 && r != 0.f; ++t) { r -= f16_to_f32(f32_to_f16(r)); need = t + 1; }
+        parts = std::max(parts, std::max(need, 1));
+      }
+      st.w_parts = parts;
+      st.out_scale = 1.0 / (127.5 * (double)wscale);
+      const size_t SBO = (size_t)nchunk * 128, LBO = 128;          // bytes
+      std::vector<uint16_t> hb((size_t)parts * st.Npad * st.K8, 0);
+      for (int n = 0; n < st.Cout; ++n)
+        for (int ky = 0; ky < st.kw; ++ky)
+          for (int kx = 0; kx < st.kw; ++kx)
+            for (int c = 0; c < 3; ++c) {                          // c: 0=B 1=G 2=R in the letterboxed bytes; weights are RGB
+              const int k = (ky * CPK + kx / 2) * 8 + (kx & 1) * 4 + c;
+              float r = w[(((size_t)n * st.kw + ky) * st.kw + kx) * 3 + (2 - c)] * wscale;
+              const size_t o = ((size_t)(n >> 3) * SBO + (size_t)(k >> 3) * LBO + (size_t)(n & 7) * 16 + (size_t)(k & 7) * 2) / 2;
+              for (int t = 0; t < parts; ++t) {
+                const uint16_t hbits = f32_to_f16(r);
+                hb[(size_t)t * st.Npad * st.K8 + o] = hbits;
+                r -= f16_to_f32(hbits);
+              }
+            }
+      std::vector<float> wb((hb.size() + 1) / 2, 0.f);
+      std::memcpy(wb.data(), hb.data(), hb.size() * 2);
+      const int PH = 14 + st.kw;
+      st.ns = 4; st.na = 2;
+      st.smem = (size_t)parts * st.Npad * st.K8 * 2 + 2 * (size_t)st.Npad * 4 + 16 * 8 + 128     // W, bias, alpha, barriers
+                + (size_t)st.na * 128 * st.K8 * 2 + 2 * (size_t)PH * 36 * 8 + (size_t)st.ns * ((PH * 160 + 127) / 128 * 128) + 256;
+      st.w = push(wb, wb.size());
+      st.bias = push(b, (size_t)st.Npad + 8);
+      if (alpha_tf >= 0 && !pack_alpha(alpha_tf, (size_t)st.Npad + 8, &st.alpha)) return false;
+    } else if (st.kind == kStepStem && use_tc && ru(st.Cout, 16) <= 128) {
       st.w_parts = tf32_exact(w) ? 1 : 2;
       // tensor-core stem: B operand [Npad x K8] in the UMMA K-major core-matrix layout
       st.kind = kStepStemTc;
@@ -828,7 +919,7 @@ bool Plan::build(const TfModel& m, int fuse, std::string* err, bool use_tc) {
 }
 
 std::string Plan::describe() const {
-  static const char* kn[] = {"normalize", "naive_conv", "gemm_conv", "dwpw", "add", "act", "padc", "maxpool", "resize", "stem", "dwpw_tc", "stem_tc", "block_ws"};
+  static const char* kn[] = {"normalize", "naive_conv", "gemm_conv", "dwpw", "add", "act", "padc", "maxpool", "resize", "stem", "dwpw_tc", "stem_tc", "block_ws", "stem_ws"};
   std::string s;
   char buf[512];
   double macs = 0;
