@@ -118,7 +118,7 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         p.act = st.act; p.Npad = st.Npad; p.K8 = st.K8; p.tmem_cols = st.tmem_cols; p.w_parts = st.w_parts;
         p.out_scale = (float)st.out_scale; p.smem_bytes = st.smem;
         { static const int dbg = [] { const char* e = std::getenv("FDT_STEM_DBG"); return e ? std::atoi(e) : 0; }(); p.dbg = dbg; }
-        if (!launch_stem_ws(p, B, ctx.cap, s)) fprintf(stderr, "fdt: cuTensorMapEncodeTiled failed for step '%s'\n", st.name.c_str());
+        if (!launch_stem_ws(p, B, ctx.cap, s)) { failed_ = true; fprintf(stderr, "fdt: cuTensorMapEncodeTiled failed for step '%s'\n", st.name.c_str()); }
         break;
       }
       case kStepGemmConv: {
@@ -207,10 +207,10 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
           p.in_floats = (int)((std::max(in, tail) + 3) / 4 * 4);
         }
         p.smem_bytes = st.smem;
-        p.ns = st.ns; p.na = st.na; p.nd = st.nd;
+        p.ns = st.ns; p.na = st.na; p.nd = st.nd; p.nt = st.nt;
         if (st.kind == kStepBlockWs) {
           p.in_floats = st.in_stage_floats;
-          if (!launch_block_ws(p, B, ctx.cap, s)) fprintf(stderr, "fdt: cuTensorMapEncodeTiled failed for step '%s'\n", st.name.c_str());
+          if (!launch_block_ws(p, B, ctx.cap, s)) { failed_ = true; fprintf(stderr, "fdt: cuTensorMapEncodeTiled failed for step '%s'\n", st.name.c_str()); }
         } else {
           launch_dwpw_tc(p, B, s, cta_cap(st.smem, 256));
         }

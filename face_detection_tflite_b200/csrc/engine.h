@@ -30,6 +30,8 @@ class Engine {
   int run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t s, cudaEvent_t* evs = nullptr) const;
   TV view(const EngineCtx& ctx, int ptensor) const;
 
+  // true once a launch could not be issued (tensor map encoding failed): results are invalid, callers must fail
+  bool failed() const { return failed_; }
   const Plan& plan() const { return plan_; }
   const TfModel& model() const { return model_; }
   int in_h() const { return plan_.in_h; }
@@ -40,6 +42,7 @@ class Engine {
   Plan plan_;
   float* d_blob_ = nullptr;
   int max_ctas_ = 148 * 4;
+  mutable bool failed_ = false;
 };
 
 }  // namespace fdt

@@ -438,6 +438,7 @@ int detect_impl(fdt_handle* h, const uint8_t* frames, int batch, int w, int hh, 
       if (!cuda_ok(h, cudaStreamSynchronize(h->streams[i]), "pipeline")) return FDT_ERR_CUDA;
   }
   if (!cuda_ok(h, cudaGetLastError(), "kernel launch")) return FDT_ERR_CUDA;
+  if (h->det.failed() || h->mesh.failed()) { h->err = "TMA tensor map encoding failed (cuTensorMapEncodeTiled)"; return FDT_ERR_CUDA; }
   return FDT_OK;
 }
 

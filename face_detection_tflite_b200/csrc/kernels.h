@@ -138,7 +138,7 @@ struct DwPwTcP {
   int in_floats, n_chunks, n_items;   // staged tile size (floats), staging-table / depthwise-table entries
   int w_parts;              // 1: weights exact in TF32; 2: W = W_hi + W_lo (fp32 weights), wB holds both
   int nbuf;                 // 2: double-buffered input tile (the next tile is prefetched during compute)
-  int ns, na, nd;           // k_block_ws: input ring stages, A-operand buffers, depthwise warps
+  int ns, na, nd, nt;       // k_block_ws: input ring stages, A-operand buffers, depthwise warps, TMEM accumulators
   const float* res; long long res_istride; int res_H, res_W, res_C, res_Cs, res_pool, res_mode, res_lim;
   int TH, TW, G, IH, IW, tilesX, tilesY;
   FastDiv fd_Q8, fd_IW, fd_IH, fd_TW, fd_thw, fd_tpg, fd_tilesX, fd_nstrips, fd_nslots;

@@ -293,6 +293,7 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
   constexpr int kThreads = (ND + kEpiWarps + 2) * 32;
   constexpr int kDwThreads = ND * 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel may begin its own prologue
   const int Q8 = p.K8 >> 2;                       // 16-byte K chunks per row
   const uint32_t SBO = (uint32_t)Q8 * 128u;       // bytes between 8-row groups
   const int NS = p.ns, NA = p.na;
@@ -303,13 +304,14 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
   uint2* dtab = reinterpret_cast<uint2*>(sDw + (S ? 10 * p.K8 : 0));
   uint64_t* bars = reinterpret_cast<uint64_t*>(dtab + p.n_items);
   const uint32_t a_stage_floats = 2u * 128u * (uint32_t)p.K8;
-  float* sA = reinterpret_cast<float*>(((uintptr_t)(bars + 16) + 127) & ~(uintptr_t)127);
+  float* sA = reinterpret_cast<float*>(((uintptr_t)(bars + 32) + 127) & ~(uintptr_t)127);
   float* sIn0 = sA + (size_t)NA * a_stage_floats;
   const uint32_t in_stage_floats = (uint32_t)p.in_floats;     // multiple of 32 floats (128 B)
-  // barrier slots: full_in[NS] | empty_in[NS] | a_full[NA] | a_empty[NA] | d_full[2] | d_empty[2]   (NS <= 4, NA <= 2)
+  // barrier slots: full_in[NS] | empty_in[NS] | a_full[NA] | a_empty[NA] | d_full[NT] | d_empty[NT]   (NS <= 6, NA, NT <= 4)
   const uint32_t bar0 = smem_u32(bars);
-  const uint32_t full_in = bar0, empty_in = bar0 + 8u * 4, a_full = bar0 + 8u * 8, a_empty = bar0 + 8u * 10,
-                 d_full = bar0 + 8u * 12, d_empty = bar0 + 8u * 14;
+  const uint32_t full_in = bar0, empty_in = bar0 + 8u * 6, a_full = bar0 + 8u * 12, a_empty = bar0 + 8u * 16,
+                 d_full = bar0 + 8u * 20, d_empty = bar0 + 8u * 24;
+  const int NT = p.nt;
   const int thw = p.TH * p.TW;
   const int nslots = p.G * thw;
   const bool epi_reads_stage = p.res_mode == 1;
@@ -344,7 +346,7 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
       mbar_init(a_full + 8u * i, ND);
       mbar_init(a_empty + 8u * i, 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NT; ++i) {
       mbar_init(d_full + 8u * i, 1);
       mbar_init(d_empty + 8u * i, kEpiWarps);
     }
@@ -361,6 +363,9 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
+  // Programmatic dependent launch: everything above touched only constants (weights, tables, barriers, TMEM);
+  // the activations written by the previous kernel in the stream are read (and ours written) only after this point.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp < kEpiWarps) {
     // =============================== epilogue warps =================================================
@@ -415,7 +420,7 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
         if (epi_reads_stage) mbar_arrive(empty_in + 8u * si);
       }
       if (++si == NS) { si = 0; sph ^= 1; }
-      if (++di == 2) { di = 0; dph ^= 1; }
+      if (++di == NT) { di = 0; dph ^= 1; }
     }
   } else if (warp < kEpiWarps + ND) {
     // =============================== depthwise / A-operand warps ====================================
@@ -521,7 +526,7 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
         mma_commit(a_empty + 8u * ai);   // operand buffer reusable once these MMAs have read it
         mma_commit(d_full + 8u * di);    // accumulator complete
         if (++ai == NA) { ai = 0; aph ^= 1; }
-        if (++di == 2) { di = 0; dph ^= 1; }
+        if (++di == NT) { di = 0; dph ^= 1; }
       }
     }
     __syncwarp();
@@ -548,14 +553,14 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
 //   warp 17 (1 lane) MMA     : K8/16 x w_parts tcgen05.mma into one of two TMEM accumulators
 //   warps 0..7      epilogue : two groups of four warps alternate tiles: D * out_scale + bias, ReLU/PReLU, float4 stores
 template <int KW>
-__global__ void __launch_bounds__(576, 1) k_stem_ws(const __grid_constant__ CUtensorMap tmap, StemWsP p, int B, int ntiles) {
+__global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUtensorMap tmap, StemWsP p, int B, int ntiles) {
   constexpr int TH = 8, TW = 16, PWP = 36;
   constexpr int PH = (TH - 1) * 2 + KW;
   constexpr int SEGP = KW == 5 ? 6 : 4, CPK = SEGP / 2;
   constexpr int NCH = (KW * CPK + 1) / 2 * 2;          // 16-byte K chunks per row (even)
   constexpr int K8 = NCH * 8;                          // halves
   constexpr uint32_t SBO = (uint32_t)NCH * 128u;
-  constexpr int NS = 4, NA = 2;
+  constexpr int NS = 6, NA = 4, NT = 4;
   constexpr int RAWW = 40;                             // raw patch row: the TMA box must start 16-byte aligned in x, so it
                                                        // begins up to 3 pixels left of the patch (offset rx_off) and is 40 wide
   constexpr uint32_t RAW_STAGE = (PH * RAWW * 4 + 127) / 128 * 128;
@@ -564,17 +569,18 @@ __global__ void __launch_bounds__(576, 1) k_stem_ws(const __grid_constant__ CUte
   extern __shared__ __align__(128) float smem[];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel may begin its own prologue
   uint8_t* sW = reinterpret_cast<uint8_t*>(smem);
   const uint32_t w_bytes = (uint32_t)p.w_parts * p.Npad * K8 * 2u;
   float* sBias = reinterpret_cast<float*>(sW + w_bytes);
   float* sAlpha = sBias + p.Npad;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sAlpha + p.Npad);
-  uint8_t* sA = reinterpret_cast<uint8_t*>(((uintptr_t)(bars + 16) + 127) & ~(uintptr_t)127);
+  uint8_t* sA = reinterpret_cast<uint8_t*>(((uintptr_t)(bars + 32) + 127) & ~(uintptr_t)127);
   uint8_t* sHp = sA + NA * A_BYTES;
   uint8_t* sRaw = sHp + 2 * ((HP_BYTES + 127) / 128 * 128);
   const uint32_t bar0 = smem_u32(bars);
-  const uint32_t full_raw = bar0, empty_raw = bar0 + 8u * 4, a_full = bar0 + 8u * 8, a_empty = bar0 + 8u * 10,
-                 d_full = bar0 + 8u * 12, d_empty = bar0 + 8u * 14;
+  const uint32_t full_raw = bar0, empty_raw = bar0 + 8u * 6, a_full = bar0 + 8u * 12, a_empty = bar0 + 8u * 16,
+                 d_full = bar0 + 8u * 20, d_empty = bar0 + 8u * 24;
 
   // ---- prologue ----
   const uint32_t sW_u32 = smem_u32(sW);
@@ -587,7 +593,7 @@ __global__ void __launch_bounds__(576, 1) k_stem_ws(const __grid_constant__ CUte
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(full_raw + 8u * i, 1); mbar_init(empty_raw + 8u * i, 8); }
     for (int i = 0; i < NA; ++i) { mbar_init(a_full + 8u * i, 8); mbar_init(a_empty + 8u * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(d_full + 8u * i, 1); mbar_init(d_empty + 8u * i, 4); }
+    for (int i = 0; i < NT; ++i) { mbar_init(d_full + 8u * i, 1); mbar_init(d_empty + 8u * i, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
   }
@@ -601,6 +607,9 @@ __global__ void __launch_bounds__(576, 1) k_stem_ws(const __grid_constant__ CUte
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
+  // Programmatic dependent launch: everything above touched only constants (weights, tables, barriers, TMEM);
+  // the activations written by the previous kernel in the stream are read (and ours written) only after this point.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int tilesX = (p.OW + TW - 1) / TW, tilesY = (p.OH + TH - 1) / TH;
   const int tiles_per_img = tilesX * tilesY;
   const int rx_off = (4 - (p.pl & 3)) & 3;             // ix0 = 32*txi - pl  ->  aligned start ix0 - rx_off
@@ -621,9 +630,10 @@ __global__ void __launch_bounds__(576, 1) k_stem_ws(const __grid_constant__ CUte
       const int oy = ty0 + e_ty, ox = tx0 + e_tx;
       const bool valid = oy < p.OH && ox < p.OW;
       float* orow = p.out + (size_t)b * p.out_istride + ((size_t)(valid ? oy : 0) * p.OW + (valid ? ox : 0)) * p.CoutS;
-      mbar_wait(d_full + 8u * g, (uint32_t)(k & 1));
+      const int kl = 2 * k + g, di = kl & (NT - 1);        // CTA-local tile index -> accumulator buffer
+      mbar_wait(d_full + 8u * di, (uint32_t)((kl / NT) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tcol0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * p.Npad);
+      const uint32_t tcol0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(di * p.Npad);
 #pragma unroll 1
       for (int c0 = 0; c0 < p.CoutS; c0 += 8) {
         uint32_t u[8];
@@ -640,7 +650,7 @@ __global__ void __launch_bounds__(576, 1) k_stem_ws(const __grid_constant__ CUte
                                 fmaf(__uint_as_float(u[6]), scale, b1.z), fmaf(__uint_as_float(u[7]), scale, b1.w));
         if (relu) { v0 = max4(v0, make_float4(0.f, 0.f, 0.f, 0.f)); v1 = max4(v1, make_float4(0.f, 0.f, 0.f, 0.f)); }
         else { v0 = leaky4(v0, a0); v1 = leaky4(v1, a1); }
-        if (valid) {
+        if (valid && !(p.dbg & 4)) {
           if (p.vec_store) {
             *reinterpret_cast<float4*>(orow + c0) = v0;
             if (c0 + 4 < p.CoutS) *reinterpret_cast<float4*>(orow + c0 + 4) = v1;
@@ -654,7 +664,7 @@ __global__ void __launch_bounds__(576, 1) k_stem_ws(const __grid_constant__ CUte
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(d_empty + 8u * g);
+      if (lane == 0) mbar_arrive(d_empty + 8u * di);
     }
   } else if (warp < 16) {
     // =============================== builders: raw patch -> fp16 patch -> im2col A =======================
@@ -664,7 +674,7 @@ __global__ void __launch_bounds__(576, 1) k_stem_ws(const __grid_constant__ CUte
     const uint32_t a_row = ((uint32_t)r >> 3) * SBO + ((uint32_t)r & 7u) * 16u;
     const uint32_t src_px = (uint32_t)((2 * r_ty) * PWP + 2 * r_tx) * 8u;
     constexpr int KY0 = KW == 5 ? 3 : 2;                 // part 0: ky < KY0, part 1: the rest
-    const int ky_lo = part == 0 ? 0 : KY0, ky_hi = part == 0 ? KY0 : KW;
+    const int ky_lo = part == 0 ? 0 : KY0;
     const uint32_t sA_a = smem_u32(sA), sHp_a = smem_u32(sHp), sRaw_a = smem_u32(sRaw);
     constexpr uint32_t HP_STRIDE = (HP_BYTES + 127) / 128 * 128;
     int si = 0, sph = 0, ai = 0, aph = 0, hb = 0;
@@ -675,7 +685,7 @@ __global__ void __launch_bounds__(576, 1) k_stem_ws(const __grid_constant__ CUte
       mbar_wait(full_raw + 8u * si, (uint32_t)sph);
       // ---- convert: u8x4 BGRX -> {B,G,R,0} - 127.5 as halves; pixels outside the image (SAME padding) -> 0
       const uint32_t raw_a = sRaw_a + (uint32_t)si * RAW_STAGE, hp_a = sHp_a + (uint32_t)hb * HP_STRIDE;
-      for (int i = bt; i < PH * PWP; i += 256) {
+      for (int i = bt; i < ((p.dbg & 8) ? 0 : PH * PWP); i += 256) {
         const int ly = i / PWP, lx = i - ly * PWP;
         uint32_t raw;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw) : "r"(raw_a + 4u * (uint32_t)(ly * RAWW + lx + rx_off)));
@@ -695,16 +705,22 @@ __global__ void __launch_bounds__(576, 1) k_stem_ws(const __grid_constant__ CUte
       mbar_wait(a_empty + 8u * ai, (uint32_t)(aph ^ 1));
       // ---- im2col: CPK 16-byte chunks per (pixel, ky), copied verbatim
       const uint32_t dst = sA_a + (uint32_t)ai * A_BYTES + a_row;
+      if (!(p.dbg & 16)) {
+        // all loads of this thread's tap rows first, then all stores (the asm statements keep their order)
+        constexpr int NK0 = KY0 * CPK, NK1 = (KW - KY0) * CPK;
+        uint4 v[NK0];
+        const uint32_t src = hp_a + src_px + (uint32_t)(ky_lo * PWP * 8);
+        const uint32_t dst2 = dst + (uint32_t)(ky_lo * CPK * 128);
+        const int nk = part == 0 ? NK0 : NK1;
 #pragma unroll
-      for (int ky = 0; ky < KW; ++ky) {
-        if (ky < ky_lo || ky >= ky_hi) continue;
+        for (int q = 0; q < NK0; ++q)
+          if (q < nk)
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[q].x), "=r"(v[q].y), "=r"(v[q].z), "=r"(v[q].w)
+                         : "r"(src + (uint32_t)((q / CPK) * PWP * 8 + (q % CPK) * 16)));
 #pragma unroll
-        for (int j = 0; j < CPK; ++j) {
-          uint32_t x0, x1, x2, x3;
-          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
-                       : "r"(hp_a + src_px + (uint32_t)(ky * PWP * 8 + j * 16)));
-          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)((ky * CPK + j) * 128)), "r"(x0), "r"(x1), "r"(x2), "r"(x3) : "memory");
-        }
+        for (int q = 0; q < NK0; ++q)
+          if (q < nk)
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst2 + (uint32_t)(q * 128)), "r"(v[q].x), "r"(v[q].y), "r"(v[q].z), "r"(v[q].w) : "memory");
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
@@ -741,9 +757,9 @@ __global__ void __launch_bounds__(576, 1) k_stem_ws(const __grid_constant__ CUte
       const uint32_t part_bytes = (uint32_t)p.Npad * K8 * 2u;
       int ai = 0, aph = 0, k = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
-        const int di = k & 1;
+        const int di = k & (NT - 1);
         mbar_wait(a_full + 8u * ai, (uint32_t)aph);
-        mbar_wait(d_empty + 8u * di, (uint32_t)(((k >> 1) & 1) ^ 1));
+        mbar_wait(d_empty + 8u * di, (uint32_t)(((k / NT) & 1) ^ 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_base = smem_u32(sA) + (uint32_t)ai * A_BYTES;
         const uint32_t dcol = tmem_base + (uint32_t)(di * p.Npad);
@@ -772,6 +788,24 @@ __global__ void __launch_bounds__(576, 1) k_stem_ws(const __grid_constant__ CUte
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols));
   }
+}
+
+// Launch with programmatic stream serialization (PDL): the kernel may become resident while the previous kernel of the
+// stream drains; it orders itself with griddepcontrol.wait.  enabled with FDT_PDL=1 (off by default: with two streams the gaps are already filled and early residency costs more than it saves).
+template <typename Kern, typename... Args>
+void launch_pdl(Kern kern, int grid, int block, size_t smem, cudaStream_t s, Args... args) {
+  static const bool pdl = [] { const char* e = std::getenv("FDT_PDL"); return e && e[0] == '1'; }();   // measured slower with two streams: off by default
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -830,7 +864,7 @@ void launch_ws_k(const CUtensorMap& tm, const DwPwTcP& p, int B, int ntiles, cud
   }
   int grid = std::min(ntiles, 148);
   if (grid < 1) grid = 1;
-  k_block_ws<ND, S, RS><<<grid, (ND + kEpiWarps + 2) * 32, p.smem_bytes, s>>>(tm, p, B, ntiles);
+  launch_pdl(k_block_ws<ND, S, RS>, grid, (ND + kEpiWarps + 2) * 32, p.smem_bytes, s, tm, p, B, ntiles);
 }
 
 template <int ND>
@@ -888,6 +922,7 @@ void launch_stem_ws_kw(const CUtensorMap& tm, const StemWsP& p, int B, cudaStrea
     size_t& c = cur[dev];
     if (p.smem_bytes > c) {
       cudaFuncSetAttribute(k_stem_ws<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
+      cudaFuncSetAttribute(k_stem_ws<KW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
       c = p.smem_bytes;
     }
     auto key = std::make_pair(dev, p.smem_bytes);
@@ -902,7 +937,7 @@ void launch_stem_ws_kw(const CUtensorMap& tm, const StemWsP& p, int B, cudaStrea
   const int ntiles = ((p.OW + 15) / 16) * ((p.OH + 7) / 8) * B;
   int grid = std::min(ntiles, 148 * per_sm);
   if (grid < 1) grid = 1;
-  k_stem_ws<KW><<<grid, 576, p.smem_bytes, s>>>(tm, p, B, ntiles);
+  launch_pdl(k_stem_ws<KW>, grid, 576, p.smem_bytes, s, tm, p, B, ntiles);
 }
 
 }  // namespace

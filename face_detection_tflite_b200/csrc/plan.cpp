@@ -445,8 +445,8 @@ struct Builder {
   bool plan_ws(PStep* st, int OH, int OW) {
     static const int want = [] { const char* e = std::getenv("FDT_WS"); return e ? std::atoi(e) : 1; }();
     static const int want_nd = [] { const char* e = std::getenv("FDT_WS_ND"); return e ? std::atoi(e) : 0; }();
-    static const int max_ns = [] { const char* e = std::getenv("FDT_WS_NS"); return e ? std::atoi(e) : 4; }();
-    static const int max_na = [] { const char* e = std::getenv("FDT_WS_NA"); return e ? std::atoi(e) : 2; }();
+    static const int max_ns = [] { const char* e = std::getenv("FDT_WS_NS"); return e ? std::atoi(e) : 6; }();
+    static const int max_na = [] { const char* e = std::getenv("FDT_WS_NA"); return e ? std::atoi(e) : 4; }();
     if (!want) return false;
     PStep s = *st;
     // staged pixel stride: >= K8 (and >= CoutS when the residual is read from the stage, so the epilogue needs no
@@ -457,8 +457,9 @@ struct Builder {
       if ((ks / 4) % 2 == 0) ks += 4;
       s.KS = ks;
     }
+    s.nt = 4 * s.Npad <= 512 ? 4 : 2;                  // TMEM accumulator ring
     s.tmem_cols = 32;
-    while (s.tmem_cols < 2 * s.Npad) s.tmem_cols *= 2;
+    while (s.tmem_cols < s.nt * s.Npad) s.tmem_cols *= 2;
     if (s.tmem_cols > 512) return false;
     const size_t cap = (size_t)225 * 1024;
     for (int Pn = 128; Pn >= 32; Pn /= 2) {
@@ -505,10 +506,10 @@ struct Builder {
         s.nd = 12;
       }
       size_t n_items = s.has_dw ? (size_t)s.G * (s.K8 / 4) * (s.TH / s.RS) * s.TW : 0;
-      size_t head = ((size_t)s.w_parts * s.Npad * s.K8 + 2 * (size_t)s.Npad + (s.has_dw ? 10 * (size_t)s.K8 : 0)) * 4 + n_items * 8 + 16 * 8 + 128;
+      size_t head = ((size_t)s.w_parts * s.Npad * s.K8 + 2 * (size_t)s.Npad + (s.has_dw ? 10 * (size_t)s.K8 : 0)) * 4 + n_items * 8 + 32 * 8 + 128;
       size_t a_bytes = (size_t)2 * 128 * s.K8 * 4;
       size_t in_bytes = ((size_t)s.G * s.IH * s.IW * s.KS * 4 + 127) / 128 * 128;
-      static const int combos[5][2] = {{2, 4}, {2, 3}, {2, 2}, {1, 2}, {1, 1}};
+      static const int combos[9][2] = {{4, 6}, {4, 5}, {3, 5}, {3, 4}, {2, 4}, {2, 3}, {2, 2}, {1, 2}, {1, 1}};
       for (const auto& c : combos) {
         if (c[0] > max_na || c[1] > max_ns) continue;
         size_t total = head + c[0] * a_bytes + c[1] * in_bytes;
@@ -638,7 +639,7 @@ struct Builder {
       st.K8 = nchunk * 8;
       st.Npad = ru(st.Cout, 16);
       st.tmem_cols = 32;
-      while (st.tmem_cols < 2 * st.Npad) st.tmem_cols *= 2;
+      while (st.tmem_cols < 4 * st.Npad) st.tmem_cols *= 2;
       float wmax = 0.f;
       for (float v : w) wmax = std::max(wmax, std::fabs(v));
       float wscale = 1.f;
@@ -671,8 +672,8 @@ struct Builder {
       std::vector<float> wb((hb.size() + 1) / 2, 0.f);
       std::memcpy(wb.data(), hb.data(), hb.size() * 2);
       const int PH = 14 + st.kw;
-      st.ns = 4; st.na = 2;
-      st.smem = (size_t)parts * st.Npad * st.K8 * 2 + 2 * (size_t)st.Npad * 4 + 16 * 8 + 128     // W, bias, alpha, barriers
+      st.ns = 6; st.na = 4;
+      st.smem = (size_t)parts * st.Npad * st.K8 * 2 + 2 * (size_t)st.Npad * 4 + 32 * 8 + 128     // W, bias, alpha, barriers
                 + (size_t)st.na * 128 * st.K8 * 2 + 2 * (size_t)PH * 36 * 8 + (size_t)st.ns * ((PH * 160 + 127) / 128 * 128) + 256;
       st.w = push(wb, wb.size());
       st.bias = push(b, (size_t)st.Npad + 8);

@@ -1,5 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for d in 1 2 0; do
-  echo "== FDT_STEM_TMTYPE=$d"; FDT_STEM_TMTYPE=$d timeout 120 python __graft_entry__.py --smoke 2>&1 | tail -2
+for d in 28 30 31 29; do
+  FDT_STEM_DBG=$d timeout 200 python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e 2>gpurun_out/sweep.err | D="$d" python -c "
+import json,sys,os
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); ks=d['kernels']
+print('[dbg %s] value %d  sum %.3f ms | '%(os.environ['D'],d['value'],sum(k['ms'] for k in ks)) + ' '.join('%.0f'%(k['ms']*1e3) for k in ks[:6]))
+" || tail -3 gpurun_out/sweep.err
 done
