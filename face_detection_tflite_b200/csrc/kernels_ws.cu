@@ -22,6 +22,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <mutex>
@@ -34,6 +35,7 @@ namespace {
 
 constexpr uint32_t kLBO = 128;   // bytes between the two 16-byte K chunks of one MMA (adjacent core matrices)
 constexpr int kEpiWarps = 4;
+constexpr int kMmaWarps = 2;   // issuing one tcgen05.mma costs its thread ~150 cycles: two issuers alternate tiles
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -73,10 +75,21 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes
   return d;
 }
 
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc));
+// The MMA issuer is ONE thread: every instruction it spends per tcgen05.mma is serial latency for the whole CTA.
+// Descriptors are therefore kept as two 32-bit words: the low word (start address >> 4 | LBO) advances by a plain
+// 32-bit add per K step (16 = 2 core matrices of 128 B, >> 4), the high word (SBO | version) is loop-invariant.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | ((kLBO >> 4) << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
+template <int F16>
+__device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t acc) {
+  if (F16)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\tsetp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc));
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\tsetp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}\n" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc));
 }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -92,9 +105,22 @@ __device__ __forceinline__ void split_store(float* sAhi, float* sAlo, uint32_t o
   *reinterpret_cast<float4*>(sAlo + off_floats) = lo;
 }
 
+#ifndef FDT_NO_FFMA2
+// two packed fp32 FMAs (sm_100 FFMA2): same rounding as four scalar fmaf, half the issue slots
+__device__ __forceinline__ void fma4(float4& a, const float4& v, const float4& w) {
+  asm("{\n\t.reg .b64 ra, rv, rw;\n\t"
+      "mov.b64 ra, {%0, %1};\n\tmov.b64 rv, {%4, %5};\n\tmov.b64 rw, {%8, %9};\n\t"
+      "fma.rn.f32x2 ra, rv, rw, ra;\n\tmov.b64 {%0, %1}, ra;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rv, {%6, %7};\n\tmov.b64 rw, {%10, %11};\n\t"
+      "fma.rn.f32x2 ra, rv, rw, ra;\n\tmov.b64 {%2, %3}, ra;\n\t}"
+      : "+f"(a.x), "+f"(a.y), "+f"(a.z), "+f"(a.w)
+      : "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "f"(w.x), "f"(w.y), "f"(w.z), "f"(w.w));
+}
+#else
 __device__ __forceinline__ void fma4(float4& a, const float4& v, const float4& w) {
   a.x = fmaf(v.x, w.x, a.x); a.y = fmaf(v.y, w.y, a.y); a.z = fmaf(v.z, w.z, a.z); a.w = fmaf(v.w, w.w, a.w);
 }
+#endif
 __device__ __forceinline__ float4 max4(const float4& a, const float4& b) {
   return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
 }
@@ -281,16 +307,19 @@ __device__ __forceinline__ void epi_tile(const DwPwTcP& p, uint32_t tcol0, uint3
   }
 }
 
+// debug trace: role r, CTA-local tile i, stamp j (0 = before waits, 1 = after waits, 2 = work done)
+#define WS_TRACE(r, i, j) do { if (tr && (i) < 64) tr[((r) * 64 + (i)) * 3 + (j)] = clock64(); } while (0)
+
 // Shared-memory carve-up (must match plan_ws in plan.cpp):
 //   [W (w_parts x Npad x K8)] [bias Npad] [alpha Npad] [dw taps+bias 10 x K8] [dtab n_items x 8 B] [barriers 128 B]
 //   | 128-byte aligned: [A ring: NA x (hi, lo) x 128 x K8] [input ring: NS x in_stage_bytes]
 // S: depthwise stride (0 = no depthwise, pointwise only); RS: output rows per depthwise work item.
 template <int ND, int S, int RS>
-__global__ void __launch_bounds__((ND + kEpiWarps + 2) * 32, 1)
+__global__ void __launch_bounds__((ND + kEpiWarps + 1 + kMmaWarps) * 32, 1)
 k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntiles) {
   extern __shared__ __align__(128) float smem[];
   __shared__ uint32_t tmem_base_s;
-  constexpr int kThreads = (ND + kEpiWarps + 2) * 32;
+  constexpr int kThreads = (ND + kEpiWarps + 1 + kMmaWarps) * 32;
   constexpr int kDwThreads = ND * 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel may begin its own prologue
@@ -382,16 +411,20 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
     const bool fast = p.vec_store && res_kind != 3 && (res_kind == 0 || p.KS >= p.CoutS);
     const uint32_t ks_b = (uint32_t)p.KS * 4u, row_b = (uint32_t)p.IW * ks_b;
     int si = 0, sph = 0, di = 0, dph = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    long long* tr = (p.trace && blockIdx.x == 0 && tid == 0) ? p.trace : nullptr;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       int grp, trem, tyi, txi;
       p.fd_tpg.divmod(tile, grp, trem);
       p.fd_tilesX.divmod(trem, tyi, txi);
       const int ty0 = tyi * p.TH, tx0 = txi * p.TW;
       const int b0 = grp * p.G;
+      WS_TRACE(0, it, 0);
       const uint32_t res_a = sIn0_a + ((uint32_t)si * in_stage_floats + res_off) * 4u;
       if (epi_reads_stage) mbar_wait(full_in + 8u * si, (uint32_t)sph);   // visibility of the TMA writes to this thread
       mbar_wait(d_full + 8u * di, (uint32_t)dph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      WS_TRACE(0, it, 1);
       const int oy = ty0 + e_ty, ox = tx0 + e_tx, b = b0 + e_g;
       const bool valid = slot_ok && b < B && oy < p.OH && ox < p.OW;
       float* orow = p.out + (long long)b0 * p.out_istride + ((long long)ty0 * p.OW + tx0) * p.CoutS + o_rel;
@@ -419,6 +452,7 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
         mbar_arrive(d_empty + 8u * di);
         if (epi_reads_stage) mbar_arrive(empty_in + 8u * si);
       }
+      WS_TRACE(0, it, 2);
       if (++si == NS) { si = 0; sph ^= 1; }
       if (++di == NT) { di = 0; dph ^= 1; }
     }
@@ -442,12 +476,16 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
       bias0 = lds4(wq + (uint32_t)(9 * p.K8) * 4u);
     }
     int si = 0, sph = 0, ai = 0, aph = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    long long* tr = (p.trace && blockIdx.x == 0 && dtid == 0) ? p.trace : nullptr;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      WS_TRACE(1, it, 0);
       const uint32_t sIn_a = sIn0_a + (uint32_t)si * in_stage_floats * 4u;
       float* sAhi = sA + (size_t)ai * a_stage_floats;
       float* sAlo = sAhi + 128 * p.K8;
       mbar_wait(full_in + 8u * si, (uint32_t)sph);
       mbar_wait(a_empty + 8u * ai, (uint32_t)(aph ^ 1));
+      WS_TRACE(1, it, 1);
       if (S != 0) {
         if (hoist) {
           if (mine) dw_item<S ? S : 1, RS>(sIn_a + e0.x, row_b, ks_b, w0, bias0, sAhi, sAlo, e0.y & 0xFFu, (e0.y >> 8) * kLBO, SBO, (uint32_t)p.TW);
@@ -477,6 +515,7 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
         mbar_arrive(a_full + 8u * ai);
         mbar_arrive(empty_in + 8u * si);
       }
+      WS_TRACE(1, it, 2);
       if (++si == NS) { si = 0; sph ^= 1; }
       if (++ai == NA) { ai = 0; aph ^= 1; }
     }
@@ -485,19 +524,24 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
     if (lane == 0) {
       const uint32_t stage_bytes = (uint32_t)(p.G * p.IH * p.IW * p.KS) * 4u;
       int si = 0, sph = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      long long* tr = (p.trace && blockIdx.x == 0) ? p.trace : nullptr;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         int grp, trem, tyi, txi;
         p.fd_tpg.divmod(tile, grp, trem);
         p.fd_tilesX.divmod(trem, tyi, txi);
         const int b0 = grp * p.G;
         const int iy0 = tyi * p.TH * p.s - p.dpt, ix0 = txi * p.TW * p.s - p.dpl;
+        WS_TRACE(2, it, 0);
         mbar_wait(empty_in + 8u * si, (uint32_t)(sph ^ 1));
+        WS_TRACE(2, it, 1);
         const uint32_t bar = full_in + 8u * si;
         mbar_expect_tx(bar, stage_bytes);
         const uint32_t dst = smem_u32(sIn0 + (size_t)si * in_stage_floats);
         asm volatile(
             "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
             ::"r"(dst), "l"(&tmap), "r"(0), "r"(ix0), "r"(iy0), "r"(b0), "r"(bar) : "memory");
+        WS_TRACE(2, it, 2);
         if (++si == NS) { si = 0; sph ^= 1; }
       }
     }
@@ -507,26 +551,43 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((128u >> 4) << 24);
       const int ksteps = p.K8 >> 3;
-      const uint32_t b_lo = sB_u32 + (uint32_t)p.Npad * p.K8 * 4u;
-      int ai = 0, aph = 0, di = 0, dph = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const uint32_t hi = desc_hi(SBO);
+      const uint32_t w_hi0 = desc_lo(sB_u32), w_lo0 = desc_lo(sB_u32 + (uint32_t)p.Npad * p.K8 * 4u);
+      const uint32_t a0 = desc_lo(smem_u32(sA)), a_buf = (a_stage_floats * 4u) >> 4, a_half = (128u * (uint32_t)p.K8 * 4u) >> 4;
+      const bool w_split = p.w_parts > 1;
+      // Issuer mi takes the CTA's tiles it = mi, mi + nmi, ...  A parity wait must see every phase of its barrier, so a
+      // slot may only ever be visited by one issuer: two issuers need even ring sizes, otherwise issuer 0 does all tiles.
+      const int nmi = (NA % kMmaWarps == 0 && NT % kMmaWarps == 0) ? kMmaWarps : 1;
+      const int mi = warp - (kEpiWarps + ND + 1);
+      int ai = mi, aph = 0, di = mi, dph = 0;
+      while (ai >= NA) { ai -= NA; aph ^= 1; }
+      while (di >= NT) { di -= NT; dph ^= 1; }
+      long long* tr = (p.trace && blockIdx.x == 0 && mi == 0) ? p.trace : nullptr;
+      int it = mi;
+      for (int tile = mi < nmi ? blockIdx.x + mi * gridDim.x : ntiles; tile < ntiles; tile += nmi * gridDim.x, it += nmi) {
+        WS_TRACE(3, it, 0);
         mbar_wait(a_full + 8u * ai, (uint32_t)aph);
         mbar_wait(d_empty + 8u * di, (uint32_t)(dph ^ 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_hi = smem_u32(sA + (size_t)ai * a_stage_floats), a_lo = a_hi + 128u * (uint32_t)p.K8 * 4u;
+        WS_TRACE(3, it, 1);
         const uint32_t dcol = tmem_base + (uint32_t)(di * p.Npad);
+        uint32_t ah = a0 + (uint32_t)ai * a_buf, al = ah + a_half, wh = w_hi0, wl = w_lo0, acc = 0u;
+#pragma unroll 1
         for (int ks = 0; ks < ksteps; ++ks) {
-          const uint64_t db = make_desc(sB_u32 + ks * 2 * kLBO, SBO);
-          const uint64_t dah = make_desc(a_hi + ks * 2 * kLBO, SBO);
-          mma_tf32(dcol, dah, db, idesc, ks > 0 ? 1u : 0u);
-          mma_tf32(dcol, make_desc(a_lo + ks * 2 * kLBO, SBO), db, idesc, 1u);
+          mma_ss<0>(dcol, ah, hi, wh, hi, idesc, acc);
+          mma_ss<0>(dcol, al, hi, wh, hi, idesc, 1u);
           // fp32 weights (face_landmark): W = W_hi + W_lo, third product A_hi * W_lo (A_lo * W_lo ~ 2^-22, dropped)
-          if (p.w_parts > 1) mma_tf32(dcol, dah, make_desc(b_lo + ks * 2 * kLBO, SBO), idesc, 1u);
+          if (w_split) mma_ss<0>(dcol, ah, hi, wl, hi, idesc, 1u);
+          ah += 16u; al += 16u; wh += 16u; wl += 16u; acc = 1u;
         }
+        WS_TRACE(4, it, 0);
         mma_commit(a_empty + 8u * ai);   // operand buffer reusable once these MMAs have read it
+        WS_TRACE(4, it, 1);
         mma_commit(d_full + 8u * di);    // accumulator complete
-        if (++ai == NA) { ai = 0; aph ^= 1; }
-        if (++di == NT) { di = 0; dph ^= 1; }
+        WS_TRACE(4, it, 2);
+        WS_TRACE(3, it, 2);
+        ai += nmi; while (ai >= NA) { ai -= NA; aph ^= 1; }
+        di += nmi; while (di >= NT) { di -= NT; dph ^= 1; }
       }
     }
     __syncwarp();
@@ -754,25 +815,25 @@ __global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUte
     // =============================== MMA issuer =====================================================
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Npad >> 3) << 17) | ((128u >> 4) << 24);   // D f32, A/B f16, K-major
-      const uint32_t part_bytes = (uint32_t)p.Npad * K8 * 2u;
+      const uint32_t part_q = ((uint32_t)p.Npad * K8 * 2u) >> 4;   // one weight part, in descriptor address units
+      const uint32_t hi = desc_hi(SBO), a_desc0 = desc_lo(smem_u32(sA)), w_desc0 = desc_lo(sW_u32);
+      const int parts = p.w_parts;
       int ai = 0, aph = 0, k = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
         const int di = k & (NT - 1);
         mbar_wait(a_full + 8u * ai, (uint32_t)aph);
         mbar_wait(d_empty + 8u * di, (uint32_t)(((k / NT) & 1) ^ 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_base = smem_u32(sA) + (uint32_t)ai * A_BYTES;
         const uint32_t dcol = tmem_base + (uint32_t)(di * p.Npad);
+        const uint32_t a_lo0 = a_desc0 + (uint32_t)ai * (A_BYTES >> 4);
         uint32_t acc = 0u;
-#pragma unroll 1
-        for (int ks = 0; ks < K8 / 16; ++ks) {
-          const uint64_t da = make_desc(a_base + ks * 2 * kLBO, SBO);
-          for (int t = 0; t < p.w_parts; ++t) {
-            const uint64_t db = make_desc(sW_u32 + (uint32_t)t * part_bytes + ks * 2 * kLBO, SBO);
-            if (!(p.dbg & 2)) asm volatile(
-                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(dcol), "l"(da), "l"(db), "r"(idesc), "r"(acc));
+        if (!(p.dbg & 2)) {
+#pragma unroll
+          for (int ks = 0; ks < K8 / 16; ++ks) {
+            mma_ss<1>(dcol, a_lo0 + 16u * ks, hi, w_desc0 + 16u * ks, hi, idesc, acc);
             acc = 1u;
+            if (parts > 1) mma_ss<1>(dcol, a_lo0 + 16u * ks, hi, w_desc0 + part_q + 16u * ks, hi, idesc, 1u);
+            if (parts > 2) mma_ss<1>(dcol, a_lo0 + 16u * ks, hi, w_desc0 + 2u * part_q + 16u * ks, hi, idesc, 1u);
           }
         }
         mma_commit(a_empty + 8u * ai);
@@ -864,7 +925,7 @@ void launch_ws_k(const CUtensorMap& tm, const DwPwTcP& p, int B, int ntiles, cud
   }
   int grid = std::min(ntiles, 148);
   if (grid < 1) grid = 1;
-  launch_pdl(k_block_ws<ND, S, RS>, grid, (ND + kEpiWarps + 2) * 32, p.smem_bytes, s, tm, p, B, ntiles);
+  launch_pdl(k_block_ws<ND, S, RS>, grid, (ND + kEpiWarps + 1 + kMmaWarps) * 32, p.smem_bytes, s, tm, p, B, ntiles);
 }
 
 template <int ND>
@@ -942,13 +1003,42 @@ void launch_stem_ws_kw(const CUtensorMap& tm, const StemWsP& p, int B, cudaStrea
 
 }  // namespace
 
-bool launch_block_ws(const DwPwTcP& p, int B, int cap, cudaStream_t s) {
+bool launch_block_ws(const DwPwTcP& p0, int B, int cap, cudaStream_t s) {
+  DwPwTcP p = p0;
   CUtensorMap tm;
   if (!input_tensor_map(p, cap, &tm)) return false;
   int groups = (B + p.G - 1) / p.G;
   int ntiles = groups * p.tilesX * p.tilesY;
+  // FDT_WS_TRACE=1: per-role timeline of CTA 0 (diagnostic; synchronises after every launch)
+  static const bool trace = [] { const char* e = std::getenv("FDT_WS_TRACE"); return e && e[0] == '1'; }();
+  static long long* d_trace = nullptr;
+  if (trace) {
+    if (!d_trace) cudaMalloc(&d_trace, 5 * 64 * 3 * sizeof(long long));
+    cudaMemsetAsync(d_trace, 0, 5 * 64 * 3 * sizeof(long long), s);
+    p.trace = d_trace;
+  }
   if (p.nd == 12) launch_ws_nd<12>(tm, p, B, ntiles, s);
   else launch_ws_nd<8>(tm, p, B, ntiles, s);
+  if (trace) {
+    static long long h[5 * 64 * 3];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h, d_trace, sizeof h, cudaMemcpyDeviceToHost);
+    const int n = std::min(64, (ntiles + 147) / 148);
+    static const char* rn[5] = {"epi", "dw", "prod", "mma", "commit(a,d)"};
+    fprintf(stderr, "WS_TRACE K8=%d Npad=%d S=%d RS=%d nd=%d ns=%d na=%d tiles/cta=%d:", p.K8, p.Npad, p.has_dw ? p.s : 0, p.RS, p.nd, p.ns, p.na, n);
+    for (int r = 0; r < 5; ++r) {
+      double wait = 0, work = 0; int cnt = 0;
+      for (int i = 2; i < n - 1; ++i) {          // steady state: skip the first two and the last tile
+        const long long* t = h + (r * 64 + i) * 3;
+        if (!t[0] || !t[1] || !t[2]) continue;
+        wait += (double)(t[1] - t[0]); work += (double)(t[2] - t[1]); ++cnt;
+      }
+      double period = 0;
+      if (n > 4 && h[(r * 64 + n - 2) * 3] && h[(r * 64 + 2) * 3]) period = (double)(h[(r * 64 + n - 2) * 3] - h[(r * 64 + 2) * 3]) / (n - 4);
+      if (cnt) fprintf(stderr, "  %s wait %.0f work %.0f period %.0f |", rn[r], wait / cnt, work / cnt, period);
+    }
+    fprintf(stderr, "\n");
+  }
   return true;
 }
 

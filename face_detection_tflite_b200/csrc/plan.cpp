@@ -509,7 +509,8 @@ struct Builder {
       size_t head = ((size_t)s.w_parts * s.Npad * s.K8 + 2 * (size_t)s.Npad + (s.has_dw ? 10 * (size_t)s.K8 : 0)) * 4 + n_items * 8 + 32 * 8 + 128;
       size_t a_bytes = (size_t)2 * 128 * s.K8 * 4;
       size_t in_bytes = ((size_t)s.G * s.IH * s.IW * s.KS * 4 + 127) / 128 * 128;
-      static const int combos[9][2] = {{4, 6}, {4, 5}, {3, 5}, {3, 4}, {2, 4}, {2, 3}, {2, 2}, {1, 2}, {1, 1}};
+      // (A buffers, input stages); even A rings let the two MMA issuers alternate tiles
+      static const int combos[8][2] = {{4, 6}, {4, 5}, {2, 5}, {2, 4}, {2, 3}, {2, 2}, {1, 2}, {1, 1}};
       for (const auto& c : combos) {
         if (c[0] > max_na || c[1] > max_ns) continue;
         size_t total = head + c[0] * a_bytes + c[1] * in_bytes;

@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 180 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; rc=$?; tail -3 gpurun_out/smoke.log
+timeout 90 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; rc=$?; tail -3 gpurun_out/smoke.log
 if [ $rc -ne 0 ]; then echo "SMOKE FAILED rc=$rc"; fi
-timeout 1500 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+timeout 400 python -m pytest tests -m gpu -q -x --timeout 120 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -${TAILN:-25} gpurun_out/pytest_gpu.log
 for c in ${CHUNKS:-256}; do timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu --chunk $c 2>gpurun_out/bench_c$c.err > gpurun_out/bench_c$c.json; python - <<PY
 import json
