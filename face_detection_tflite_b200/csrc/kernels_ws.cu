@@ -199,9 +199,14 @@ __device__ __forceinline__ void dw_item(uint32_t base, uint32_t row_b, uint32_t 
 // ---- fast epilogue (float4 stores, residual none / staged / staged + 2x2 max-pool, staged pixel stride KS >= CoutS) ----
 // Straight-line per 8-column group: TMEM load, bias and residual LDS issued before tcgen05.wait::ld, add, activation,
 // two float4 stores.  Channels >= Cout inside CoutS come out as exact zeros (zero weights, bias and TMA zero fill).
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// RES 3 / 4: residual from another HBM tensor (same size / 2x2 max-pooled), float4 loads; `gres` points at this thread's
+// residual pixel (top-left of the pool window), gks / grow are its pixel / row strides in floats, gres_c its channels.
 template <int RES, int LEAKY>
 __device__ __forceinline__ void epi_fast(uint32_t tcol0, uint32_t res_a, uint32_t bias_a, uint32_t alpha_a, float* orow, bool valid,
-                                         int cout_s, uint32_t ks_b, uint32_t row_b) {
+                                         int cout_s, uint32_t ks_b, uint32_t row_b,
+                                         const float* gres = nullptr, int gks = 0, int grow = 0, int gres_c = 0) {
 #pragma unroll 1
   for (int c0 = 0; c0 < cout_s; c0 += 8) {
     uint32_t u[8];
@@ -217,6 +222,16 @@ __device__ __forceinline__ void epi_fast(uint32_t tcol0, uint32_t res_a, uint32_
     } else if (RES == 2) {
       r0 = max4(max4(lds4(res_a + cb), lds4(res_a + ks_b + cb)), max4(lds4(res_a + row_b + cb), lds4(res_a + row_b + ks_b + cb)));
       r1 = max4(max4(lds4(res_a + cb + 16u), lds4(res_a + ks_b + cb + 16u)), max4(lds4(res_a + row_b + cb + 16u), lds4(res_a + row_b + ks_b + cb + 16u)));
+    } else if (RES == 3) {
+      if (valid) {
+        if (c0 < gres_c) r0 = ldg4(gres + c0);
+        if (c0 + 4 < gres_c) r1 = ldg4(gres + c0 + 4);
+      }
+    } else if (RES == 4) {
+      if (valid) {
+        if (c0 < gres_c) r0 = max4(max4(ldg4(gres + c0), ldg4(gres + gks + c0)), max4(ldg4(gres + grow + c0), ldg4(gres + grow + gks + c0)));
+        if (c0 + 4 < gres_c) r1 = max4(max4(ldg4(gres + c0 + 4), ldg4(gres + gks + c0 + 4)), max4(ldg4(gres + grow + c0 + 4), ldg4(gres + grow + gks + c0 + 4)));
+      }
     }
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     float4 v0 = make_float4(__uint_as_float(u[0]) + b0.x, __uint_as_float(u[1]) + b0.y, __uint_as_float(u[2]) + b0.z, __uint_as_float(u[3]) + b0.w);
@@ -408,7 +423,11 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
     const uint32_t res_off = slot_ok ? (uint32_t)((((size_t)e_g * p.IH + e_ty * rs + p.dpt) * p.IW + e_tx * rs + p.dpl) * p.KS) : 0u;
     const uint32_t sIn0_a = smem_u32(sIn0), bias_a = smem_u32(sBias), alpha_a = smem_u32(sAlpha);
     const int res_kind = p.res_mode == 1 ? (p.res_pool ? 2 : 1) : (p.res_mode == 2 ? 3 : 0);
-    const bool fast = p.vec_store && res_kind != 3 && (res_kind == 0 || p.KS >= p.CoutS);
+    // global residual fast path: float4-aligned residual tensor; pooled windows must lie inside it (even dimensions)
+    const bool gfast = res_kind == 3 && p.res_Cs % 4 == 0 && p.res_C % 4 == 0 && p.res_istride % 4 == 0 && ((size_t)p.res % 16 == 0) &&
+                       (!p.res_pool || (p.res_H == 2 * p.OH && p.res_W == 2 * p.OW));
+    const bool fast = p.vec_store && (res_kind == 3 ? gfast : (res_kind == 0 || p.KS >= p.CoutS));
+    const int gmul = p.res_pool ? 2 : 1, gks = p.res_Cs, grow = p.res_W * p.res_Cs;
     const uint32_t ks_b = (uint32_t)p.KS * 4u, row_b = (uint32_t)p.IW * ks_b;
     int si = 0, sph = 0, di = 0, dph = 0;
     long long* tr = (p.trace && blockIdx.x == 0 && tid == 0) ? p.trace : nullptr;
@@ -430,7 +449,16 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
       float* orow = p.out + (long long)b0 * p.out_istride + ((long long)ty0 * p.OW + tx0) * p.CoutS + o_rel;
       const float* rbase = p.res_mode == 2 ? p.res + (size_t)(valid ? b : 0) * p.res_istride : nullptr;
       const uint32_t tcol0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(di * p.Npad);
-      if (fast) {
+      if (fast && res_kind == 3) {
+        const float* gres = rbase + ((size_t)(valid ? oy : 0) * gmul * p.res_W + (size_t)(valid ? ox : 0) * gmul) * p.res_Cs;
+        if (p.act == kActRelu) {
+          if (p.res_pool) epi_fast<4, 0>(tcol0, res_a, bias_a, alpha_a, orow, valid, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C);
+          else epi_fast<3, 0>(tcol0, res_a, bias_a, alpha_a, orow, valid, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C);
+        } else {
+          if (p.res_pool) epi_fast<4, 1>(tcol0, res_a, bias_a, alpha_a, orow, valid, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C);
+          else epi_fast<3, 1>(tcol0, res_a, bias_a, alpha_a, orow, valid, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C);
+        }
+      } else if (fast) {
         if (p.act == kActRelu) {
           if (res_kind == 1) epi_fast<1, 0>(tcol0, res_a, bias_a, alpha_a, orow, valid, p.CoutS, ks_b, row_b);
           else if (res_kind == 2) epi_fast<2, 0>(tcol0, res_a, bias_a, alpha_a, orow, valid, p.CoutS, ks_b, row_b);
