@@ -114,7 +114,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="frames per GPU per step")
-    ap.add_argument("--chunk", type=int, default=0, help="frames per internal chunk (0 = library default)")
+    ap.add_argument("--chunk", type=int, default=512, help="frames per internal chunk (fdt_config.max_batch; 0 = library default 256)")
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -128,7 +128,8 @@ def main():
     config = {"workload": "configs[1]: short-range BlazeFace 128x128 (896 anchors), batch %d synthetic 1280x720 BGR frames per GPU, "
                           "letterbox->detect->weighted NMS" % args.batch,
               "frames_per_gpu": args.batch, "frame": "1280x720x3 u8 BGR", "sharding": "frames split across ranks, no collective",
-              "l2": "inputs_exceed_l2 (%.1f GB of frames per step)" % (args.batch * WIDTH * HEIGHT * 3 / 1e9)}
+              "l2": "inputs_exceed_l2 (%.1f GB of frames per step)" % (args.batch * WIDTH * HEIGHT * 3 / 1e9),
+              "chunk": "%d frames per internal chunk (fdt_config.max_batch), chunks alternate over two streams" % (args.chunk or 256)}
 
     if args.impl == "reference":
         if rank != 0:

@@ -135,6 +135,6 @@ def test_plan_lowering(lib, model_bytes, model, macs, steps):
         assert abs(float(m.group(2)) - macs) < 0.002                      # SURVEY.md 2.3 MAC counts
         if fuse == 1 and steps:
             assert int(m.group(1)) == steps                               # stem + 16 BlazeBlocks + 4 heads
-            assert text.count(" dwpw_tc ") == 20 and text.count(" stem_tc ") == 1   # BlazeBlocks + heads on tcgen05
+            assert text.count(" block_ws ") == 20 and text.count(" stem_ws ") == 1   # BlazeBlocks + heads + stem on the warp-specialised tcgen05 kernels
     assert lib.fdt_host_plan_describe(d[:1000], 1000, 1, buf, len(buf)) != 0   # truncated flatbuffer is rejected, not a crash
     assert lib.fdt_host_plan_describe(b"\x00" * 64, 64, 1, buf, len(buf)) != 0

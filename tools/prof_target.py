@@ -1,4 +1,4 @@
-"""Small fixed workload for ncu: 3 chunks of 256 synthetic 1280x720 frames through the fast-mode
+"""Small fixed workload for ncu: 3 chunks of 512 synthetic 1280x720 frames through the fast-mode
 pipeline (23 kernel launches per chunk: letterbox, stem, 16 BlazeBlocks, 4 heads, decode+NMS)."""
 import sys
 from pathlib import Path
@@ -7,7 +7,7 @@ sys.path.insert(0, str(ROOT))
 import numpy as np, torch
 import face_detection_tflite_b200 as fdt
 from face_detection_tflite_b200 import synth
-chunk = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+chunk = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 d = fdt.FaceDetector.create(fdt.FaceDetectionModel.shortRange, withMesh=False, maxBatch=chunk)
 base = np.concatenate([synth.face_frames(56, 1280, 720), synth.noise_frames(8, 1280, 720)])
 dev = torch.from_numpy(base).cuda().repeat(chunk // 64, 1, 1, 1).contiguous()
