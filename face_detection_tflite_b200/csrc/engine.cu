@@ -208,6 +208,7 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         }
         p.smem_bytes = st.smem;
         p.ns = st.ns; p.na = st.na; p.nd = st.nd; p.nt = st.nt; p.trace = nullptr;
+        p.no = st.no; p.KSo = st.KSo; p.out_stage_floats = st.out_stage_floats;
         if (st.kind == kStepBlockWs) {
           p.in_floats = st.in_stage_floats;
           if (!launch_block_ws(p, B, ctx.cap, s)) { failed_ = true; fprintf(stderr, "fdt: cuTensorMapEncodeTiled failed for step '%s'\n", st.name.c_str()); }

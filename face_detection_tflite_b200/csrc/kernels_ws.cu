@@ -35,7 +35,10 @@ namespace {
 
 constexpr uint32_t kLBO = 128;   // bytes between the two 16-byte K chunks of one MMA (adjacent core matrices)
 constexpr int kEpiWarps = 4;
-constexpr int kMmaWarps = 2;   // issuing one tcgen05.mma costs its thread ~150 cycles: two issuers alternate tiles
+#ifndef FDT_MMA_WARPS
+#define FDT_MMA_WARPS 2
+#endif
+constexpr int kMmaWarps = FDT_MMA_WARPS;   // issuing one tcgen05.mma costs its thread ~150 cycles: two issuers alternate tiles
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -52,6 +55,11 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive without release ordering: used where the signal only says "I have finished READING" (TMEM accumulator / input
+// stage consumed into registers).  A releasing arrive would also wait for the epilogue's global stores to be performed.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -203,45 +211,61 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 
 // RES 3 / 4: residual from another HBM tensor (same size / 2x2 max-pooled), float4 loads; `gres` points at this thread's
 // residual pixel (top-left of the pool window), gks / grow are its pixel / row strides in floats, gres_c its channels.
-template <int RES, int LEAKY>
-__device__ __forceinline__ void epi_fast(uint32_t tcol0, uint32_t res_a, uint32_t bias_a, uint32_t alpha_a, float* orow, bool valid,
-                                         int cout_s, uint32_t ks_b, uint32_t row_b,
+// SM = 1: the results go to the shared-memory output tile at `out_s` (then one TMA store per tile) instead of to HBM.
+template <int RES, int LEAKY, int SM>
+__device__ __forceinline__ void epi_fast(uint32_t tcol0, uint32_t res_a, uint32_t bias_a, uint32_t alpha_a, float* orow, uint32_t out_s,
+                                         bool valid, bool store_ok, int cout_s, uint32_t ks_b, uint32_t row_b,
                                          const float* gres = nullptr, int gks = 0, int grow = 0, int gres_c = 0) {
+  // 16 columns per TMEM round trip (8 for the pooled residuals, whose four taps per quad need the registers); the
+  // accumulator is Npad = 16k columns wide, quads >= cout_s are computed on whatever lies there and dropped at the store
+#ifdef FDT_EPI_X8
+  constexpr int NQ = 2;
+#else
+  constexpr int NQ = (RES == 2 || RES == 4) ? 2 : 4;
+#endif
 #pragma unroll 1
-  for (int c0 = 0; c0 < cout_s; c0 += 8) {
-    uint32_t u[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
-                 : "r"(tcol0 + (uint32_t)c0));
+  for (int c0 = 0; c0 < cout_s; c0 += 4 * NQ) {
+    uint32_t u[16];
+    if (NQ == 4)
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+            "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+          : "r"(tcol0 + (uint32_t)c0));
+    else
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                   : "r"(tcol0 + (uint32_t)c0));
     const uint32_t cb = 4u * (uint32_t)c0;
-    float4 b0 = lds4(bias_a + cb), b1 = lds4(bias_a + cb + 16u);
-    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, a0 = r0, a1 = r0;
-    if (LEAKY) { a0 = lds4(alpha_a + cb); a1 = lds4(alpha_a + cb + 16u); }
-    if (RES == 1) {
-      r0 = lds4(res_a + cb); r1 = lds4(res_a + cb + 16u);
-    } else if (RES == 2) {
-      r0 = max4(max4(lds4(res_a + cb), lds4(res_a + ks_b + cb)), max4(lds4(res_a + row_b + cb), lds4(res_a + row_b + ks_b + cb)));
-      r1 = max4(max4(lds4(res_a + cb + 16u), lds4(res_a + ks_b + cb + 16u)), max4(lds4(res_a + row_b + cb + 16u), lds4(res_a + row_b + ks_b + cb + 16u)));
-    } else if (RES == 3) {
-      if (valid) {
-        if (c0 < gres_c) r0 = ldg4(gres + c0);
-        if (c0 + 4 < gres_c) r1 = ldg4(gres + c0 + 4);
-      }
-    } else if (RES == 4) {
-      if (valid) {
-        if (c0 < gres_c) r0 = max4(max4(ldg4(gres + c0), ldg4(gres + gks + c0)), max4(ldg4(gres + grow + c0), ldg4(gres + grow + gks + c0)));
-        if (c0 + 4 < gres_c) r1 = max4(max4(ldg4(gres + c0 + 4), ldg4(gres + gks + c0 + 4)), max4(ldg4(gres + grow + c0 + 4), ldg4(gres + grow + gks + c0 + 4)));
+    float4 bv[NQ], rv[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const uint32_t o = cb + 16u * q;
+      bv[q] = lds4(bias_a + o);
+      rv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (RES == 1) {
+        rv[q] = lds4(res_a + o);
+      } else if (RES == 2) {
+        rv[q] = max4(max4(lds4(res_a + o), lds4(res_a + ks_b + o)), max4(lds4(res_a + row_b + o), lds4(res_a + row_b + ks_b + o)));
+      } else if (RES == 3) {
+        if (valid && c0 + 4 * q < gres_c) rv[q] = ldg4(gres + c0 + 4 * q);
+      } else if (RES == 4) {
+        if (valid && c0 + 4 * q < gres_c)
+          rv[q] = max4(max4(ldg4(gres + c0 + 4 * q), ldg4(gres + gks + c0 + 4 * q)), max4(ldg4(gres + grow + c0 + 4 * q), ldg4(gres + grow + gks + c0 + 4 * q)));
       }
     }
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    float4 v0 = make_float4(__uint_as_float(u[0]) + b0.x, __uint_as_float(u[1]) + b0.y, __uint_as_float(u[2]) + b0.z, __uint_as_float(u[3]) + b0.w);
-    float4 v1 = make_float4(__uint_as_float(u[4]) + b1.x, __uint_as_float(u[5]) + b1.y, __uint_as_float(u[6]) + b1.z, __uint_as_float(u[7]) + b1.w);
-    if (RES) { add4(v0, r0); add4(v1, r1); }
-    if (LEAKY) { v0 = leaky4(v0, a0); v1 = leaky4(v1, a1); }
-    else { v0 = max4(v0, make_float4(0.f, 0.f, 0.f, 0.f)); v1 = max4(v1, make_float4(0.f, 0.f, 0.f, 0.f)); }
-    if (valid) {
-      *reinterpret_cast<float4*>(orow + c0) = v0;
-      if (c0 + 4 < cout_s) *reinterpret_cast<float4*>(orow + c0 + 4) = v1;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      float4 v = make_float4(__uint_as_float(u[4 * q]) + bv[q].x, __uint_as_float(u[4 * q + 1]) + bv[q].y,
+                             __uint_as_float(u[4 * q + 2]) + bv[q].z, __uint_as_float(u[4 * q + 3]) + bv[q].w);
+      if (RES) add4(v, rv[q]);
+      if (LEAKY) v = leaky4(v, lds4(alpha_a + cb + 16u * q));
+      else v = max4(v, make_float4(0.f, 0.f, 0.f, 0.f));
+      if (store_ok && c0 + 4 * q < cout_s) {
+        if (SM) asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(out_s + 4u * (uint32_t)(c0 + 4 * q)), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+        else *reinterpret_cast<float4*>(orow + c0 + 4 * q) = v;
+      }
     }
   }
 }
@@ -323,18 +347,23 @@ __device__ __forceinline__ void epi_tile(const DwPwTcP& p, uint32_t tcol0, uint3
 }
 
 // debug trace: role r, CTA-local tile i, stamp j (0 = before waits, 1 = after waits, 2 = work done)
+// (compiled in only with -DFDT_TRACE_BUILD: the stamps cost ~3 % even when the trace pointer is null)
+#ifndef FDT_TRACE_BUILD
+#define WS_TRACE(r, i, j) do { (void)tr; } while (0)
+#else
 #define WS_TRACE(r, i, j) do { if (tr && (i) < 64) tr[((r) * 64 + (i)) * 3 + (j)] = clock64(); } while (0)
+#endif
 
 // Shared-memory carve-up (must match plan_ws in plan.cpp):
 //   [W (w_parts x Npad x K8)] [bias Npad] [alpha Npad] [dw taps+bias 10 x K8] [dtab n_items x 8 B] [barriers 128 B]
 //   | 128-byte aligned: [A ring: NA x (hi, lo) x 128 x K8] [input ring: NS x in_stage_bytes]
 // S: depthwise stride (0 = no depthwise, pointwise only); RS: output rows per depthwise work item.
 template <int ND, int S, int RS>
-__global__ void __launch_bounds__((ND + kEpiWarps + 1 + kMmaWarps) * 32, 1)
-k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntiles) {
+__global__ void __launch_bounds__((ND + kEpiWarps + 2 + kMmaWarps) * 32, 1)
+k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out, DwPwTcP p, int B, int ntiles) {
   extern __shared__ __align__(128) float smem[];
   __shared__ uint32_t tmem_base_s;
-  constexpr int kThreads = (ND + kEpiWarps + 1 + kMmaWarps) * 32;
+  constexpr int kThreads = (ND + kEpiWarps + 2 + kMmaWarps) * 32;
   constexpr int kDwThreads = ND * 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel may begin its own prologue
@@ -359,6 +388,16 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
   const int thw = p.TH * p.TW;
   const int nslots = p.G * thw;
   const bool epi_reads_stage = p.res_mode == 1;
+  // epilogue mode (uniform for the CTA; the epilogue and the store warp must agree on it)
+  const int res_kind = p.res_mode == 1 ? (p.res_pool ? 2 : 1) : (p.res_mode == 2 ? 3 : 0);
+  // global residual fast path: float4-aligned residual tensor; pooled windows must lie inside it (even dimensions)
+  const bool gfast = res_kind == 3 && p.res_Cs % 4 == 0 && p.res_C % 4 == 0 && p.res_istride % 4 == 0 && ((size_t)p.res % 16 == 0) &&
+                     (!p.res_pool || (p.res_H == 2 * p.OH && p.res_W == 2 * p.OW));
+  const bool fast = p.vec_store && (res_kind == 3 ? gfast : (res_kind == 0 || p.KS >= p.CoutS));
+  const int gmul = p.res_pool ? 2 : 1, gks = p.res_Cs, grow = p.res_W * p.res_Cs;
+  const bool tma_out = fast && p.no > 0;
+  const uint32_t sOut_a = smem_u32(sIn0 + (size_t)NS * in_stage_floats), out_stage_b = (uint32_t)p.out_stage_floats * 4u, kso_b = (uint32_t)p.KSo * 4u;
+  const uint32_t out_full = bar0 + 8u * 28, out_empty = bar0 + 8u * 30;
 
   // ---- prologue (all threads): weights, bias, tables, barriers, TMEM -------------------------------
   const uint32_t sB_u32 = smem_u32(sB);
@@ -394,8 +433,13 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
       mbar_init(d_full + 8u * i, 1);
       mbar_init(d_empty + 8u * i, kEpiWarps);
     }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(out_full + 8u * i, kEpiWarps);
+      mbar_init(out_empty + 8u * i, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    if (p.no > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_out) : "memory");
   }
   if (warp == kEpiWarps + ND + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)p.tmem_cols));
@@ -422,12 +466,7 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
     const int rs = p.res_pool ? 2 : 1;
     const uint32_t res_off = slot_ok ? (uint32_t)((((size_t)e_g * p.IH + e_ty * rs + p.dpt) * p.IW + e_tx * rs + p.dpl) * p.KS) : 0u;
     const uint32_t sIn0_a = smem_u32(sIn0), bias_a = smem_u32(sBias), alpha_a = smem_u32(sAlpha);
-    const int res_kind = p.res_mode == 1 ? (p.res_pool ? 2 : 1) : (p.res_mode == 2 ? 3 : 0);
-    // global residual fast path: float4-aligned residual tensor; pooled windows must lie inside it (even dimensions)
-    const bool gfast = res_kind == 3 && p.res_Cs % 4 == 0 && p.res_C % 4 == 0 && p.res_istride % 4 == 0 && ((size_t)p.res % 16 == 0) &&
-                       (!p.res_pool || (p.res_H == 2 * p.OH && p.res_W == 2 * p.OW));
-    const bool fast = p.vec_store && (res_kind == 3 ? gfast : (res_kind == 0 || p.KS >= p.CoutS));
-    const int gmul = p.res_pool ? 2 : 1, gks = p.res_Cs, grow = p.res_W * p.res_Cs;
+    int ob = 0, oph = 0;
     const uint32_t ks_b = (uint32_t)p.KS * 4u, row_b = (uint32_t)p.IW * ks_b;
     int si = 0, sph = 0, di = 0, dph = 0;
     long long* tr = (p.trace && blockIdx.x == 0 && tid == 0) ? p.trace : nullptr;
@@ -449,24 +488,59 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
       float* orow = p.out + (long long)b0 * p.out_istride + ((long long)ty0 * p.OW + tx0) * p.CoutS + o_rel;
       const float* rbase = p.res_mode == 2 ? p.res + (size_t)(valid ? b : 0) * p.res_istride : nullptr;
       const uint32_t tcol0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(di * p.Npad);
-      if (fast && res_kind == 3) {
-        const float* gres = rbase + ((size_t)(valid ? oy : 0) * gmul * p.res_W + (size_t)(valid ? ox : 0) * gmul) * p.res_Cs;
-        if (p.act == kActRelu) {
-          if (p.res_pool) epi_fast<4, 0>(tcol0, res_a, bias_a, alpha_a, orow, valid, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C);
-          else epi_fast<3, 0>(tcol0, res_a, bias_a, alpha_a, orow, valid, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C);
+      if (fast) {
+        const float* gres = res_kind == 3 ? rbase + ((size_t)(valid ? oy : 0) * gmul * p.res_W + (size_t)(valid ? ox : 0) * gmul) * p.res_Cs : nullptr;
+        if (tma_out) {
+          // the output tile is assembled in shared memory and leaves with one TMA store (full-line writes; direct
+          // float4 stores at a CoutS-float pixel stride touch 24..32 lines per instruction and saturate the LSU)
+          const uint32_t out_s = sOut_a + (uint32_t)ob * out_stage_b + (uint32_t)slot * kso_b;
+          WS_TRACE(5, it, 0);
+          mbar_wait(out_empty + 8u * ob, (uint32_t)(oph ^ 1));      // the store warp has finished reading buffer `ob`
+          WS_TRACE(5, it, 1);
+          if (res_kind == 3) {
+            if (p.act == kActRelu) {
+              if (p.res_pool) epi_fast<4, 0, 1>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, slot_ok, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C);
+              else epi_fast<3, 0, 1>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, slot_ok, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C);
+            } else {
+              if (p.res_pool) epi_fast<4, 1, 1>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, slot_ok, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C);
+              else epi_fast<3, 1, 1>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, slot_ok, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C);
+            }
+          } else if (p.act == kActRelu) {
+            if (res_kind == 1) epi_fast<1, 0, 1>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, slot_ok, p.CoutS, ks_b, row_b);
+            else if (res_kind == 2) epi_fast<2, 0, 1>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, slot_ok, p.CoutS, ks_b, row_b);
+            else epi_fast<0, 0, 1>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, slot_ok, p.CoutS, ks_b, row_b);
+          } else {
+            if (res_kind == 1) epi_fast<1, 1, 1>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, slot_ok, p.CoutS, ks_b, row_b);
+            else if (res_kind == 2) epi_fast<2, 1, 1>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, slot_ok, p.CoutS, ks_b, row_b);
+            else epi_fast<0, 1, 1>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, slot_ok, p.CoutS, ks_b, row_b);
+          }
+          WS_TRACE(5, it, 2);
+          WS_TRACE(6, it, 0);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile's STS -> visible to the TMA store
+          WS_TRACE(6, it, 1);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(out_full + 8u * ob);
+          WS_TRACE(6, it, 2);
+          if (++ob == p.no) { ob = 0; oph ^= 1; }
         } else {
-          if (p.res_pool) epi_fast<4, 1>(tcol0, res_a, bias_a, alpha_a, orow, valid, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C);
-          else epi_fast<3, 1>(tcol0, res_a, bias_a, alpha_a, orow, valid, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C);
-        }
-      } else if (fast) {
-        if (p.act == kActRelu) {
-          if (res_kind == 1) epi_fast<1, 0>(tcol0, res_a, bias_a, alpha_a, orow, valid, p.CoutS, ks_b, row_b);
-          else if (res_kind == 2) epi_fast<2, 0>(tcol0, res_a, bias_a, alpha_a, orow, valid, p.CoutS, ks_b, row_b);
-          else epi_fast<0, 0>(tcol0, res_a, bias_a, alpha_a, orow, valid, p.CoutS, ks_b, row_b);
-        } else {
-          if (res_kind == 1) epi_fast<1, 1>(tcol0, res_a, bias_a, alpha_a, orow, valid, p.CoutS, ks_b, row_b);
-          else if (res_kind == 2) epi_fast<2, 1>(tcol0, res_a, bias_a, alpha_a, orow, valid, p.CoutS, ks_b, row_b);
-          else epi_fast<0, 1>(tcol0, res_a, bias_a, alpha_a, orow, valid, p.CoutS, ks_b, row_b);
+          const uint32_t out_s = 0u;
+          if (res_kind == 3) {
+            if (p.act == kActRelu) {
+              if (p.res_pool) epi_fast<4, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C);
+              else epi_fast<3, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C);
+            } else {
+              if (p.res_pool) epi_fast<4, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C);
+              else epi_fast<3, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C);
+            }
+          } else if (p.act == kActRelu) {
+            if (res_kind == 1) epi_fast<1, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b);
+            else if (res_kind == 2) epi_fast<2, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b);
+            else epi_fast<0, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b);
+          } else {
+            if (res_kind == 1) epi_fast<1, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b);
+            else if (res_kind == 2) epi_fast<2, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b);
+            else epi_fast<0, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b);
+          }
         }
       } else {
         if (res_kind == 1) epi_tile<1, 1>(p, tcol0, res_a, bias_a, alpha_a, orow, valid, rbase, oy, ox);
@@ -477,8 +551,8 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(d_empty + 8u * di);
-        if (epi_reads_stage) mbar_arrive(empty_in + 8u * si);
+        mbar_arrive_relaxed(d_empty + 8u * di);
+        if (epi_reads_stage) mbar_arrive_relaxed(empty_in + 8u * si);
       }
       WS_TRACE(0, it, 2);
       if (++si == NS) { si = 0; sph ^= 1; }
@@ -574,6 +648,33 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
       }
     }
     __syncwarp();
+  } else if (warp == kEpiWarps + ND + 1 + kMmaWarps) {
+    // =============================== output store warp ==============================================
+    // One TMA store per tile from the shared-memory output tile the epilogue warps have filled; keeps the bulk-group
+    // bookkeeping (commit / wait_group.read) off the epilogue's critical path.
+    if (lane == 0 && tma_out) {
+      int ob = 0, oph = 0, prev = -1;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int grp, trem, tyi, txi;
+        p.fd_tpg.divmod(tile, grp, trem);
+        p.fd_tilesX.divmod(trem, tyi, txi);
+        mbar_wait(out_full + 8u * ob, (uint32_t)oph);
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+                     ::"l"(&tmap_out), "r"(0), "r"(txi * p.TW), "r"(tyi * p.TH), "r"(grp * p.G), "r"(sOut_a + (uint32_t)ob * out_stage_b) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (p.no == 2) {
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // every store but the newest has read its tile
+          if (prev >= 0) mbar_arrive(out_empty + 8u * prev);
+          prev = ob;
+        } else {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          mbar_arrive(out_empty + 8u * ob);
+        }
+        if (++ob == p.no) { ob = 0; oph ^= 1; }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");            // all output tiles written before the CTA exits
+    }
+    __syncwarp();
   } else {
     // =============================== MMA issuer =====================================================
     if (lane == 0) {
@@ -600,6 +701,16 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
         WS_TRACE(3, it, 1);
         const uint32_t dcol = tmem_base + (uint32_t)(di * p.Npad);
         uint32_t ah = a0 + (uint32_t)ai * a_buf, al = ah + a_half, wh = w_hi0, wl = w_lo0, acc = 0u;
+#ifdef FDT_OLD_MMA
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t db = ((uint64_t)hi << 32) | (wh + 16u * ks), dah = ((uint64_t)hi << 32) | (ah + 16u * ks), dal = ((uint64_t)hi << 32) | (al + 16u * ks);
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(dcol), "l"(dah), "l"(db), "r"(idesc), "r"(ks > 0 ? 1u : 0u));
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(dcol), "l"(dal), "l"(db), "r"(idesc), "r"(1u));
+          if (w_split) { const uint64_t dbl = ((uint64_t)hi << 32) | (wl + 16u * ks);
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(dcol), "l"(dah), "l"(dbl), "r"(idesc), "r"(1u)); }
+        }
+        (void)acc;
+#else
 #pragma unroll 1
         for (int ks = 0; ks < ksteps; ++ks) {
           mma_ss<0>(dcol, ah, hi, wh, hi, idesc, acc);
@@ -608,6 +719,7 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, DwPwTcP p, int B, int ntile
           if (w_split) mma_ss<0>(dcol, ah, hi, wl, hi, idesc, 1u);
           ah += 16u; al += 16u; wh += 16u; wl += 16u; acc = 1u;
         }
+#endif
         WS_TRACE(4, it, 0);
         mma_commit(a_empty + 8u * ai);   // operand buffer reusable once these MMAs have read it
         WS_TRACE(4, it, 1);
@@ -753,7 +865,7 @@ __global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUte
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(d_empty + 8u * di);
+      if (lane == 0) mbar_arrive_relaxed(d_empty + 8u * di);
     }
   } else if (warp < 16) {
     // =============================== builders: raw patch -> fp16 patch -> im2col A =======================
@@ -937,8 +1049,33 @@ bool input_tensor_map(const DwPwTcP& p, int cap, CUtensorMap* out) {
   return true;
 }
 
+// Tensor map of the block's output activation: f32 [cap][OH][OW][CoutS], box {KSo, TW, TH, G}; channels >= CoutS of the
+// shared-memory tile, pixels outside the image and images >= cap are dropped by the store.
+bool output_tensor_map(const DwPwTcP& p, int cap, CUtensorMap* out) {
+  typedef std::tuple<const void*, int, int, int, int, int, int, int, int, long long> Key;
+  static std::mutex mu;
+  static std::map<Key, CUtensorMap> cache;
+  Key key(p.out, cap, p.OH, p.OW, p.CoutS, p.KSo, p.TW, p.TH, p.G, p.out_istride);
+  std::lock_guard<std::mutex> g(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return true; }
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t gdim[4] = {(cuuint64_t)p.CoutS, (cuuint64_t)p.OW, (cuuint64_t)p.OH, (cuuint64_t)cap};
+  cuuint64_t gstr[3] = {(cuuint64_t)p.CoutS * 4, (cuuint64_t)p.OW * p.CoutS * 4, (cuuint64_t)p.out_istride * 4};
+  cuuint32_t box[4] = {(cuuint32_t)p.KSo, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.G};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap tm;
+  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  cache[key] = tm;
+  *out = tm;
+  return true;
+}
+
 template <int ND, int S, int RS>
-void launch_ws_k(const CUtensorMap& tm, const DwPwTcP& p, int B, int ntiles, cudaStream_t s) {
+void launch_ws_k(const CUtensorMap& tm, const CUtensorMap& tmo, const DwPwTcP& p, int B, int ntiles, cudaStream_t s) {
   static std::mutex mu;
   static std::map<int, size_t> cur;
   int dev = 0;
@@ -953,20 +1090,20 @@ void launch_ws_k(const CUtensorMap& tm, const DwPwTcP& p, int B, int ntiles, cud
   }
   int grid = std::min(ntiles, 148);
   if (grid < 1) grid = 1;
-  launch_pdl(k_block_ws<ND, S, RS>, grid, (ND + kEpiWarps + 1 + kMmaWarps) * 32, p.smem_bytes, s, tm, p, B, ntiles);
+  launch_pdl(k_block_ws<ND, S, RS>, grid, (ND + kEpiWarps + 2 + kMmaWarps) * 32, p.smem_bytes, s, tm, tmo, p, B, ntiles);
 }
 
 template <int ND>
-void launch_ws_nd(const CUtensorMap& tm, const DwPwTcP& p, int B, int ntiles, cudaStream_t s) {
+void launch_ws_nd(const CUtensorMap& tm, const CUtensorMap& tmo, const DwPwTcP& p, int B, int ntiles, cudaStream_t s) {
   const int S = p.has_dw ? p.s : 0;
   switch (S * 16 + (S ? p.RS : 1)) {
-    case 1: launch_ws_k<ND, 0, 1>(tm, p, B, ntiles, s); break;
-    case 16 + 1: launch_ws_k<ND, 1, 1>(tm, p, B, ntiles, s); break;
-    case 16 + 2: launch_ws_k<ND, 1, 2>(tm, p, B, ntiles, s); break;
-    case 16 + 4: launch_ws_k<ND, 1, 4>(tm, p, B, ntiles, s); break;
-    case 32 + 1: launch_ws_k<ND, 2, 1>(tm, p, B, ntiles, s); break;
-    case 32 + 2: launch_ws_k<ND, 2, 2>(tm, p, B, ntiles, s); break;
-    case 32 + 4: launch_ws_k<ND, 2, 4>(tm, p, B, ntiles, s); break;
+    case 1: launch_ws_k<ND, 0, 1>(tm, tmo, p, B, ntiles, s); break;
+    case 16 + 1: launch_ws_k<ND, 1, 1>(tm, tmo, p, B, ntiles, s); break;
+    case 16 + 2: launch_ws_k<ND, 1, 2>(tm, tmo, p, B, ntiles, s); break;
+    case 16 + 4: launch_ws_k<ND, 1, 4>(tm, tmo, p, B, ntiles, s); break;
+    case 32 + 1: launch_ws_k<ND, 2, 1>(tm, tmo, p, B, ntiles, s); break;
+    case 32 + 2: launch_ws_k<ND, 2, 2>(tm, tmo, p, B, ntiles, s); break;
+    case 32 + 4: launch_ws_k<ND, 2, 4>(tm, tmo, p, B, ntiles, s); break;
     default: break;
   }
 }
@@ -1033,28 +1170,36 @@ void launch_stem_ws_kw(const CUtensorMap& tm, const StemWsP& p, int B, cudaStrea
 
 bool launch_block_ws(const DwPwTcP& p0, int B, int cap, cudaStream_t s) {
   DwPwTcP p = p0;
-  CUtensorMap tm;
+  CUtensorMap tm, tmo;
   if (!input_tensor_map(p, cap, &tm)) return false;
+  // the TMA-store epilogue needs a float4-aligned output tensor (the heads' dense views keep direct stores)
+  if (p.no > 0 && !(p.vec_store && p.CoutS % 4 == 0 && p.out_istride % 4 == 0)) p.no = 0;
+  if (p.no > 0) { if (!output_tensor_map(p, cap, &tmo)) return false; } else tmo = tm;
   int groups = (B + p.G - 1) / p.G;
   int ntiles = groups * p.tilesX * p.tilesY;
-  // FDT_WS_TRACE=1: per-role timeline of CTA 0 (diagnostic; synchronises after every launch)
+  // FDT_WS_TRACE=1 (library built with FDT_NVCC_FLAGS=-DFDT_TRACE_BUILD): per-role timeline of CTA 0 (diagnostic;
+  // synchronises after every launch)
+#ifdef FDT_TRACE_BUILD
   static const bool trace = [] { const char* e = std::getenv("FDT_WS_TRACE"); return e && e[0] == '1'; }();
+#else
+  static const bool trace = false;
+#endif
   static long long* d_trace = nullptr;
   if (trace) {
-    if (!d_trace) cudaMalloc(&d_trace, 5 * 64 * 3 * sizeof(long long));
-    cudaMemsetAsync(d_trace, 0, 5 * 64 * 3 * sizeof(long long), s);
+    if (!d_trace) cudaMalloc(&d_trace, 7 * 64 * 3 * sizeof(long long));
+    cudaMemsetAsync(d_trace, 0, 7 * 64 * 3 * sizeof(long long), s);
     p.trace = d_trace;
   }
-  if (p.nd == 12) launch_ws_nd<12>(tm, p, B, ntiles, s);
-  else launch_ws_nd<8>(tm, p, B, ntiles, s);
+  if (p.nd == 12) launch_ws_nd<12>(tm, tmo, p, B, ntiles, s);
+  else launch_ws_nd<8>(tm, tmo, p, B, ntiles, s);
   if (trace) {
-    static long long h[5 * 64 * 3];
+    static long long h[7 * 64 * 3];
     cudaStreamSynchronize(s);
     cudaMemcpy(h, d_trace, sizeof h, cudaMemcpyDeviceToHost);
     const int n = std::min(64, (ntiles + 147) / 148);
-    static const char* rn[5] = {"epi", "dw", "prod", "mma", "commit(a,d)"};
+    static const char* rn[7] = {"epi", "dw", "prod", "mma", "commit(a,d)", "epi(bufwait,math)", "epi(fence,arrive)"};
     fprintf(stderr, "WS_TRACE K8=%d Npad=%d S=%d RS=%d nd=%d ns=%d na=%d tiles/cta=%d:", p.K8, p.Npad, p.has_dw ? p.s : 0, p.RS, p.nd, p.ns, p.na, n);
-    for (int r = 0; r < 5; ++r) {
+    for (int r = 0; r < 7; ++r) {
       double wait = 0, work = 0; int cnt = 0;
       for (int i = 2; i < n - 1; ++i) {          // steady state: skip the first two and the last tile
         const long long* t = h + (r * 64 + i) * 3;

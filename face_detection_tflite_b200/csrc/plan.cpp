@@ -509,18 +509,33 @@ struct Builder {
       size_t head = ((size_t)s.w_parts * s.Npad * s.K8 + 2 * (size_t)s.Npad + (s.has_dw ? 10 * (size_t)s.K8 : 0)) * 4 + n_items * 8 + 32 * 8 + 128;
       size_t a_bytes = (size_t)2 * 128 * s.K8 * 4;
       size_t in_bytes = ((size_t)s.G * s.IH * s.IW * s.KS * 4 + 127) / 128 * 128;
-      // (A buffers, input stages); even A rings let the two MMA issuers alternate tiles
-      static const int combos[8][2] = {{4, 6}, {4, 5}, {2, 5}, {2, 4}, {2, 3}, {2, 2}, {1, 2}, {1, 1}};
-      for (const auto& c : combos) {
-        if (c[0] > max_na || c[1] > max_ns) continue;
-        size_t total = head + c[0] * a_bytes + c[1] * in_bytes;
-        if (total > cap) continue;
-        s.na = c[0]; s.ns = c[1];
-        s.in_stage_floats = (int)(in_bytes / 4);
-        s.smem = total;
-        s.kind = kStepBlockWs;
-        *st = s;
-        return true;
+      // Output tile for the TMA-store epilogue: pixel stride KSo = CoutS rounded to an odd number of quads (conflict-free
+      // STS.128), one or two buffers.  Ring choice: (A buffers, input stages) with even A rings preferred (the two MMA
+      // issuers alternate tiles); output buffers first, since the direct-store epilogue saturates the LSU.
+      static const int want_no = [] { const char* e = std::getenv("FDT_WS_NO"); return e ? std::atoi(e) : 0; }();   // measured: direct stores are as fast; TMA store via FDT_WS_NO=2
+      const int couts = ru(s.Cout, 4);
+      s.KSo = ((couts / 4) % 2 == 0) ? couts + 4 : couts;
+      const size_t out_bytes = ((size_t)s.G * s.TH * s.TW * s.KSo * 4 + 127) / 128 * 128;
+      const bool can_tma_out = s.KSo <= 256;
+      static const int combos[10][2] = {{4, 6}, {4, 5}, {4, 4}, {2, 5}, {2, 4}, {2, 3}, {2, 2}, {1, 2}, {1, 1}, {0, 0}};
+      // preference: two output tiles + prefetching input ring (ns >= 2), then one output tile + prefetching ring, then any
+      // ring with an output tile, then direct stores
+      static const int prefs[5][2] = {{2, 2}, {1, 2}, {2, 1}, {1, 1}, {0, 1}};     // (output tiles, min input stages)
+      for (const auto& pr : prefs) {
+        const int no = pr[0];
+        if (no > want_no || (no > 0 && !can_tma_out)) continue;
+        for (const auto& c : combos) {
+          if (c[0] == 0 || c[0] > max_na || c[1] > max_ns || c[1] < pr[1]) continue;
+          size_t total = head + c[0] * a_bytes + c[1] * in_bytes + no * out_bytes;
+          if (total > cap) continue;
+          s.na = c[0]; s.ns = c[1]; s.no = no;
+          s.in_stage_floats = (int)(in_bytes / 4);
+          s.out_stage_floats = (int)(out_bytes / 4);
+          s.smem = total;
+          s.kind = kStepBlockWs;
+          *st = s;
+          return true;
+        }
       }
     }
     return false;
@@ -930,10 +945,10 @@ std::string Plan::describe() const {
     const PTensor& o = tensors[st.out];
     macs += st.macs;
     snprintf(buf, sizeof buf,
-             "%3zu %-10s in=%d res=%d%s/m%d out=%d[%dx%dx%d Cs%d %s] act=%d dw=%d/s%d K=%d NC=%dx%d TM=%d NPG=%d tile=%dx%dx%d RS=%d nd=%d ns=%d na=%d smem=%zu  %s\n",
+             "%3zu %-10s in=%d res=%d%s/m%d out=%d[%dx%dx%d Cs%d %s] act=%d dw=%d/s%d K=%d NC=%dx%d TM=%d NPG=%d tile=%dx%dx%d RS=%d nd=%d ns=%d na=%d no=%d smem=%zu  %s\n",
              i, kn[st.kind], st.in >= 0 ? tensors[st.in].tf : -1, st.in2 >= 0 ? tensors[st.in2].tf : -1,
              st.res_pool ? "(pool)" : "", st.res_mode, o.tf, o.H, o.W, o.C, o.Cs, o.root >= 0 ? "view" : "arena", st.act,
-             (int)st.has_dw, st.dws, st.K, st.NC, st.nchunks, st.TM, st.NPG, st.TH, st.TW, st.G, st.RS, st.nd, st.ns, st.na, st.smem, st.name.c_str());
+             (int)st.has_dw, st.dws, st.K, st.NC, st.nchunks, st.TM, st.NPG, st.TH, st.TW, st.G, st.RS, st.nd, st.ns, st.na, st.no, st.smem, st.name.c_str());
     s += buf;
   }
   snprintf(buf, sizeof buf, "steps=%zu  MACs/image=%.3fM  arena/image=%.1f KB  weights=%.1f KB\n", steps.size(),

@@ -41,7 +41,8 @@ struct PStep {
   size_t smem = 0;
   int K8 = 0, Npad = 0, a_rows = 0, RS = 1, tmem_cols = 0, w_parts = 1, nbuf = 1;   // tensor-core variant
   double out_scale = 1.0;    // k_stem_ws: D * out_scale + bias
-  int ns = 0, na = 0, nd = 8, nt = 2, in_stage_floats = 0;   // warp-specialised variant: input stages, A buffers, depthwise warps
+  int ns = 0, na = 0, nd = 8, nt = 2, in_stage_floats = 0;
+  int no = 0, KSo = 0, out_stage_floats = 0;           // TMA-store epilogue (k_block_ws)   // warp-specialised variant: input stages, A buffers, depthwise warps
   int fh = 1, fw = 1, align = 0, half = 0;
   double macs = 0;  // per image
 };

@@ -463,3 +463,51 @@ def test_c_abi_status_codes(fdt, lib):
     assert lib.fdt_get_info(h, C.byref(iw), C.byref(ih), C.byref(na), C.byref(mf), C.byref(mb)) == 0
     assert (iw.value, ih.value, na.value, mf.value) == (128, 128, 896, 100)
     assert lib.fdt_last_h2d_bytes(h) == 48 and lib.fdt_last_launch_count(h) == 23
+
+
+# ---- alternative kernel paths (environment switches are read once per process -> subprocesses) ----------
+import os
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+_VARIANT_SCRIPT = r"""
+import sys
+sys.path.insert(0, %r)
+import numpy as np, cv2
+import face_detection_tflite_b200 as fdt
+from oracle.pipeline import OraclePipeline
+from pathlib import Path
+root = Path(%r)
+img = cv2.imread(str(root / "assets/samples/group-shot-bounding-box-ex1.jpeg"))
+for model, f in (("shortRange", "face_detection_short_range.tflite"), ("full", "face_detection_full_range.tflite")):
+    det_bytes = (root / "assets/models" / f).read_bytes()
+    d = fdt.FaceDetector.create(fdt.FaceDetectionModel[model], withMesh=False)
+    frames = np.stack([img, img[:, ::-1].copy(), img[::-1].copy()])
+    d.detectBatchRaw(frames, count=3, width=img.shape[1], height=img.shape[0])
+    boxes, scores = d.debugRawHeads(3)
+    o = OraclePipeline(det_bytes, model, None, "f64")
+    ref = o.det.run(np.stack([o.preprocess(fr)[0] for fr in frames]))
+    for got, want in ((boxes, ref[0]), (scores, ref[1])):
+        want = np.asarray(want).reshape(got.shape)
+        err = float(np.abs(got - want).max() / np.abs(want).max())
+        assert err <= 1e-4, (model, err)                     # north_star: 1e-4 relative on raw head outputs
+    d.dispose()
+print("variant ok")
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", [{"FDT_WS_NO": "2"},          # TMA-store epilogue (output tile in shared memory + store warp)
+                                 {"FDT_WS": "0"},             # k_dwpw_tc (bulk-synchronous tcgen05 kernel) instead of k_block_ws
+                                 {"FDT_STEM_WS": "0"},        # k_stem_tc (TF32 hi/lo im2col) instead of the fp16 stem
+                                 {"FDT_WS_ND": "8"},          # 8 depthwise warps everywhere
+                                 {"FDT_WS_NA": "1", "FDT_WS_NS": "2"},   # minimal rings, single MMA issuer
+                                 {"FDT_PDL": "1"}])           # programmatic dependent launch
+def test_kernel_variants_match_the_oracle(env):
+    """Every tuning switch selects code that must stay parity-green: raw heads of two models vs the fp64 oracle."""
+    import subprocess
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT % (str(ROOT), str(ROOT))], env=e, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0 and "variant ok" in r.stdout, (env, r.stdout[-500:], r.stderr[-1500:])
