@@ -1,4 +1,4 @@
-"""Condenses gpurun_out/raw_<tag>.csv (ncu --set full, one chunk of 256 frames = 23 launches) and
+"""Condenses gpurun_out/raw_<tag>.csv (ncu --set full, one chunk of frames = 23 launches) and
 gpurun_out/launches_<tag>.csv into tracked files under profiles/: a per-launch summary CSV and the
 per-launch DRAM traffic table bench.py quotes in its `roofline.traffic` field."""
 import csv, json, sys
@@ -25,8 +25,8 @@ for i, r in enumerate(data):
     rd = float(r[idx['dram__bytes_read.sum']].replace(',', '')) * scale[units[idx['dram__bytes_read.sum']]]
     wr = float(r[idx['dram__bytes_write.sum']].replace(',', '')) * scale[units[idx['dram__bytes_write.sum']]]
     traffic.append({'launch': i, 'kernel': r[idx['Kernel Name']].split('(')[0].replace('void fdt::<unnamed>::', '').replace('fdt::<unnamed>::', '').replace('void unnamed>::', '').replace('unnamed>::', ''),
-                    'dram_bytes_per_launch': rd + wr, 'images_per_launch': 256})
-json.dump({'source': 'ncu --set full --clock-control none, tools/prof_target.py (one chunk of 256 frames), capture %s' % tag,
+                    'dram_bytes_per_launch': rd + wr, 'images_per_launch': int(sys.argv[3]) if len(sys.argv) > 3 else 512})
+json.dump({'source': 'ncu --set full --clock-control none, tools/prof_target.py (one chunk of frames), capture %s' % tag,
            'launches': traffic}, open('profiles/%s_traffic.json' % out, 'w'), indent=1)
 import shutil
 shutil.copy('gpurun_out/launches_%s.csv' % tag, 'profiles/%s_launches.csv' % out)
