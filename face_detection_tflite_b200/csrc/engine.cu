@@ -117,7 +117,6 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         p.wB = blob + st.w; p.bias = blob + st.bias; p.alpha = st.alpha >= 0 ? blob + st.alpha : nullptr;
         p.act = st.act; p.Npad = st.Npad; p.K8 = st.K8; p.tmem_cols = st.tmem_cols; p.w_parts = st.w_parts;
         p.out_scale = (float)st.out_scale; p.smem_bytes = st.smem;
-        { static const int dbg = [] { const char* e = std::getenv("FDT_STEM_DBG"); return e ? std::atoi(e) : 0; }(); p.dbg = dbg; }
         if (!launch_stem_ws(p, B, ctx.cap, s)) { failed_ = true; fprintf(stderr, "fdt: cuTensorMapEncodeTiled failed for step '%s'\n", st.name.c_str()); }
         break;
       }

@@ -172,7 +172,6 @@ struct StemWsP {
   const float* bias; const float* alpha;
   int act, Npad, K8, tmem_cols, w_parts;
   float out_scale;
-  int dbg;                  // FDT_STEM_DBG bisect switches (0 in production)
   size_t smem_bytes;
 };
 bool launch_stem_ws(const StemWsP& p, int B, int cap, cudaStream_t s);

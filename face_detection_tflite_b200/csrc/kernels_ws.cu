@@ -851,7 +851,7 @@ __global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUte
                                 fmaf(__uint_as_float(u[6]), scale, b1.z), fmaf(__uint_as_float(u[7]), scale, b1.w));
         if (relu) { v0 = max4(v0, make_float4(0.f, 0.f, 0.f, 0.f)); v1 = max4(v1, make_float4(0.f, 0.f, 0.f, 0.f)); }
         else { v0 = leaky4(v0, a0); v1 = leaky4(v1, a1); }
-        if (valid && !(p.dbg & 4)) {
+        if (valid) {
           if (p.vec_store) {
             *reinterpret_cast<float4*>(orow + c0) = v0;
             if (c0 + 4 < p.CoutS) *reinterpret_cast<float4*>(orow + c0 + 4) = v1;
@@ -886,7 +886,7 @@ __global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUte
       mbar_wait(full_raw + 8u * si, (uint32_t)sph);
       // ---- convert: u8x4 BGRX -> {B,G,R,0} - 127.5 as halves; pixels outside the image (SAME padding) -> 0
       const uint32_t raw_a = sRaw_a + (uint32_t)si * RAW_STAGE, hp_a = sHp_a + (uint32_t)hb * HP_STRIDE;
-      for (int i = bt; i < ((p.dbg & 8) ? 0 : PH * PWP); i += 256) {
+      for (int i = bt; i < PH * PWP; i += 256) {
         const int ly = i / PWP, lx = i - ly * PWP;
         uint32_t raw;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw) : "r"(raw_a + 4u * (uint32_t)(ly * RAWW + lx + rx_off)));
@@ -906,7 +906,7 @@ __global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUte
       mbar_wait(a_empty + 8u * ai, (uint32_t)(aph ^ 1));
       // ---- im2col: CPK 16-byte chunks per (pixel, ky), copied verbatim
       const uint32_t dst = sA_a + (uint32_t)ai * A_BYTES + a_row;
-      if (!(p.dbg & 16)) {
+      {
         // all loads of this thread's tap rows first, then all stores (the asm statements keep their order)
         constexpr int NK0 = KY0 * CPK, NK1 = (KW - KY0) * CPK;
         uint4 v[NK0];
@@ -940,7 +940,7 @@ __global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUte
         const int iy0 = (trem / tilesX) * TH * 2 - p.pt, ix0 = (trem % tilesX) * TW * 2 - p.pl;
         mbar_wait(empty_raw + 8u * si, (uint32_t)(sph ^ 1));
         const uint32_t bar = full_raw + 8u * si;
-        if (p.dbg & 1) { mbar_arrive(bar); } else {
+        {
         mbar_expect_tx(bar, (uint32_t)(PH * RAWW * 4));
         const uint32_t dst = smem_u32(sRaw) + (uint32_t)si * RAW_STAGE;
         asm volatile(
@@ -967,7 +967,7 @@ __global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUte
         const uint32_t dcol = tmem_base + (uint32_t)(di * p.Npad);
         const uint32_t a_lo0 = a_desc0 + (uint32_t)ai * (A_BYTES >> 4);
         uint32_t acc = 0u;
-        if (!(p.dbg & 2)) {
+        {
 #pragma unroll
           for (int ks = 0; ks < K8 / 16; ++ks) {
             mma_ss<1>(dcol, a_lo0 + 16u * ks, hi, w_desc0 + 16u * ks, hi, idesc, acc);
