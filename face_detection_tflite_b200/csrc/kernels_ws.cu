@@ -749,19 +749,27 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
 // patch keeps 4 halves {B,G,R,0} per pixel, so the KW taps of one kernel row are SEGP consecutive pixels = CPK
 // 16-byte chunks that are copied verbatim (LDS.128 -> STS.128) into the UMMA K-major core-matrix layout.
 //
-//   warp 16 (1 lane) producer: TMA of the raw u8x4 patch [PH][40] (zero fill outside the image) into a 4-stage ring
-//   warps 8..15     builders : raw -> fp16 patch (PRMT + 2 HSUB2 per pixel pair, 0 outside the image), then im2col
-//   warp 17 (1 lane) MMA     : K8/16 x w_parts tcgen05.mma into one of two TMEM accumulators
-//   warps 0..7      epilogue : two groups of four warps alternate tiles: D * out_scale + bias, ReLU/PReLU, float4 stores
+//   warp 12 (1 lane) producer: TMA of the raw u8x4 patch [PH][40] (zero fill outside the image) into a 6-stage ring
+//   warps 4..11     builders : raw -> fp16 patch (PRMT + 2 HSUB2 per pixel pair, 0 outside the image), then im2col
+//   warp 13 (1 lane) MMA     : K8/16 x w_parts tcgen05.mma into one of four TMEM accumulators
+//   warps 0..3      epilogue : D * out_scale + bias, ReLU/PReLU, float4 stores
+// Two such CTAs share an SM (registers are allocated per four warps: 14 warps x 56 registers fit twice, 18 would not).
+// Warps: 4*kStemEG epilogue, 8 builders, 1 producer, 1 MMA.  Registers are allocated per 4 warps, so 14 warps x 56 registers
+// let two CTAs share an SM (16 builder + 8 epilogue warps per SM); 18 warps would not.
+constexpr int kStemEG = 1;                       // epilogue groups of four warps (alternate tiles when 2)
+constexpr int kStemThreads = (4 * kStemEG + 10) * 32;
 template <int KW>
-__global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUtensorMap tmap, StemWsP p, int B, int ntiles) {
+__global__ void __launch_bounds__(kStemThreads, 2) k_stem_ws(const __grid_constant__ CUtensorMap tmap, StemWsP p, int B, int ntiles) {
   constexpr int TH = 8, TW = 16, PWP = 36;
   constexpr int PH = (TH - 1) * 2 + KW;
   constexpr int SEGP = KW == 5 ? 6 : 4, CPK = SEGP / 2;
   constexpr int NCH = (KW * CPK + 1) / 2 * 2;          // 16-byte K chunks per row (even)
   constexpr int K8 = NCH * 8;                          // halves
   constexpr uint32_t SBO = (uint32_t)NCH * 128u;
-  constexpr int NS = 6, NA = 4, NT = 4;
+#ifndef FDT_STEM_NA
+#define FDT_STEM_NA 2
+#endif
+  constexpr int NS = 6, NA = FDT_STEM_NA, NT = 4;   // NA = 2 keeps the CTA under 113 KB: two CTAs (36 warps) per SM
   constexpr int RAWW = 40;                             // raw patch row: the TMA box must start 16-byte aligned in x, so it
                                                        // begins up to 3 pixels left of the patch (offset rx_off) and is 40 wide
   constexpr uint32_t RAW_STAGE = (PH * RAWW * 4 + 127) / 128 * 128;
@@ -785,12 +793,12 @@ __global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUte
 
   // ---- prologue ----
   const uint32_t sW_u32 = smem_u32(sW);
-  for (int i = tid; i < (int)(w_bytes >> 4); i += 576) cp_async16_u32(sW_u32 + 16u * i, reinterpret_cast<const uint8_t*>(p.wB) + 16 * (size_t)i);
-  for (int i = tid; i < p.Npad; i += 576) {
+  for (int i = tid; i < (int)(w_bytes >> 4); i += kStemThreads) cp_async16_u32(sW_u32 + 16u * i, reinterpret_cast<const uint8_t*>(p.wB) + 16 * (size_t)i);
+  for (int i = tid; i < p.Npad; i += kStemThreads) {
     sBias[i] = p.bias[i];
     sAlpha[i] = p.act == kActPrelu ? p.alpha[i] : (p.act == kActRelu ? 0.f : 1.f);
   }
-  for (int i = tid; i < (int)(NA * A_BYTES / 16); i += 576) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);   // pad chunks stay zero
+  for (int i = tid; i < (int)(NA * A_BYTES / 16); i += kStemThreads) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);   // pad chunks stay zero
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(full_raw + 8u * i, 1); mbar_init(empty_raw + 8u * i, 8); }
     for (int i = 0; i < NA; ++i) { mbar_init(a_full + 8u * i, 8); mbar_init(a_empty + 8u * i, 1); }
@@ -798,7 +806,8 @@ __global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUte
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
   }
-  if (warp == 17) {
+  constexpr int kW0 = 4 * kStemEG;                  // first builder warp
+  if (warp == kW0 + 9) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)p.tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
@@ -815,8 +824,8 @@ __global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUte
   const int tiles_per_img = tilesX * tilesY;
   const int rx_off = (4 - (p.pl & 3)) & 3;             // ix0 = 32*txi - pl  ->  aligned start ix0 - rx_off
 
-  if (warp < 8) {
-    // =============================== epilogue: group g takes every second tile of this CTA =============
+  if (warp < kW0) {
+    // =============================== epilogue: group g takes every kStemEG-th tile of this CTA ==========
     const int g = warp >> 2, quarter = warp & 3;
     const int slot = quarter * 32 + lane;
     const int e_ty = slot >> 4, e_tx = slot & 15;
@@ -824,14 +833,14 @@ __global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUte
     const float scale = p.out_scale;
     const bool relu = p.act == kActRelu;
     int k = 0;
-    for (int tile = blockIdx.x + g * gridDim.x; tile < ntiles; tile += 2 * gridDim.x, ++k) {
+    for (int tile = blockIdx.x + g * gridDim.x; tile < ntiles; tile += kStemEG * gridDim.x, ++k) {
       const int b = tile / tiles_per_img;
       const int trem = tile - b * tiles_per_img;
       const int ty0 = (trem / tilesX) * TH, tx0 = (trem % tilesX) * TW;
       const int oy = ty0 + e_ty, ox = tx0 + e_tx;
       const bool valid = oy < p.OH && ox < p.OW;
       float* orow = p.out + (size_t)b * p.out_istride + ((size_t)(valid ? oy : 0) * p.OW + (valid ? ox : 0)) * p.CoutS;
-      const int kl = 2 * k + g, di = kl & (NT - 1);        // CTA-local tile index -> accumulator buffer
+      const int kl = kStemEG * k + g, di = kl & (NT - 1);  // CTA-local tile index -> accumulator buffer
       mbar_wait(d_full + 8u * di, (uint32_t)((kl / NT) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tcol0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(di * p.Npad);
@@ -867,9 +876,9 @@ __global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUte
       __syncwarp();
       if (lane == 0) mbar_arrive_relaxed(d_empty + 8u * di);
     }
-  } else if (warp < 16) {
+  } else if (warp < kW0 + 8) {
     // =============================== builders: raw patch -> fp16 patch -> im2col A =======================
-    const int bt = tid - 256;
+    const int bt = tid - kW0 * 32;
     const int r = bt & 127, part = bt >> 7;
     const int r_ty = r >> 4, r_tx = r & 15;
     const uint32_t a_row = ((uint32_t)r >> 3) * SBO + ((uint32_t)r & 7u) * 16u;
@@ -930,7 +939,7 @@ __global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUte
       if (++si == NS) { si = 0; sph ^= 1; }
       if (++ai == NA) { ai = 0; aph ^= 1; }
     }
-  } else if (warp == 16) {
+  } else if (warp == kW0 + 8) {
     // =============================== TMA producer ===================================================
     if (lane == 0) {
       int si = 0, sph = 0;
@@ -985,7 +994,7 @@ __global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUte
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 17) {
+  if (warp == kW0 + 9) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols));
   }
@@ -1155,7 +1164,13 @@ void launch_stem_ws_kw(const CUtensorMap& tm, const StemWsP& p, int B, cudaStrea
     auto it = occ.find(key);
     if (it == occ.end()) {
       int nb = 1;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_stem_ws<KW>, 576, p.smem_bytes) != cudaSuccess || nb < 1) nb = 1;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_stem_ws<KW>, kStemThreads, p.smem_bytes) != cudaSuccess || nb < 1) nb = 1;
+      if (std::getenv("FDT_DEBUG_OCC")) {
+        cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, k_stem_ws<KW>);
+        cudaDeviceProp dp; cudaGetDeviceProperties(&dp, dev);
+        fprintf(stderr, "k_stem_ws<%d>: smem %zu -> %d CTAs/SM (regs %d, static smem %zu, maxDyn %d, carveout %d; SM: regs %d, smem %zu, reserved %zu)\n", KW, p.smem_bytes, nb,
+                fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.preferredShmemCarveout, dp.regsPerMultiprocessor, dp.sharedMemPerMultiprocessor, dp.reservedSharedMemPerBlock);
+      }
       it = occ.emplace(key, nb).first;
     }
     per_sm = it->second;
@@ -1163,7 +1178,7 @@ void launch_stem_ws_kw(const CUtensorMap& tm, const StemWsP& p, int B, cudaStrea
   const int ntiles = ((p.OW + 15) / 16) * ((p.OH + 7) / 8) * B;
   int grid = std::min(ntiles, 148 * per_sm);
   if (grid < 1) grid = 1;
-  launch_pdl(k_stem_ws<KW>, grid, 576, p.smem_bytes, s, tm, p, B, ntiles);
+  launch_pdl(k_stem_ws<KW>, grid, kStemThreads, p.smem_bytes, s, tm, p, B, ntiles);
 }
 
 }  // namespace

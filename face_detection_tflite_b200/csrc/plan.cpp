@@ -688,7 +688,7 @@ struct Builder {
       std::vector<float> wb((hb.size() + 1) / 2, 0.f);
       std::memcpy(wb.data(), hb.data(), hb.size() * 2);
       const int PH = 14 + st.kw;
-      st.ns = 6; st.na = 4;
+      st.ns = 6; st.na = 2;   // must match FDT_STEM_NA in kernels_ws.cu
       st.smem = (size_t)parts * st.Npad * st.K8 * 2 + 2 * (size_t)st.Npad * 4 + 32 * 8 + 128     // W, bias, alpha, barriers
                 + (size_t)st.na * 128 * st.K8 * 2 + 2 * (size_t)PH * 36 * 8 + (size_t)st.ns * ((PH * 160 + 127) / 128 * 128) + 256;
       st.w = push(wb, wb.size());
