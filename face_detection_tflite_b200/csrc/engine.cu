@@ -89,7 +89,7 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         p.in8 = in_u8; p.H = it.H; p.W = it.W; p.OH = out.H; p.OW = out.W;
         p.kw = st.kw; p.pt = st.pt; p.pl = st.pl; p.K = st.K; p.KP = st.KP;
         p.out = out.p; p.out_istride = out.istride; p.Cout = st.Cout; p.CoutS = out.Cs;
-        p.vec_store = (out.Cs % 4 == 0 && out.istride % 4 == 0 && ((size_t)out.p % 16 == 0)) ? 1 : 0;
+        p.vec_store = (out.Cs % 4 == 0 && out.istride % 4 == 0 && ((size_t)out.p % 16 == 0)) ? ((out.Cs % 8 == 0 && out.istride % 8 == 0 && ((size_t)out.p % 32 == 0)) ? 2 : 1) : 0;   // 2: 32-byte stores allowed
         p.w = blob + st.w; p.bias = blob + st.bias; p.alpha = st.alpha >= 0 ? blob + st.alpha : nullptr;
         p.act = st.act; p.CoutP = st.CoutP; p.NC = st.NC; p.smem_bytes = st.smem;
         launch_stem(p, B, s, cta_cap(st.smem, 32 * (st.NC / 4)));
@@ -101,7 +101,7 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         p.in8 = in_u8; p.H = it.H; p.W = it.W; p.OH = out.H; p.OW = out.W;
         p.kw = st.kw; p.pt = st.pt; p.pl = st.pl;
         p.out = out.p; p.out_istride = out.istride; p.Cout = st.Cout; p.CoutS = out.Cs;
-        p.vec_store = (out.Cs % 4 == 0 && out.istride % 4 == 0 && ((size_t)out.p % 16 == 0)) ? 1 : 0;
+        p.vec_store = (out.Cs % 4 == 0 && out.istride % 4 == 0 && ((size_t)out.p % 16 == 0)) ? ((out.Cs % 8 == 0 && out.istride % 8 == 0 && ((size_t)out.p % 32 == 0)) ? 2 : 1) : 0;   // 2: 32-byte stores allowed
         p.wB = blob + st.w; p.bias = blob + st.bias; p.alpha = st.alpha >= 0 ? blob + st.alpha : nullptr;
         p.act = st.act; p.Npad = st.Npad; p.tmem_cols = st.tmem_cols; p.w_parts = st.w_parts; p.smem_bytes = st.smem;
         launch_stem_tc(p, B, s);
@@ -113,7 +113,7 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         p.in8 = in_u8; p.H = it.H; p.W = it.W; p.OH = out.H; p.OW = out.W;
         p.kw = st.kw; p.pt = st.pt; p.pl = st.pl;
         p.out = out.p; p.out_istride = out.istride; p.Cout = st.Cout; p.CoutS = out.Cs;
-        p.vec_store = (out.Cs % 4 == 0 && out.istride % 4 == 0 && ((size_t)out.p % 16 == 0)) ? 1 : 0;
+        p.vec_store = (out.Cs % 4 == 0 && out.istride % 4 == 0 && ((size_t)out.p % 16 == 0)) ? ((out.Cs % 8 == 0 && out.istride % 8 == 0 && ((size_t)out.p % 32 == 0)) ? 2 : 1) : 0;   // 2: 32-byte stores allowed
         p.wB = blob + st.w; p.bias = blob + st.bias; p.alpha = st.alpha >= 0 ? blob + st.alpha : nullptr;
         p.act = st.act; p.Npad = st.Npad; p.K8 = st.K8; p.tmem_cols = st.tmem_cols; p.w_parts = st.w_parts;
         p.out_scale = (float)st.out_scale; p.smem_bytes = st.smem;
@@ -135,7 +135,7 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         p.OH = out.H; p.OW = out.W;
         p.K = st.K; p.KP = st.KP; p.KS = st.KS;
         p.out = out.p; p.out_istride = out.istride; p.Cout = st.Cout; p.CoutS = out.Cs;
-        p.vec_store = (out.Cs % 4 == 0 && out.istride % 4 == 0 && ((size_t)out.p % 16 == 0)) ? 1 : 0;
+        p.vec_store = (out.Cs % 4 == 0 && out.istride % 4 == 0 && ((size_t)out.p % 16 == 0)) ? ((out.Cs % 8 == 0 && out.istride % 8 == 0 && ((size_t)out.p % 32 == 0)) ? 2 : 1) : 0;   // 2: 32-byte stores allowed
         p.w = blob + st.w; p.bias = blob + st.bias; p.alpha = st.alpha >= 0 ? blob + st.alpha : nullptr;
         p.act = st.act; p.CoutP = st.CoutP; p.NC = st.NC; p.nchunks = st.nchunks;
         p.NPG = st.NPG; p.TM = st.TM; p.smem_bytes = st.smem;
@@ -155,7 +155,7 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         p.dww = st.dww >= 0 ? blob + st.dww : nullptr; p.dwb = st.dwb >= 0 ? blob + st.dwb : nullptr;
         p.KP = st.KP; p.KS = st.KS;
         p.out = out.p; p.out_istride = out.istride; p.Cout = st.Cout; p.CoutS = out.Cs;
-        p.vec_store = (out.Cs % 4 == 0 && out.istride % 4 == 0 && ((size_t)out.p % 16 == 0)) ? 1 : 0;
+        p.vec_store = (out.Cs % 4 == 0 && out.istride % 4 == 0 && ((size_t)out.p % 16 == 0)) ? ((out.Cs % 8 == 0 && out.istride % 8 == 0 && ((size_t)out.p % 32 == 0)) ? 2 : 1) : 0;   // 2: 32-byte stores allowed
         p.w = blob + st.w; p.bias = blob + st.bias; p.alpha = st.alpha >= 0 ? blob + st.alpha : nullptr;
         p.act = st.act; p.CoutP = st.CoutP; p.NC = st.NC; p.nchunks = st.nchunks;
         p.NPG = st.NPG; p.TM = st.TM;
@@ -184,7 +184,7 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         p.dww = st.dww >= 0 ? blob + st.dww : nullptr; p.dwb = st.dwb >= 0 ? blob + st.dwb : nullptr;
         p.K8 = st.K8; p.KS = st.KS;
         p.out = out.p; p.out_istride = out.istride; p.Cout = st.Cout; p.CoutS = out.Cs;
-        p.vec_store = (out.Cs % 4 == 0 && out.istride % 4 == 0 && ((size_t)out.p % 16 == 0)) ? 1 : 0;
+        p.vec_store = (out.Cs % 4 == 0 && out.istride % 4 == 0 && ((size_t)out.p % 16 == 0)) ? ((out.Cs % 8 == 0 && out.istride % 8 == 0 && ((size_t)out.p % 32 == 0)) ? 2 : 1) : 0;   // 2: 32-byte stores allowed
         p.wB = blob + st.w; p.bias = blob + st.bias; p.alpha = st.alpha >= 0 ? blob + st.alpha : nullptr;
         p.act = st.act; p.Npad = st.Npad; p.tmem_cols = st.tmem_cols; p.a_rows = st.a_rows; p.RS = st.RS; p.w_parts = st.w_parts; p.nbuf = st.nbuf;
         p.res_mode = st.in2 >= 0 ? st.res_mode : 0;

@@ -207,6 +207,11 @@ __device__ __forceinline__ void dw_item(uint32_t base, uint32_t row_b, uint32_t 
 // ---- fast epilogue (float4 stores, residual none / staged / staged + 2x2 max-pool, staged pixel stride KS >= CoutS) ----
 // Straight-line per 8-column group: TMEM load, bias and residual LDS issued before tcgen05.wait::ld, add, activation,
 // two float4 stores.  Channels >= Cout inside CoutS come out as exact zeros (zero weights, bias and TMA zero fill).
+// 256-bit store (sm_100 STG.256): halves the number of store instructions, each of which costs the LSU one slot per
+// 128-byte line it touches (24-32 lines at a CoutS-float pixel stride)
+__device__ __forceinline__ void stg8(float* p, const float4& a, const float4& b) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 // RES 3 / 4: residual from another HBM tensor (same size / 2x2 max-pooled), float4 loads; `gres` points at this thread's
@@ -215,7 +220,7 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 template <int RES, int LEAKY, int SM>
 __device__ __forceinline__ void epi_fast(uint32_t tcol0, uint32_t res_a, uint32_t bias_a, uint32_t alpha_a, float* orow, uint32_t out_s,
                                          bool valid, bool store_ok, int cout_s, uint32_t ks_b, uint32_t row_b,
-                                         const float* gres = nullptr, int gks = 0, int grow = 0, int gres_c = 0) {
+                                         const float* gres = nullptr, int gks = 0, int grow = 0, int gres_c = 0, bool wide = false) {
   // 16 columns per TMEM round trip (8 for the pooled residuals, whose four taps per quad need the registers); the
   // accumulator is Npad = 16k columns wide, quads >= cout_s are computed on whatever lies there and dropped at the store
 #ifdef FDT_EPI_X8
@@ -255,6 +260,7 @@ __device__ __forceinline__ void epi_fast(uint32_t tcol0, uint32_t res_a, uint32_
       }
     }
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    float4 vq[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
       float4 v = make_float4(__uint_as_float(u[4 * q]) + bv[q].x, __uint_as_float(u[4 * q + 1]) + bv[q].y,
@@ -262,10 +268,20 @@ __device__ __forceinline__ void epi_fast(uint32_t tcol0, uint32_t res_a, uint32_
       if (RES) add4(v, rv[q]);
       if (LEAKY) v = leaky4(v, lds4(alpha_a + cb + 16u * q));
       else v = max4(v, make_float4(0.f, 0.f, 0.f, 0.f));
-      if (store_ok && c0 + 4 * q < cout_s) {
-        if (SM) asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(out_s + 4u * (uint32_t)(c0 + 4 * q)), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-        else *reinterpret_cast<float4*>(orow + c0 + 4 * q) = v;
-      }
+      vq[q] = v;
+    }
+    if (!SM && wide) {
+      // CoutS % 8 == 0 and a 32-byte aligned pixel record: one 256-bit store per pair of quads
+#pragma unroll
+      for (int q = 0; q < NQ; q += 2)
+        if (store_ok && c0 + 4 * q < cout_s) stg8(orow + c0 + 4 * q, vq[q], vq[q + 1]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q)
+        if (store_ok && c0 + 4 * q < cout_s) {
+          if (SM) asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(out_s + 4u * (uint32_t)(c0 + 4 * q)), "f"(vq[q].x), "f"(vq[q].y), "f"(vq[q].z), "f"(vq[q].w) : "memory");
+          else *reinterpret_cast<float4*>(orow + c0 + 4 * q) = vq[q];
+        }
     }
   }
 }
@@ -396,6 +412,7 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
   const bool fast = p.vec_store && (res_kind == 3 ? gfast : (res_kind == 0 || p.KS >= p.CoutS));
   const int gmul = p.res_pool ? 2 : 1, gks = p.res_Cs, grow = p.res_W * p.res_Cs;
   const bool tma_out = fast && p.no > 0;
+  const bool wide = p.vec_store == 2;
   const uint32_t sOut_a = smem_u32(sIn0 + (size_t)NS * in_stage_floats), out_stage_b = (uint32_t)p.out_stage_floats * 4u, kso_b = (uint32_t)p.KSo * 4u;
   const uint32_t out_full = bar0 + 8u * 28, out_empty = bar0 + 8u * 30;
 
@@ -526,20 +543,20 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
           const uint32_t out_s = 0u;
           if (res_kind == 3) {
             if (p.act == kActRelu) {
-              if (p.res_pool) epi_fast<4, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C);
-              else epi_fast<3, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C);
+              if (p.res_pool) epi_fast<4, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C, wide);
+              else epi_fast<3, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C, wide);
             } else {
-              if (p.res_pool) epi_fast<4, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C);
-              else epi_fast<3, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C);
+              if (p.res_pool) epi_fast<4, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C, wide);
+              else epi_fast<3, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C, wide);
             }
           } else if (p.act == kActRelu) {
-            if (res_kind == 1) epi_fast<1, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b);
-            else if (res_kind == 2) epi_fast<2, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b);
-            else epi_fast<0, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b);
+            if (res_kind == 1) epi_fast<1, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, nullptr, 0, 0, 0, wide);
+            else if (res_kind == 2) epi_fast<2, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, nullptr, 0, 0, 0, wide);
+            else epi_fast<0, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, nullptr, 0, 0, 0, wide);
           } else {
-            if (res_kind == 1) epi_fast<1, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b);
-            else if (res_kind == 2) epi_fast<2, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b);
-            else epi_fast<0, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b);
+            if (res_kind == 1) epi_fast<1, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, nullptr, 0, 0, 0, wide);
+            else if (res_kind == 2) epi_fast<2, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, nullptr, 0, 0, 0, wide);
+            else epi_fast<0, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, nullptr, 0, 0, 0, wide);
           }
         }
       } else {
@@ -861,7 +878,9 @@ __global__ void __launch_bounds__(kStemThreads, 2) k_stem_ws(const __grid_consta
         if (relu) { v0 = max4(v0, make_float4(0.f, 0.f, 0.f, 0.f)); v1 = max4(v1, make_float4(0.f, 0.f, 0.f, 0.f)); }
         else { v0 = leaky4(v0, a0); v1 = leaky4(v1, a1); }
         if (valid) {
-          if (p.vec_store) {
+          if (p.vec_store == 2) {
+            stg8(orow + c0, v0, v1);                 // CoutS % 8 == 0: one 256-bit store per 8 channels
+          } else if (p.vec_store) {
             *reinterpret_cast<float4*>(orow + c0) = v0;
             if (c0 + 4 < p.CoutS) *reinterpret_cast<float4*>(orow + c0 + 4) = v1;
           } else {

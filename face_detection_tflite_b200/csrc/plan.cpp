@@ -900,7 +900,7 @@ struct Builder {
     std::sort(order.begin(), order.end(), [&](int a, int b) { return P.tensors[a].def_step < P.tensors[b].def_step; });
     for (int t : order) {
       PTensor& x = P.tensors[t];
-      long long need = (x.istride + 3) / 4 * 4;
+      long long need = (x.istride + 7) / 8 * 8;      // 32-byte granules: the epilogues may use 256-bit stores
       bool placed = false;
       if (fuse == 1) {
         for (Block& b : blocks) {
