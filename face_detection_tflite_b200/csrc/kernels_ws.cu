@@ -775,8 +775,9 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
 // let two CTAs share an SM (16 builder + 8 epilogue warps per SM); 18 warps would not.
 constexpr int kStemEG = 1;                       // epilogue groups of four warps (alternate tiles when 2)
 constexpr int kStemThreads = (4 * kStemEG + 10) * 32;
+// (launch bound declared for 576 threads so that ptxas caps the kernel at 56 registers: 2 x 16 allocated warps x 56 fit the SM)
 template <int KW>
-__global__ void __launch_bounds__(kStemThreads, 2) k_stem_ws(const __grid_constant__ CUtensorMap tmap, StemWsP p, int B, int ntiles) {
+__global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUtensorMap tmap, StemWsP p, int B, int ntiles) {
   constexpr int TH = 8, TW = 16, PWP = 36;
   constexpr int PH = (TH - 1) * 2 + KW;
   constexpr int SEGP = KW == 5 ? 6 : 4, CPK = SEGP / 2;
@@ -1182,18 +1183,18 @@ void launch_stem_ws_kw(const CUtensorMap& tm, const StemWsP& p, int B, cudaStrea
     auto key = std::make_pair(dev, p.smem_bytes);
     auto it = occ.find(key);
     if (it == occ.end()) {
-      int nb = 1;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_stem_ws<KW>, kStemThreads, p.smem_bytes) != cudaSuccess || nb < 1) nb = 1;
-      if (std::getenv("FDT_DEBUG_OCC")) {
-        cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, k_stem_ws<KW>);
-        cudaDeviceProp dp; cudaGetDeviceProperties(&dp, dev);
-        fprintf(stderr, "k_stem_ws<%d>: smem %zu -> %d CTAs/SM (regs %d, static smem %zu, maxDyn %d, carveout %d; SM: regs %d, smem %zu, reserved %zu)\n", KW, p.smem_bytes, nb,
-                fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.preferredShmemCarveout, dp.regsPerMultiprocessor, dp.sharedMemPerMultiprocessor, dp.reservedSharedMemPerBlock);
-      }
+      // Resident CTAs per SM from the resources themselves (the occupancy API answers 1 for this kernel, yet two CTAs
+      // do run concurrently: 101 vs 124 us measured): shared memory, registers (allocated per 4 warps), TMEM columns.
+      const int by_smem = (int)((227u * 1024u) / (p.smem_bytes + 1024u));
+      const int by_regs = 65536 / (((kStemThreads / 32 + 3) / 4 * 4) * 32 * 56);
+      const int by_tmem = 512 / std::max(32, p.tmem_cols);
+      int nb = std::max(1, std::min(std::min(by_smem, by_regs), by_tmem));
       it = occ.emplace(key, nb).first;
     }
     per_sm = it->second;
   }
+  static const int force_per_sm = [] { const char* e = std::getenv("FDT_STEM_PERSM"); return e ? std::atoi(e) : 0; }();
+  if (force_per_sm > 0) per_sm = force_per_sm;
   const int ntiles = ((p.OW + 15) / 16) * ((p.OH + 7) / 8) * B;
   int grid = std::min(ntiles, 148 * per_sm);
   if (grid < 1) grid = 1;
