@@ -416,15 +416,44 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
   const uint32_t sOut_a = smem_u32(sIn0 + (size_t)NS * in_stage_floats), out_stage_b = (uint32_t)p.out_stage_floats * 4u, kso_b = (uint32_t)p.KSo * 4u;
   const uint32_t out_full = bar0 + 8u * 28, out_empty = bar0 + 8u * 30;
 
-  // ---- prologue (all threads): weights, bias, tables, barriers, TMEM -------------------------------
+  // ---- prologue ---------------------------------------------------------------------------------------
+  // The producer lane arms the input ring and fires the CTA's first loads before anything else, so their latency
+  // overlaps the weight / table set-up of the other threads.
+  int early = 0;                                  // tiles already requested (producer lane only)
+  if (warp == kEpiWarps + ND && lane == 0) {
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(full_in + 8u * i, 1);
+      mbar_init(empty_in + 8u * i, ND + (epi_reads_stage ? kEpiWarps : 0));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    if (p.no > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_out) : "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");          // (PDL) the input is the previous kernel's output
+    const uint32_t stage_bytes = (uint32_t)(p.G * p.IH * p.IW * p.KS) * 4u;
+    for (int tile = blockIdx.x; tile < ntiles && early < NS; tile += gridDim.x, ++early) {
+      int grp, trem, tyi, txi;
+      p.fd_tpg.divmod(tile, grp, trem);
+      p.fd_tilesX.divmod(trem, tyi, txi);
+      const uint32_t bar = full_in + 8u * early;
+      mbar_expect_tx(bar, stage_bytes);
+      asm volatile(
+          "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+          ::"r"(smem_u32(sIn0 + (size_t)early * in_stage_floats)), "l"(&tmap), "r"(0), "r"(txi * p.TW * p.s - p.dpl),
+            "r"(tyi * p.TH * p.s - p.dpt), "r"(grp * p.G), "r"(bar) : "memory");
+    }
+  }
+  // all threads: weights, bias, slopes, depthwise taps (cp.async), depthwise table
   const uint32_t sB_u32 = smem_u32(sB);
   for (int i = tid; i < p.w_parts * p.Npad * Q8; i += kThreads) cp_async16_u32(sB_u32 + 16u * i, p.wB + 4 * (size_t)i);
-  for (int i = tid; i < p.Npad; i += kThreads) {
-    sBias[i] = p.bias[i];
-    sAlpha[i] = p.act == kActPrelu ? p.alpha[i] : (p.act == kActRelu ? 0.f : 1.f);
+  for (int i = tid; i < (p.Npad >> 2); i += kThreads) cp_async16_u32(smem_u32(sBias) + 16u * i, p.bias + 4 * (size_t)i);
+  if (p.act == kActPrelu) {
+    for (int i = tid; i < (p.Npad >> 2); i += kThreads) cp_async16_u32(smem_u32(sAlpha) + 16u * i, p.alpha + 4 * (size_t)i);
+  } else {
+    for (int i = tid; i < p.Npad; i += kThreads) sAlpha[i] = p.act == kActRelu ? 0.f : 1.f;
   }
   if (S) {
-    for (int i = tid; i < 10 * p.K8; i += kThreads) sDw[i] = i < 9 * p.K8 ? p.dww[i] : p.dwb[i - 9 * p.K8];
+    for (int i = tid; i < 9 * Q8; i += kThreads) cp_async16_u32(smem_u32(sDw) + 16u * i, p.dww + 4 * (size_t)i);
+    for (int i = tid; i < Q8; i += kThreads) cp_async16_u32(smem_u32(sDw + 9 * p.K8) + 16u * i, p.dwb + 4 * (size_t)i);
     // depthwise table: item = (((g*Q8 + qq)*nstrips + st)*TW + tx)  (tx fastest => conflict-free LDS)
     for (int it = tid; it < p.n_items; it += kThreads) {
       int tx, r, st, r2, qq, g;
@@ -438,10 +467,6 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
     }
   }
   if (tid == 0) {
-    for (int i = 0; i < NS; ++i) {
-      mbar_init(full_in + 8u * i, 1);
-      mbar_init(empty_in + 8u * i, ND + (epi_reads_stage ? kEpiWarps : 0));
-    }
     for (int i = 0; i < NA; ++i) {
       mbar_init(a_full + 8u * i, ND);
       mbar_init(a_empty + 8u * i, 1);
@@ -455,8 +480,6 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
       mbar_init(out_empty + 8u * i, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-    if (p.no > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_out) : "memory");
   }
   if (warp == kEpiWarps + ND + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)p.tmem_cols));
@@ -642,10 +665,10 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
     // =============================== TMA producer ===================================================
     if (lane == 0) {
       const uint32_t stage_bytes = (uint32_t)(p.G * p.IH * p.IW * p.KS) * 4u;
-      int si = 0, sph = 0;
+      int si = early == NS ? 0 : early, sph = early == NS ? 1 : 0;     // the first `early` tiles were requested in the prologue
       long long* tr = (p.trace && blockIdx.x == 0) ? p.trace : nullptr;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      int it = early;
+      for (int tile = blockIdx.x + early * gridDim.x; tile < ntiles; tile += gridDim.x, ++it) {
         int grp, trem, tyi, txi;
         p.fd_tpg.divmod(tile, grp, trem);
         p.fd_tilesX.divmod(trem, tyi, txi);
