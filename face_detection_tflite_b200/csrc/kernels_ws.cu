@@ -371,8 +371,8 @@ __device__ __forceinline__ void epi_tile(const DwPwTcP& p, uint32_t tcol0, uint3
 #endif
 
 // Shared-memory carve-up (must match plan_ws in plan.cpp):
-//   [W (w_parts x Npad x K8)] [bias Npad] [alpha Npad] [dw taps+bias 10 x K8] [dtab n_items x 8 B] [barriers 128 B]
-//   | 128-byte aligned: [A ring: NA x (hi, lo) x 128 x K8] [input ring: NS x in_stage_bytes]
+//   [W (w_parts x Npad x K8)] [bias Npad] [alpha Npad] [dw taps+bias 10 x K8] [dtab n_items x 4 B] [barriers 256 B]
+//   | 128-byte aligned: [A ring: NA x (hi, lo) x a_rows x K8] [input ring: NS x in_stage_bytes] [output tiles]
 // S: depthwise stride (0 = no depthwise, pointwise only); RS: output rows per depthwise work item.
 template <int ND, int S, int RS>
 __global__ void __launch_bounds__((ND + kEpiWarps + 2 + kMmaWarps) * 32, 1)
@@ -390,9 +390,11 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
   float* sBias = sB + (size_t)p.w_parts * p.Npad * p.K8;
   float* sAlpha = sBias + p.Npad;
   float* sDw = sAlpha + p.Npad;
-  uint2* dtab = reinterpret_cast<uint2*>(sDw + (S ? 10 * p.K8 : 0));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(dtab + p.n_items);
-  const uint32_t a_stage_floats = 2u * 128u * (uint32_t)p.K8;
+  uint32_t* dtab = reinterpret_cast<uint32_t*>(sDw + (S ? 10 * p.K8 : 0));   // [n_items]: in_off/16 | slot0 << 14 | qq << 22
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dtab + ((p.n_items + 1) & ~1));
+  // operand buffer: hi + lo parts of a_rows (<= 128) rows; the MMA always reads 128 rows, the surplus rows come from
+  // whatever follows in shared memory (finite or not, they only feed accumulator rows that are never stored)
+  const uint32_t a_part_floats = (uint32_t)p.a_rows * (uint32_t)p.K8, a_stage_floats = 2u * a_part_floats;
   float* sA = reinterpret_cast<float*>(((uintptr_t)(bars + 32) + 127) & ~(uintptr_t)127);
   float* sIn0 = sA + (size_t)NA * a_stage_floats;
   const uint32_t in_stage_floats = (uint32_t)p.in_floats;     // multiple of 32 floats (128 B)
@@ -463,7 +465,7 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
       const int tyb = st * RS;
       uint32_t in_off = (uint32_t)(((g * p.IH + tyb * S) * p.IW + tx * S) * p.KS + 4 * qq);
       uint32_t slot0 = (uint32_t)(g * thw + tyb * p.TW + tx);
-      dtab[it] = make_uint2(in_off * 4u, slot0 | ((uint32_t)qq << 8));
+      dtab[it] = (in_off >> 2) | (slot0 << 14) | ((uint32_t)qq << 22);
     }
   }
   if (tid == 0) {
@@ -606,13 +608,13 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
     // one work item per thread: its taps stay in registers for the whole kernel
     const bool hoist = S != 0 && p.n_items <= kDwThreads;
     const bool mine = hoist && dtid < p.n_items;
-    uint2 e0 = make_uint2(0u, 0u);
+    uint32_t e0 = 0u;
     float4 w0[9], bias0 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int t = 0; t < 9; ++t) w0[t] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (S != 0 && mine) {
       e0 = dtab[dtid];
-      const uint32_t wq = sDw_a + 16u * (e0.y >> 8);
+      const uint32_t wq = sDw_a + 16u * (e0 >> 22);
 #pragma unroll
       for (int t = 0; t < 9; ++t) w0[t] = lds4(wq + (uint32_t)(t * p.K8) * 4u);
       bias0 = lds4(wq + (uint32_t)(9 * p.K8) * 4u);
@@ -624,22 +626,22 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
       WS_TRACE(1, it, 0);
       const uint32_t sIn_a = sIn0_a + (uint32_t)si * in_stage_floats * 4u;
       float* sAhi = sA + (size_t)ai * a_stage_floats;
-      float* sAlo = sAhi + 128 * p.K8;
+      float* sAlo = sAhi + a_part_floats;
       mbar_wait(full_in + 8u * si, (uint32_t)sph);
       mbar_wait(a_empty + 8u * ai, (uint32_t)(aph ^ 1));
       WS_TRACE(1, it, 1);
       if (S != 0) {
         if (hoist) {
-          if (mine) dw_item<S ? S : 1, RS>(sIn_a + e0.x, row_b, ks_b, w0, bias0, sAhi, sAlo, e0.y & 0xFFu, (e0.y >> 8) * kLBO, SBO, (uint32_t)p.TW);
+          if (mine) dw_item<S ? S : 1, RS>(sIn_a + ((e0 & 0x3FFFu) << 4), row_b, ks_b, w0, bias0, sAhi, sAlo, (e0 >> 14) & 0xFFu, (e0 >> 22) * kLBO, SBO, (uint32_t)p.TW);
         } else {
           for (int it = dtid; it < p.n_items; it += kDwThreads) {
-            const uint2 e = dtab[it];
-            const uint32_t wq = sDw_a + 16u * (e.y >> 8);
+            const uint32_t e = dtab[it];
+            const uint32_t wq = sDw_a + 16u * (e >> 22);
             float4 w[9];
 #pragma unroll
             for (int t = 0; t < 9; ++t) w[t] = lds4(wq + (uint32_t)(t * p.K8) * 4u);
             const float4 bias = lds4(wq + (uint32_t)(9 * p.K8) * 4u);
-            dw_item<S ? S : 1, RS>(sIn_a + e.x, row_b, ks_b, w, bias, sAhi, sAlo, e.y & 0xFFu, (e.y >> 8) * kLBO, SBO, (uint32_t)p.TW);
+            dw_item<S ? S : 1, RS>(sIn_a + ((e & 0x3FFFu) << 4), row_b, ks_b, w, bias, sAhi, sAlo, (e >> 14) & 0xFFu, (e >> 22) * kLBO, SBO, (uint32_t)p.TW);
           }
         }
       } else {
@@ -722,7 +724,7 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
       const int ksteps = p.K8 >> 3;
       const uint32_t hi = desc_hi(SBO);
       const uint32_t w_hi0 = desc_lo(sB_u32), w_lo0 = desc_lo(sB_u32 + (uint32_t)p.Npad * p.K8 * 4u);
-      const uint32_t a0 = desc_lo(smem_u32(sA)), a_buf = (a_stage_floats * 4u) >> 4, a_half = (128u * (uint32_t)p.K8 * 4u) >> 4;
+      const uint32_t a0 = desc_lo(smem_u32(sA)), a_buf = (a_stage_floats * 4u) >> 4, a_half = (a_part_floats * 4u) >> 4;
       const bool w_split = p.w_parts > 1;
       // Issuer mi takes the CTA's tiles it = mi, mi + nmi, ...  A parity wait must see every phase of its barrier, so a
       // slot may only ever be visited by one issuer: two issuers need even ring sizes, otherwise issuer 0 does all tiles.

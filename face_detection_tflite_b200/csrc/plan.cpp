@@ -485,7 +485,7 @@ struct Builder {
       s.tilesY = (OH + s.TH - 1) / s.TH;
       s.tilesX = (OW + s.TW - 1) / s.TW;
       if (s.IH > 256 || s.IW > 256 || s.G > 256 || s.KS > 256) continue;      // TMA box limits
-      s.a_rows = 128;
+      s.a_rows = std::min(128, ru(s.G * s.TH * s.TW, 8));      // operand rows really written (the MMA's over-read lands in what follows)
       // Depthwise work split: ND warps (8 with 128 registers, 12 with 96) and RS output rows per item, chosen by an
       // instruction-count estimate per thread and tile; one item per thread lets the taps stay in registers.
       s.RS = 1; s.nd = 8;
@@ -506,8 +506,8 @@ struct Builder {
         s.nd = 12;
       }
       size_t n_items = s.has_dw ? (size_t)s.G * (s.K8 / 4) * (s.TH / s.RS) * s.TW : 0;
-      size_t head = ((size_t)s.w_parts * s.Npad * s.K8 + 2 * (size_t)s.Npad + (s.has_dw ? 10 * (size_t)s.K8 : 0)) * 4 + n_items * 8 + 32 * 8 + 128;
-      size_t a_bytes = (size_t)2 * 128 * s.K8 * 4;
+      size_t head = ((size_t)s.w_parts * s.Npad * s.K8 + 2 * (size_t)s.Npad + (s.has_dw ? 10 * (size_t)s.K8 : 0)) * 4 + (n_items + 1) / 2 * 8 + 32 * 8 + 128;
+      size_t a_bytes = (size_t)2 * s.a_rows * s.K8 * 4;
       size_t in_bytes = ((size_t)s.G * s.IH * s.IW * s.KS * 4 + 127) / 128 * 128;
       // Output tile for the TMA-store epilogue: pixel stride KSo = CoutS rounded to an odd number of quads (conflict-free
       // STS.128), one or two buffers.  Ring choice: (A buffers, input stages) with even A rings preferred (the two MMA
@@ -527,6 +527,9 @@ struct Builder {
         for (const auto& c : combos) {
           if (c[0] == 0 || c[0] > max_na || c[1] > max_ns || c[1] < pr[1]) continue;
           size_t total = head + c[0] * a_bytes + c[1] * in_bytes + no * out_bytes;
+          // the MMA reads 128 operand rows: its over-read past the last A buffer must stay inside the allocation
+          const size_t over = (size_t)(128 - s.a_rows) * s.K8 * 4, after = c[1] * in_bytes + no * out_bytes;
+          if (over > after) total += over - after;
           if (total > cap) continue;
           s.na = c[0]; s.ns = c[1]; s.no = no;
           s.in_stage_floats = (int)(in_bytes / 4);
