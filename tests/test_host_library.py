@@ -138,3 +138,26 @@ def test_plan_lowering(lib, model_bytes, model, macs, steps):
             assert text.count(" block_ws ") == 20 and text.count(" stem_ws ") == 1   # BlazeBlocks + heads + stem on the warp-specialised tcgen05 kernels
     assert lib.fdt_host_plan_describe(d[:1000], 1000, 1, buf, len(buf)) != 0   # truncated flatbuffer is rejected, not a crash
     assert lib.fdt_host_plan_describe(b"\x00" * 64, 64, 1, buf, len(buf)) != 0
+
+
+@pytest.mark.parametrize("model", ["shortRange", "full", "backCamera", "mesh"])
+def test_warp_specialised_plans_respect_the_hardware_limits(lib, model_bytes, model):
+    """Every k_block_ws / k_stem_ws step must fit the 227 KB opt-in shared memory of an sm_100 CTA with room for the
+    1 KB system reservation, use ring depths the kernel's barrier slots provide, and keep TMA boxes <= 256 per dim."""
+    buf = C.create_string_buffer(1 << 17)
+    d = model_bytes[model]
+    assert lib.fdt_host_plan_describe(d, len(d), 1, buf, len(buf)) == 0, buf.value
+    n_ws = 0
+    for line in buf.value.decode().splitlines():
+        m = re.search(r"^\s*\d+\s+(block_ws|stem_ws)\s.*tile=(\d+)x(\d+)x(\d+) RS=(\d+) nd=(\d+) ns=(\d+) na=(\d+) no=(\d+) smem=(\d+)", line)
+        if not m:
+            continue
+        n_ws += 1
+        kind = m.group(1)
+        th, tw, g, rs, nd, ns, na, no, smem = (int(x) for x in m.groups()[1:])
+        assert smem <= 227 * 1024 - 1024, line
+        assert 1 <= ns <= 6 and 1 <= na <= 4 and 0 <= no <= 2, line
+        if kind == "block_ws":
+            assert nd in (8, 12) and rs in (1, 2, 4) and g * th * tw <= 128, line
+            assert (th - 1) * 2 + 3 <= 256 and (tw - 1) * 2 + 3 <= 256 and g <= 256, line
+    assert n_ws >= 10, "the conv stack should run on the warp-specialised kernels"
