@@ -20,6 +20,8 @@
 #include <mutex>
 #include <utility>
 
+#include <algorithm>
+
 #include "kernels.h"
 
 #ifndef FDT_MINB
@@ -200,7 +202,8 @@ __global__ void __launch_bounds__(384, FDT_MINB) k_gemm_conv(GemmConvP p, int B,
   p.fd_NQ.divmod(tid, pg, q);          // threads beyond NPG*NQ only help with the im2col staging
   const long long total_px = (long long)B * p.OH * p.OW;
 
-  for (int chunk = 0; chunk < p.nchunks; ++chunk) {
+  // output-channel chunks are spread over gridDim.y (a [faces x 288] x [288 x 1404] head has only a handful of pixel tiles)
+  for (int chunk = blockIdx.y; chunk < p.nchunks; chunk += gridDim.y) {
     const int c0 = chunk * p.NC;
     __syncthreads();
     load_weights(sW, p.w, p.KP, p.CoutP, c0, p.NC, tid, nt);
@@ -285,7 +288,8 @@ __global__ void __launch_bounds__(384, FDT_MINB) k_dwpw(DwPwP p, int B, int ntil
   const int Q = p.KP >> 2;
   const int thw = p.TH * p.TW;
 
-  for (int chunk = 0; chunk < p.nchunks; ++chunk) {
+  // output-channel chunks are spread over gridDim.y (a [faces x 288] x [288 x 1404] head has only a handful of pixel tiles)
+  for (int chunk = blockIdx.y; chunk < p.nchunks; chunk += gridDim.y) {
     const int c0 = chunk * p.NC;
     __syncthreads();
     load_weights(sW, p.w, p.KP, p.CoutP, c0, p.NC, tid, nt);
@@ -489,15 +493,18 @@ void launch_gemm_conv(const GemmConvP& p, int B, cudaStream_t s, int max_ctas) {
   int ntiles = (int)((total_px + P - 1) / P);
   int grid = ntiles < max_ctas ? ntiles : max_ctas;
   if (grid < 1) grid = 1;
+  // few pixel tiles and many channel chunks: give each chunk its own CTAs (at least ~2 waves of the 148 SMs in total)
+  int gy = 1;
+  if (p.nchunks > 1 && grid < 148) gy = std::min(p.nchunks, (296 + grid - 1) / grid);
   int nt = p.NPG * (p.NC >> 2);
   if (nt < 128) nt = 128;               // extra threads help with the im2col staging
   nt = (nt + 31) / 32 * 32;
   if (p.TM == 8) {
     set_smem((const void*)k_gemm_conv<8>, p.smem_bytes);
-    k_gemm_conv<8><<<grid, nt, p.smem_bytes, s>>>(p, B, ntiles);
+    k_gemm_conv<8><<<dim3(grid, gy), nt, p.smem_bytes, s>>>(p, B, ntiles);
   } else {
     set_smem((const void*)k_gemm_conv<4>, p.smem_bytes);
-    k_gemm_conv<4><<<grid, nt, p.smem_bytes, s>>>(p, B, ntiles);
+    k_gemm_conv<4><<<dim3(grid, gy), nt, p.smem_bytes, s>>>(p, B, ntiles);
   }
 }
 
