@@ -208,6 +208,12 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         p.smem_bytes = st.smem;
         p.ns = st.ns; p.na = st.na; p.nd = st.nd; p.nt = st.nt; p.trace = nullptr;
         p.no = st.no; p.KSo = st.KSo; p.out_stage_floats = st.out_stage_floats;
+        p.out2 = nullptr; p.out2_istride = 0; p.Cs2 = 0; p.c1 = 0; p.c2 = 0;
+        if (st.out2 >= 0) {
+          TV o2 = view(ctx, st.out2);
+          p.out2 = o2.p; p.out2_istride = o2.istride; p.Cs2 = o2.Cs; p.c1 = st.c1; p.c2 = st.c2;
+          p.Cout = st.c1;                       // columns of the first output
+        }
         if (st.kind == kStepBlockWs) {
           p.in_floats = st.in_stage_floats;
           if (!launch_block_ws(p, B, ctx.cap, s)) { failed_ = true; fprintf(stderr, "fdt: cuTensorMapEncodeTiled failed for step '%s'\n", st.name.c_str()); }

@@ -140,6 +140,7 @@ struct DwPwTcP {
   int nbuf;                 // 2: double-buffered input tile (the next tile is prefetched during compute)
   int ns, na, nd, nt;       // k_block_ws: input ring stages, A-operand buffers, depthwise warps, TMEM accumulators
   int no, KSo, out_stage_floats;   // k_block_ws TMA-store epilogue: output tile buffers (0 = direct stores), its pixel stride, floats per buffer
+  float* out2; long long out2_istride; int Cs2, c1, c2;   // second output of a merged head pair (c2 == 0: none)
   long long* trace;         // FDT_WS_TRACE=1: per-role clock64 stamps of CTA 0 ([4 roles][64 tiles][3]); null in production
   const float* res; long long res_istride; int res_H, res_W, res_C, res_Cs, res_pool, res_mode, res_lim;
   int TH, TW, G, IH, IW, tilesX, tilesY;

@@ -220,7 +220,8 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 template <int RES, int LEAKY, int SM>
 __device__ __forceinline__ void epi_fast(uint32_t tcol0, uint32_t res_a, uint32_t bias_a, uint32_t alpha_a, float* orow, uint32_t out_s,
                                          bool valid, bool store_ok, int cout_s, uint32_t ks_b, uint32_t row_b,
-                                         const float* gres = nullptr, int gks = 0, int grow = 0, int gres_c = 0, bool wide = false) {
+                                         const float* gres = nullptr, int gks = 0, int grow = 0, int gres_c = 0, bool wide = false,
+                                         float* orow2 = nullptr, int c1 = 1 << 30, int c2 = 0) {
   // 16 columns per TMEM round trip (8 for the pooled residuals, whose four taps per quad need the registers); the
   // accumulator is Npad = 16k columns wide, quads >= cout_s are computed on whatever lies there and dropped at the store
 #ifdef FDT_EPI_X8
@@ -270,18 +271,27 @@ __device__ __forceinline__ void epi_fast(uint32_t tcol0, uint32_t res_a, uint32_
       else v = max4(v, make_float4(0.f, 0.f, 0.f, 0.f));
       vq[q] = v;
     }
-    if (!SM && wide) {
-      // CoutS % 8 == 0 and a 32-byte aligned pixel record: one 256-bit store per pair of quads
+    // columns [0, c1) -> orow (float4 / 256-bit stores); columns [c1, c1 + c2) -> orow2 (second head of a merged pair,
+    // dense [.., c2] view: scalar stores).  Without a second output c1 is "infinite" and cout_s bounds the loop.
 #pragma unroll
-      for (int q = 0; q < NQ; q += 2)
-        if (store_ok && c0 + 4 * q < cout_s) stg8(orow + c0 + 4 * q, vq[q], vq[q + 1]);
-    } else {
-#pragma unroll
-      for (int q = 0; q < NQ; ++q)
-        if (store_ok && c0 + 4 * q < cout_s) {
-          if (SM) asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(out_s + 4u * (uint32_t)(c0 + 4 * q)), "f"(vq[q].x), "f"(vq[q].y), "f"(vq[q].z), "f"(vq[q].w) : "memory");
-          else *reinterpret_cast<float4*>(orow + c0 + 4 * q) = vq[q];
+    for (int q = 0; q < NQ; ++q) {
+      const int c = c0 + 4 * q;
+      if (!store_ok || c >= cout_s) continue;
+      if (c < c1) {
+        if (SM) {
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(out_s + 4u * (uint32_t)c), "f"(vq[q].x), "f"(vq[q].y), "f"(vq[q].z), "f"(vq[q].w) : "memory");
+        } else if (wide) {
+          // CoutS (c1) % 8 == 0 and a 32-byte aligned pixel record: one 256-bit store per pair of quads
+          if ((q & 1) == 0) stg8(orow + c, vq[q], vq[q + 1 < NQ ? q + 1 : q]);
+        } else {
+          *reinterpret_cast<float4*>(orow + c) = vq[q];
         }
+      } else {
+        const float vv[4] = {vq[q].x, vq[q].y, vq[q].z, vq[q].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (c - c1 + j < c2) orow2[c - c1 + j] = vv[j];
+      }
     }
   }
 }
@@ -505,6 +515,8 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
     p.fd_TW.divmod(e_r, e_ty, e_tx);
     const bool slot_ok = slot < nslots;
     const long long o_rel = slot_ok ? (long long)e_g * p.out_istride + ((long long)e_ty * p.OW + e_tx) * p.CoutS : 0;
+    const long long o_rel2 = slot_ok ? (long long)e_g * p.out2_istride + ((long long)e_ty * p.OW + e_tx) * p.Cs2 : 0;
+    const int cout_loop = p.c2 > 0 ? p.c1 + ((p.c2 + 3) & ~3) : p.CoutS, c1 = p.c2 > 0 ? p.c1 : (1 << 30);
     const int rs = p.res_pool ? 2 : 1;
     const uint32_t res_off = slot_ok ? (uint32_t)((((size_t)e_g * p.IH + e_ty * rs + p.dpt) * p.IW + e_tx * rs + p.dpl) * p.KS) : 0u;
     const uint32_t sIn0_a = smem_u32(sIn0), bias_a = smem_u32(sBias), alpha_a = smem_u32(sAlpha);
@@ -528,6 +540,7 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
       const int oy = ty0 + e_ty, ox = tx0 + e_tx, b = b0 + e_g;
       const bool valid = slot_ok && b < B && oy < p.OH && ox < p.OW;
       float* orow = p.out + (long long)b0 * p.out_istride + ((long long)ty0 * p.OW + tx0) * p.CoutS + o_rel;
+      float* orow2 = p.c2 > 0 ? p.out2 + (long long)b0 * p.out2_istride + ((long long)ty0 * p.OW + tx0) * p.Cs2 + o_rel2 : nullptr;
       const float* rbase = p.res_mode == 2 ? p.res + (size_t)(valid ? b : 0) * p.res_istride : nullptr;
       const uint32_t tcol0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(di * p.Npad);
       if (fast) {
@@ -568,20 +581,20 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
           const uint32_t out_s = 0u;
           if (res_kind == 3) {
             if (p.act == kActRelu) {
-              if (p.res_pool) epi_fast<4, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C, wide);
-              else epi_fast<3, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C, wide);
+              if (p.res_pool) epi_fast<4, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, gres, gks, grow, p.res_C, wide, orow2, c1, p.c2);
+              else epi_fast<3, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, gres, gks, grow, p.res_C, wide, orow2, c1, p.c2);
             } else {
-              if (p.res_pool) epi_fast<4, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C, wide);
-              else epi_fast<3, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, gres, gks, grow, p.res_C, wide);
+              if (p.res_pool) epi_fast<4, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, gres, gks, grow, p.res_C, wide, orow2, c1, p.c2);
+              else epi_fast<3, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, gres, gks, grow, p.res_C, wide, orow2, c1, p.c2);
             }
           } else if (p.act == kActRelu) {
-            if (res_kind == 1) epi_fast<1, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, nullptr, 0, 0, 0, wide);
-            else if (res_kind == 2) epi_fast<2, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, nullptr, 0, 0, 0, wide);
-            else epi_fast<0, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, nullptr, 0, 0, 0, wide);
+            if (res_kind == 1) epi_fast<1, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, 0, wide, orow2, c1, p.c2);
+            else if (res_kind == 2) epi_fast<2, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, 0, wide, orow2, c1, p.c2);
+            else epi_fast<0, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, 0, wide, orow2, c1, p.c2);
           } else {
-            if (res_kind == 1) epi_fast<1, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, nullptr, 0, 0, 0, wide);
-            else if (res_kind == 2) epi_fast<2, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, nullptr, 0, 0, 0, wide);
-            else epi_fast<0, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, p.CoutS, ks_b, row_b, nullptr, 0, 0, 0, wide);
+            if (res_kind == 1) epi_fast<1, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, 0, wide, orow2, c1, p.c2);
+            else if (res_kind == 2) epi_fast<2, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, 0, wide, orow2, c1, p.c2);
+            else epi_fast<0, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, 0, wide, orow2, c1, p.c2);
           }
         }
       } else {
@@ -1234,6 +1247,7 @@ bool launch_block_ws(const DwPwTcP& p0, int B, int cap, cudaStream_t s) {
   if (!input_tensor_map(p, cap, &tm)) return false;
   // the TMA-store epilogue needs a float4-aligned output tensor (the heads' dense views keep direct stores)
   if (p.no > 0 && !(p.vec_store && p.CoutS % 4 == 0 && p.out_istride % 4 == 0)) p.no = 0;
+  if (p.c2 > 0 && (!p.vec_store || p.res_mode != 0 || p.no > 0)) return false;   // merged heads: float4-aligned first output, no residual
   if (p.no > 0) { if (!output_tensor_map(p, cap, &tmo)) return false; } else tmo = tm;
   int groups = (B + p.G - 1) / p.G;
   int ntiles = groups * p.tilesX * p.tilesY;

@@ -68,7 +68,7 @@ struct View { int root = -1; long long off = 0; };
 struct Fused {       // analysis result for one CONV_2D
   bool ok = false;
   PStep st;
-  int src_tf = -1, res_tf = -1, out_tf = -1;
+  int src_tf = -1, res_tf = -1, out_tf = -1, out2_tf = -1;
 };
 
 struct Builder {
@@ -311,9 +311,60 @@ struct Builder {
     if (!m.const_f32(conv.in[1], &w)) return fail("conv weights are not constant");
     if (conv.in.size() > 2 && conv.in[2] >= 0) { if (!m.const_f32(conv.in[2], &b)) return fail("conv bias is not constant"); }
     b.resize(st.Cout, 0.f);
+    // Two heads of one scale (classificator + regressor read the same tensor and write dense graph outputs): one launch.
+    // The head whose channel count is a multiple of 4 comes first so that its columns keep their float4 stores; the kernel
+    // writes columns [0, c1) to its output and [c1, c1 + c2) to the other head's.
+    static const int want_dual = [] { const char* e = std::getenv("FDT_WS_DUAL"); return e ? std::atoi(e) : 1; }();
+    if (use_tc && want_dual && !st.has_dw && res < 0 && st.act == kActNone && is_view(cur)) {
+      int sib = -1;
+      for (size_t j = 0; j < m.ops.size() && sib < 0; ++j) {
+        const TfOp& o2 = m.ops[j];
+        if ((int)j == ci || done[j] || o2.code != kOpConv2D || o2.in[0] != conv.in[0]) continue;
+        const TfTensor& w2t = m.tensors[o2.in[1]];
+        if (w2t.shape.size() != 4 || w2t.shape[1] != 1 || w2t.shape[2] != 1 || w2t.shape[3] != Cin) continue;
+        if (o2.stride_h != 1 || o2.stride_w != 1 || o2.act != 0 || !is_view(o2.out[0])) continue;
+        sib = (int)j;
+      }
+      if (sib >= 0) {
+        const TfOp& o2 = m.ops[sib];
+        const int sib_out = o2.out[0];
+        std::vector<float> w2, b2;
+        bool ok2 = m.const_f32(o2.in[1], &w2);
+        if (ok2 && o2.in.size() > 2 && o2.in[2] >= 0) ok2 = m.const_f32(o2.in[2], &b2);
+        const int C2n = m.tensors[o2.in[1]].shape[0];
+        b2.resize(C2n, 0.f);
+        const bool this_primary = st.Cout % 4 == 0 && (C2n % 4 != 0 || st.Cout >= C2n);
+        const int Cp = this_primary ? st.Cout : C2n, Cq = this_primary ? C2n : st.Cout;
+        const int p_out = this_primary ? cur : sib_out, q_out = this_primary ? sib_out : cur;
+        const bool vec_ok = views[p_out].off % 4 == 0 && P.out_elems[views[p_out].root] % 4 == 0;
+        if (ok2 && Cp % 4 == 0 && vec_ok) {
+          std::vector<float> wm, bm;
+          const std::vector<float>& wp = this_primary ? w : w2;
+          const std::vector<float>& wq = this_primary ? w2 : w;
+          const std::vector<float>& bp = this_primary ? b : b2;
+          const std::vector<float>& bq = this_primary ? b2 : b;
+          wm.insert(wm.end(), wp.begin(), wp.end()); wm.insert(wm.end(), wq.begin(), wq.end());
+          bm.insert(bm.end(), bp.begin(), bp.end()); bm.insert(bm.end(), bq.begin(), bq.end());
+          PStep t = st;
+          t.Cout = Cp + Cq; t.c1 = Cp; t.c2 = Cq;
+          if (plan_tc(&t, Cin, OH, OW, tf32_exact(wm) ? 1 : 2) && plan_ws(&t, OH, OW)) {
+            st.Cout = Cp + Cq; st.c1 = Cp; st.c2 = Cq;
+            plan_columns(&st);
+            const std::string nm = m.tensors[p_out].name + "+" + m.tensors[q_out].name;
+            F->st = st;
+            F->st.name = nm;
+            F->out_tf = p_out; F->out2_tf = q_out;
+            done[sib] = 1;
+            fused_outputs.push_back(sib_out);
+            w.swap(wm); b.swap(bm);
+          }
+        }
+      }
+    }
     const int w_parts = tf32_exact(w) ? 1 : 2;
     bool tc = use_tc && plan_tc(&F->st, Cin, OH, OW, w_parts);
     if (tc) plan_ws(&F->st, OH, OW);
+    if (F->st.c2 > 0 && F->st.kind != kStepBlockWs) return fail("internal: merged heads need the warp-specialised kernel");
     const PStep& fs = F->st;
     if (tc) {
       // B operand [Npad x K8] in the UMMA K-major core-matrix layout (8 rows x 16 bytes per core matrix)
@@ -523,7 +574,7 @@ struct Builder {
       static const int prefs[5][2] = {{2, 2}, {1, 2}, {2, 1}, {1, 1}, {0, 1}};     // (output tiles, min input stages)
       for (const auto& pr : prefs) {
         const int no = pr[0];
-        if (no > want_no || (no > 0 && !can_tma_out)) continue;
+        if (no > want_no || (no > 0 && (!can_tma_out || s.c2 > 0))) continue;
         for (const auto& c : combos) {
           if (c[0] == 0 || c[0] > max_na || c[1] > max_ns || c[1] < pr[1]) continue;
           size_t total = head + c[0] * a_bytes + c[1] * in_bytes + no * out_bytes;
@@ -751,9 +802,11 @@ struct Builder {
     if (s.in2 >= 0 && !P.tensors[s.in2].materialized)
       return fail("internal: step '" + s.name + "' reads a residual that is not materialised");
     P.tensors[s.out].materialized = true;
+    if (s.out2 >= 0) P.tensors[s.out2].materialized = true;
     if (!s.in_u8) use(idx, s.in);
     use(idx, s.in2);
     use(idx, s.out);
+    use(idx, s.out2);
     P.steps.push_back(std::move(s));
     return true;
   }
@@ -812,6 +865,7 @@ struct Builder {
         s.in = pt(F.src_tf);
         s.in2 = F.res_tf >= 0 ? pt(F.res_tf) : -1;
         s.out = pt(F.out_tf);
+        s.out2 = F.out2_tf >= 0 ? pt(F.out2_tf) : -1;
         if (s.in_u8) s.in = P.input;
         if (!emit(s)) return false;
         continue;

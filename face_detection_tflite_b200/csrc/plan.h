@@ -42,7 +42,8 @@ struct PStep {
   int K8 = 0, Npad = 0, a_rows = 0, RS = 1, tmem_cols = 0, w_parts = 1, nbuf = 1;   // tensor-core variant
   double out_scale = 1.0;    // k_stem_ws: D * out_scale + bias
   int ns = 0, na = 0, nd = 8, nt = 2, in_stage_floats = 0;
-  int no = 0, KSo = 0, out_stage_floats = 0;           // TMA-store epilogue (k_block_ws)   // warp-specialised variant: input stages, A buffers, depthwise warps
+  int no = 0, KSo = 0, out_stage_floats = 0;           // TMA-store epilogue (k_block_ws)
+  int out2 = -1, c1 = 0, c2 = 0;                        // two heads in one launch: columns [0,c1) -> out, [c1,c1+c2) -> out2   // warp-specialised variant: input stages, A buffers, depthwise warps
   int fh = 1, fw = 1, align = 0, half = 0;
   double macs = 0;  // per image
 };

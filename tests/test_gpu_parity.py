@@ -462,7 +462,7 @@ def test_c_abi_status_codes(fdt, lib):
     iw, ih, na, mf, mb = (C.c_int32() for _ in range(5))
     assert lib.fdt_get_info(h, C.byref(iw), C.byref(ih), C.byref(na), C.byref(mf), C.byref(mb)) == 0
     assert (iw.value, ih.value, na.value, mf.value) == (128, 128, 896, 100)
-    assert lib.fdt_last_h2d_bytes(h) == 48 and lib.fdt_last_launch_count(h) == 23
+    assert lib.fdt_last_h2d_bytes(h) == 48 and lib.fdt_last_launch_count(h) == 21   # letterbox + stem + 16 blocks + 2 head pairs + decode
 
 
 # ---- alternative kernel paths (environment switches are read once per process -> subprocesses) ----------
@@ -503,7 +503,8 @@ print("variant ok")
                                  {"FDT_STEM_WS": "0"},        # k_stem_tc (TF32 hi/lo im2col) instead of the fp16 stem
                                  {"FDT_WS_ND": "8"},          # 8 depthwise warps everywhere
                                  {"FDT_WS_NA": "1", "FDT_WS_NS": "2"},   # minimal rings, single MMA issuer
-                                 {"FDT_PDL": "1"}])           # programmatic dependent launch
+                                 {"FDT_PDL": "1"},            # programmatic dependent launch
+                                 {"FDT_WS_DUAL": "0"}])       # one launch per head instead of one per head pair
 def test_kernel_variants_match_the_oracle(env):
     """Every tuning switch selects code that must stay parity-green: raw heads of two models vs the fp64 oracle."""
     import subprocess

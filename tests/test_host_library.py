@@ -124,7 +124,7 @@ def test_face_roi_matches_oracle(lib):
     assert lib.fdt_host_face_roi(kp.ctypes.data, 100.0, 100.0, 192, out.ctypes.data) == 0
 
 
-@pytest.mark.parametrize("model,macs,steps", [("shortRange", 30.761, 21), ("full", 105.671, None), ("backCamera", 188.750, None), ("mesh", 34.979, None)])
+@pytest.mark.parametrize("model,macs,steps", [("shortRange", 30.761, 19), ("full", 105.671, None), ("backCamera", 188.750, None), ("mesh", 34.979, None)])
 def test_plan_lowering(lib, model_bytes, model, macs, steps):
     buf = C.create_string_buffer(1 << 17)
     d = model_bytes[model]
@@ -134,8 +134,8 @@ def test_plan_lowering(lib, model_bytes, model, macs, steps):
         m = re.search(r"steps=(\d+)\s+MACs/image=([0-9.]+)M", text)
         assert abs(float(m.group(2)) - macs) < 0.002                      # SURVEY.md 2.3 MAC counts
         if fuse == 1 and steps:
-            assert int(m.group(1)) == steps                               # stem + 16 BlazeBlocks + 4 heads
-            assert text.count(" block_ws ") == 20 and text.count(" stem_ws ") == 1   # BlazeBlocks + heads + stem on the warp-specialised tcgen05 kernels
+            assert int(m.group(1)) == steps                               # stem + 16 BlazeBlocks + 2 merged head pairs
+            assert text.count(" block_ws ") == 18 and text.count(" stem_ws ") == 1   # BlazeBlocks + heads + stem on the warp-specialised tcgen05 kernels
     assert lib.fdt_host_plan_describe(d[:1000], 1000, 1, buf, len(buf)) != 0   # truncated flatbuffer is rejected, not a crash
     assert lib.fdt_host_plan_describe(b"\x00" * 64, 64, 1, buf, len(buf)) != 0
 

@@ -1,4 +1,4 @@
-"""Condenses gpurun_out/raw_<tag>.csv (ncu --set full, one chunk of frames = 23 launches) and
+"""Condenses gpurun_out/raw_<tag>.csv (ncu --set full, one chunk of frames = 21 launches) and
 gpurun_out/launches_<tag>.csv into tracked files under profiles/: a per-launch summary CSV and the
 per-launch DRAM traffic table bench.py quotes in its `roofline.traffic` field."""
 import csv, json, sys

@@ -1,5 +1,5 @@
 """Small fixed workload for ncu: 3 chunks of 512 synthetic 1280x720 frames through the fast-mode
-pipeline (23 kernel launches per chunk: letterbox, stem, 16 BlazeBlocks, 4 heads, decode+NMS)."""
+pipeline (21 kernel launches per chunk: letterbox, stem, 16 BlazeBlocks, 2 head pairs, decode+NMS)."""
 import sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]
