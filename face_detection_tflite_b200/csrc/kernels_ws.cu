@@ -217,7 +217,7 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 // RES 3 / 4: residual from another HBM tensor (same size / 2x2 max-pooled), float4 loads; `gres` points at this thread's
 // residual pixel (top-left of the pool window), gks / grow are its pixel / row strides in floats, gres_c its channels.
 // SM = 1: the results go to the shared-memory output tile at `out_s` (then one TMA store per tile) instead of to HBM.
-template <int RES, int LEAKY, int SM>
+template <int RES, int LEAKY, int SM, int DUAL = 0>
 __device__ __forceinline__ void epi_fast(uint32_t tcol0, uint32_t res_a, uint32_t bias_a, uint32_t alpha_a, float* orow, uint32_t out_s,
                                          bool valid, bool store_ok, int cout_s, uint32_t ks_b, uint32_t row_b,
                                          const float* gres = nullptr, int gks = 0, int grow = 0, int gres_c = 0, bool wide = false,
@@ -271,27 +271,35 @@ __device__ __forceinline__ void epi_fast(uint32_t tcol0, uint32_t res_a, uint32_
       else v = max4(v, make_float4(0.f, 0.f, 0.f, 0.f));
       vq[q] = v;
     }
-    // columns [0, c1) -> orow (float4 / 256-bit stores); columns [c1, c1 + c2) -> orow2 (second head of a merged pair,
-    // dense [.., c2] view: scalar stores).  Without a second output c1 is "infinite" and cout_s bounds the loop.
+    if (DUAL) {
+      // merged head pair: columns [0, c1) -> orow (float4 / 256-bit stores); columns [c1, c1 + c2) -> orow2 (dense
+      // [.., c2] view of the other head: scalar stores)
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const int c = c0 + 4 * q;
-      if (!store_ok || c >= cout_s) continue;
-      if (c < c1) {
-        if (SM) {
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(out_s + 4u * (uint32_t)c), "f"(vq[q].x), "f"(vq[q].y), "f"(vq[q].z), "f"(vq[q].w) : "memory");
-        } else if (wide) {
-          // CoutS (c1) % 8 == 0 and a 32-byte aligned pixel record: one 256-bit store per pair of quads
-          if ((q & 1) == 0) stg8(orow + c, vq[q], vq[q + 1 < NQ ? q + 1 : q]);
+      for (int q = 0; q < NQ; ++q) {
+        const int c = c0 + 4 * q;
+        if (!store_ok || c >= cout_s) continue;
+        if (c < c1) {
+          if (wide) { if ((q & 1) == 0) stg8(orow + c, vq[q], vq[q + 1 < NQ ? q + 1 : q]); }   // c1 % 8 == 0 when wide
+          else *reinterpret_cast<float4*>(orow + c) = vq[q];
         } else {
-          *reinterpret_cast<float4*>(orow + c) = vq[q];
-        }
-      } else {
-        const float vv[4] = {vq[q].x, vq[q].y, vq[q].z, vq[q].w};
+          const float vv[4] = {vq[q].x, vq[q].y, vq[q].z, vq[q].w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (c - c1 + j < c2) orow2[c - c1 + j] = vv[j];
+          for (int j = 0; j < 4; ++j)
+            if (c - c1 + j < c2) orow2[c - c1 + j] = vv[j];
+        }
       }
+    } else if (!SM && wide) {
+      // CoutS % 8 == 0 and a 32-byte aligned pixel record: one 256-bit store per pair of quads
+#pragma unroll
+      for (int q = 0; q < NQ; q += 2)
+        if (store_ok && c0 + 4 * q < cout_s) stg8(orow + c0 + 4 * q, vq[q], vq[q + 1]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q)
+        if (store_ok && c0 + 4 * q < cout_s) {
+          if (SM) asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(out_s + 4u * (uint32_t)(c0 + 4 * q)), "f"(vq[q].x), "f"(vq[q].y), "f"(vq[q].z), "f"(vq[q].w) : "memory");
+          else *reinterpret_cast<float4*>(orow + c0 + 4 * q) = vq[q];
+        }
     }
   }
 }
@@ -581,20 +589,21 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
           const uint32_t out_s = 0u;
           if (res_kind == 3) {
             if (p.act == kActRelu) {
-              if (p.res_pool) epi_fast<4, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, gres, gks, grow, p.res_C, wide, orow2, c1, p.c2);
-              else epi_fast<3, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, gres, gks, grow, p.res_C, wide, orow2, c1, p.c2);
+              if (p.res_pool) epi_fast<4, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, gres, gks, grow, p.res_C, wide);
+              else epi_fast<3, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, gres, gks, grow, p.res_C, wide);
             } else {
-              if (p.res_pool) epi_fast<4, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, gres, gks, grow, p.res_C, wide, orow2, c1, p.c2);
-              else epi_fast<3, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, gres, gks, grow, p.res_C, wide, orow2, c1, p.c2);
+              if (p.res_pool) epi_fast<4, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, gres, gks, grow, p.res_C, wide);
+              else epi_fast<3, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, gres, gks, grow, p.res_C, wide);
             }
           } else if (p.act == kActRelu) {
-            if (res_kind == 1) epi_fast<1, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, 0, wide, orow2, c1, p.c2);
-            else if (res_kind == 2) epi_fast<2, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, 0, wide, orow2, c1, p.c2);
-            else epi_fast<0, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, 0, wide, orow2, c1, p.c2);
+            if (res_kind == 1) epi_fast<1, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, 0, wide);
+            else if (res_kind == 2) epi_fast<2, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, 0, wide);
+            else epi_fast<0, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, 0, wide);
           } else {
-            if (res_kind == 1) epi_fast<1, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, 0, wide, orow2, c1, p.c2);
-            else if (res_kind == 2) epi_fast<2, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, 0, wide, orow2, c1, p.c2);
-            else epi_fast<0, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, 0, wide, orow2, c1, p.c2);
+            if (res_kind == 1) epi_fast<1, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, 0, wide);
+            else if (res_kind == 2) epi_fast<2, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, 0, wide);
+            else if (p.c2 > 0) epi_fast<0, 1, 0, 1>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, 0, wide, orow2, c1, p.c2);
+            else epi_fast<0, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, 0, wide);
           }
         }
       } else {
@@ -1247,7 +1256,7 @@ bool launch_block_ws(const DwPwTcP& p0, int B, int cap, cudaStream_t s) {
   if (!input_tensor_map(p, cap, &tm)) return false;
   // the TMA-store epilogue needs a float4-aligned output tensor (the heads' dense views keep direct stores)
   if (p.no > 0 && !(p.vec_store && p.CoutS % 4 == 0 && p.out_istride % 4 == 0)) p.no = 0;
-  if (p.c2 > 0 && (!p.vec_store || p.res_mode != 0 || p.no > 0)) return false;   // merged heads: float4-aligned first output, no residual
+  if (p.c2 > 0 && (!p.vec_store || p.res_mode != 0 || p.no > 0 || p.act != kActNone)) return false;   // merged heads: float4-aligned first output, no residual
   if (p.no > 0) { if (!output_tensor_map(p, cap, &tmo)) return false; } else tmo = tm;
   int groups = (B + p.G - 1) / p.G;
   int ntiles = groups * p.tilesX * p.tilesY;
