@@ -14,6 +14,7 @@ FDT_MAT_8UC1, FDT_MAT_8UC3, FDT_MAT_8UC4 = 0, 16, 24
 FDT_MEM_HOST, FDT_MEM_DEVICE = 0, 1
 FDT_MAX_FACES = 100
 FDT_MESH_FLOATS = 1404
+FDT_IRIS_FLOATS = 456
 
 
 class FdtConfig(C.Structure):
@@ -25,7 +26,7 @@ class FdtConfig(C.Structure):
 class FdtFace(C.Structure):
     _fields_ = [("xmin", C.c_double), ("ymin", C.c_double), ("xmax", C.c_double), ("ymax", C.c_double),
                 ("score", C.c_double), ("keypoints", C.c_double * 12), ("mesh_score", C.c_double),
-                ("has_mesh", C.c_int32), ("anchor_index", C.c_int32)]
+                ("has_mesh", C.c_int32), ("anchor_index", C.c_int32), ("has_iris", C.c_int32), ("reserved", C.c_int32)]
 
 
 # every symbol include/fdt_api.h declares: name -> (restype, argtypes)
@@ -37,10 +38,12 @@ f64p = C.POINTER(C.c_double)
 SIGNATURES = {
     "fdt_default_config": (None, [C.POINTER(FdtConfig)]),
     "fdt_create": (C.c_int32, [C.POINTER(FdtConfig), C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(P)]),
+    "fdt_create_ex": (C.c_int32, [C.POINTER(FdtConfig), C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t,
+                                  i32p, C.c_int32, C.POINTER(P)]),
     "fdt_destroy": (C.c_int32, [P]),
     "fdt_detect_batch": (C.c_int32, [P, P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                     C.POINTER(FdtFace), i32p, f32p]),
-    "fdt_detect_one": (C.c_int32, [P, P, C.c_size_t, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(FdtFace), i32p, f32p]),
+                                     C.POINTER(FdtFace), i32p, f32p, f32p]),
+    "fdt_detect_one": (C.c_int32, [P, P, C.c_size_t, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(FdtFace), i32p, f32p, f32p]),
     "fdt_detect_batch_device": (C.c_int32, [P, P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                             C.POINTER(P), C.POINTER(P)]),
     "fdt_synchronize": (C.c_int32, [P]),
@@ -59,6 +62,16 @@ SIGNATURES = {
     "fdt_debug_get_candidates": (C.c_int32, [P, C.c_int32, P, C.c_int32, i32p]),
     "fdt_debug_get_tensor": (C.c_int32, [P, C.c_int32, C.c_int32, C.c_int32, P, C.c_size_t, i32p]),
     "fdt_debug_get_mesh_stage": (C.c_int32, [P, C.c_int32, P, P, P, i32p]),
+    "fdt_debug_get_iris_stage": (C.c_int32, [P, C.c_int32, P, P, P, P, i32p]),
+    "fdt_debug_decode": (C.c_int32, [P, P, P, P, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double, P,
+                                     C.POINTER(FdtFace), i32p, P, i32p]),
+    "fdt_debug_nms": (C.c_int32, [P, P, C.c_int32, C.c_double, C.c_double, P, C.POINTER(FdtFace), i32p]),
+    "fdt_extract_aligned_squares": (C.c_int32, [P, P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, P, C.c_int32, C.c_int32, P, i32p]),
+    "fdt_profile_net": (C.c_int32, [P, C.c_int32, C.c_int32, C.c_int32, f32p, C.c_int32, i32p]),
+    "fdt_get_net_step_info": (C.c_int32, [P, C.c_int32, C.c_int32, C.c_char_p, C.c_char_p, C.c_int32, f64p, f64p]),
+    "fdt_num_devices": (C.c_int32, [P]),
+    "fdt_host_eye_rois": (C.c_int32, [P, P]),
+    "fdt_host_embedding_roi": (C.c_int32, [P, P, P]),
     "fdt_last_launch_count": (C.c_int64, [P]),
     "fdt_last_h2d_bytes": (C.c_int64, [P]),
     "fdt_set_stage_timing": (C.c_int32, [P, C.c_int32]),

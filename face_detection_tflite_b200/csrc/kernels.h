@@ -190,39 +190,48 @@ struct DecodeP {
   fdt_face* faces;                                // [B][max_faces]
   int* counts;                                    // [B]
   int* cand_idx; int cand_cap; int* cand_n;       // debug taps (may be null)
+  // test hooks (fdt_debug_decode / fdt_debug_nms); null / 0 in production
+  const double* pre;                              // [B][N][17] already decoded detections (box4, score, kp12): skips threshold + decode
+  double* dbg_dec;                                // [B][N][18] decoded candidates in anchor order: box4, score, kp12, kept flag
+  int skip_roi;                                   // 1: keep faces whose alignment ROI is degenerate (round(size) <= 0)
 };
 size_t decode_smem_bytes(int N);
 void launch_decode_nms(const DecodeP& p, int B, cudaStream_t s);
 
-// ---- mesh stage ----
-struct FaceListP {
-  const int* counts; int B, max_faces;
-  const fdt_face* faces;
-  double img_w, img_h; int out_size;
-  int cap;                 // capacity of the face list
-  int skip;                // first face (in chunk order) of this pass
-  int* total;              // [1] number of faces with a valid ROI (<= cap)
-  int* face_img; int* face_slot;   // [cap]
-  double* affine;          // [cap][6] inverse map (dst -> src), cv::warpAffine convention
-  double* align;           // [cap][4] theta,cx,cy,size
-  int* overflow;           // [1] set when more than cap faces were found
-};
-void launch_build_face_list(const FaceListP& p, cudaStream_t s);
-
+// ---- aligned crops: cv::warpAffine(INTER_LINEAR, BORDER_CONSTANT 0) of a list of ROIs ----
+// The ROI list (source image + inverse affine map per crop) is built on the host from the detections /
+// mesh points with the host libm, exactly as the reference does (extractAlignedSquare, helpers.dart:583-625).
 struct WarpP {
   const uint8_t* frames; long long frame_stride; int row_stride, channels, src_w, src_h;
-  const int* face_img; const double* affine; int nfaces, out_size;
-  uint8_t* crops;          // [nfaces][out][out][4] BGRX
+  const int* crop_img;     // [ncrops] frame index inside `frames`
+  const double* affine;    // [ncrops][6] inverse map (dst -> src), cv::warpAffine convention
+  int ncrops, out_size;
+  int flip_odd;            // 1: odd crops are mirrored horizontally (cv.flip(rightEye, 1), face_detector_core.dart:567)
+  uint8_t* crops;          // [ncrops][out][out][4] BGRX
 };
 void launch_warp_affine(const WarpP& p, cudaStream_t s);
 
+// ---- mesh / iris post-processing ----
 struct MeshPostP {
   const float* raw; long long raw_istride;     // [F][1404]
   const float* flag; long long flag_istride;   // [F][1]
-  const double* align; int nfaces, in_size;
+  const double* roi;                           // [F][6] theta, cx, cy, size, cos(theta), sin(theta) (host libm)
+  int nfaces, in_size;
   float* mesh_out;                             // [F][1404] absolute pixels
   double* score_out;                           // [F]
+  double* eye_corners;                         // [F][8] mesh points 33, 133, 362, 263 (x, y) in f64 (eyeRoisFromMesh input)
 };
 void launch_mesh_post(const MeshPostP& p, cudaStream_t s);
+
+struct IrisPostP {
+  const float* contours; long long contours_istride;   // [2F][213] eye contour + brow points of each eye crop (input-pixel units)
+  const float* iris; long long iris_istride;           // [2F][15]  iris points
+  const double* roi;                                   // [2F][6] theta, cx, cy, size, cos, sin per eye (even = left, odd = right/flipped)
+  int nfaces, in_size;
+  double img_w, img_h;
+  float* iris_out;                                     // [F][456] 76 points of the left eye then 76 of the right, absolute pixels
+  double* eye_kp;                                      // [F][4] iris-refined leftEye / rightEye keypoints, normalised
+};
+void launch_iris_post(const IrisPostP& p, cudaStream_t s);
 
 }  // namespace fdt

@@ -2,9 +2,9 @@
 // operation by operation exactly like the reference's Dart doubles / OpenCV's C++:
 //   k_decode_nms       threshold -> ordered compaction -> decode -> sort -> weighted NMS ->
 //                      letterbox removal -> gates   (one block per image)
-//   k_build_face_list  faces of a chunk -> flat ROI list + inverse affine maps
-//   k_warp_affine      cv::warpAffine(INTER_LINEAR, BORDER_CONSTANT 0) into 192x192 BGR crops
+//   k_warp_affine      cv::warpAffine(INTER_LINEAR, BORDER_CONSTANT 0) into square BGR crops (192 face / 64 eye)
 //   k_mesh_post        _unpackLandmarks + transformMeshToAbsolute + face-flag sigmoid
+//   k_iris_post        _unpackLandmarks(clamp: false) + transformIrisNormToAbsolute + iris-centre eye keypoints
 #include "fdt_math.h"
 #include "kernels.h"
 
@@ -14,14 +14,9 @@ namespace {
 constexpr int kDecodeThreads = 128;
 constexpr int kMaxDet = 100;          // weightedNms maxDet (lib/src/util/helpers.dart:187)
 constexpr double kRawScoreLimit = 100.0;  // lib/src/shared/face_model_config.dart:49
+constexpr int kTaken = -(1 << 30);        // s_order entry of a candidate already merged into an emitted cluster
 
 struct NmsOut { double box[4]; double score; int cand; };
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 
 __global__ void __launch_bounds__(kDecodeThreads) k_decode_nms(DecodeP p) {
   extern __shared__ __align__(16) unsigned char dsm[];
@@ -33,7 +28,6 @@ __global__ void __launch_bounds__(kDecodeThreads) k_decode_nms(DecodeP p) {
   unsigned char* s_alive = reinterpret_cast<unsigned char*>(s_order + N);  // [N]
   __shared__ int s_wcnt[kDecodeThreads / 32];
   __shared__ int s_n, s_nvalid, s_top, s_pos;
-  __shared__ double s_red[kDecodeThreads / 32][5];
   __shared__ NmsOut s_out[kMaxDet];
   __shared__ fdt_face s_face[kMaxDet];
   __shared__ unsigned char s_pass[kMaxDet];
@@ -46,22 +40,30 @@ __global__ void __launch_bounds__(kDecodeThreads) k_decode_nms(DecodeP p) {
   __syncthreads();
 
   // 1. candidates: raw >= logit(minScore), ascending anchor order (_collectCandidateScores)
-  for (int base = 0; base < N; base += kDecodeThreads) {
-    int i = base + tid;
-    bool flag = i < N && (double)scores[i] >= p.raw_thresh;
-    unsigned bal = __ballot_sync(0xffffffffu, flag);
-    if (lane == 0) s_wcnt[warp] = __popc(bal);
+  const double* pre = p.pre ? p.pre + (size_t)b * N * 17 : nullptr;
+  if (pre) {
+    // test entry (fdt_debug_nms): the N rows are detections already decoded by the caller
+    for (int c = tid; c < N; c += kDecodeThreads) s_idx[c] = c;
+    if (tid == 0) s_n = N;
     __syncthreads();
-    int woff = 0, tot = 0;
+  } else {
+    for (int base = 0; base < N; base += kDecodeThreads) {
+      int i = base + tid;
+      bool flag = i < N && (double)scores[i] >= p.raw_thresh;
+      unsigned bal = __ballot_sync(0xffffffffu, flag);
+      if (lane == 0) s_wcnt[warp] = __popc(bal);
+      __syncthreads();
+      int woff = 0, tot = 0;
 #pragma unroll
-    for (int w = 0; w < kDecodeThreads / 32; ++w) {
-      if (w < warp) woff += s_wcnt[w];
-      tot += s_wcnt[w];
+      for (int w = 0; w < kDecodeThreads / 32; ++w) {
+        if (w < warp) woff += s_wcnt[w];
+        tot += s_wcnt[w];
+      }
+      if (flag) s_idx[s_n + woff + __popc(bal & ((1u << lane) - 1u))] = i;
+      __syncthreads();
+      if (tid == 0) s_n += tot;
+      __syncthreads();
     }
-    if (flag) s_idx[s_n + woff + __popc(bal & ((1u << lane) - 1u))] = i;
-    __syncthreads();
-    if (tid == 0) s_n += tot;
-    __syncthreads();
   }
   const int n = s_n;
   if (p.cand_n) {
@@ -72,15 +74,28 @@ __global__ void __launch_bounds__(kDecodeThreads) k_decode_nms(DecodeP p) {
   // 2. score + decode (+ degenerate-box filter, score >= kMinScore filter)
   for (int c = tid; c < n; c += kDecodeThreads) {
     int i = s_idx[c];
-    double sc = sigmoid_clipped((double)scores[i], kRawScoreLimit);
-    double box[4], kp[12];
-    decode_box(boxes + (size_t)i * 16, p.anchors[2 * i], p.anchors[2 * i + 1], (double)p.input_h, box, kp);
+    double sc, box[4], kp[12];
+    if (pre) {
+      for (int k = 0; k < 4; ++k) box[k] = pre[(size_t)i * 17 + k];
+      sc = pre[(size_t)i * 17 + 4];
+      for (int k = 0; k < 12; ++k) kp[k] = pre[(size_t)i * 17 + 5 + k];
+    } else {
+      sc = sigmoid_clipped((double)scores[i], kRawScoreLimit);
+      decode_box(boxes + (size_t)i * 16, p.anchors[2 * i], p.anchors[2 * i + 1], (double)p.input_h, box, kp);
+    }
     bool valid = !(box[2] <= box[0] || box[3] <= box[1]) && sc >= p.score_thresh;
     s_score[c] = sc;
     s_box[4 * c + 0] = box[0]; s_box[4 * c + 1] = box[1];
     s_box[4 * c + 2] = box[2]; s_box[4 * c + 3] = box[3];
     s_alive[c] = valid ? 1 : 0;
     if (valid) atomicAdd(&s_nvalid, 1);
+    if (p.dbg_dec) {
+      double* d = p.dbg_dec + ((size_t)b * N + c) * 18;
+      for (int k = 0; k < 4; ++k) d[k] = box[k];
+      d[4] = sc;
+      for (int k = 0; k < 12; ++k) d[5 + k] = kp[k];
+      d[17] = valid ? 1.0 : 0.0;
+    }
   }
   __syncthreads();
   const int nvalid = s_nvalid;
@@ -105,7 +120,7 @@ __global__ void __launch_bounds__(kDecodeThreads) k_decode_nms(DecodeP p) {
   while (nout < kMaxDet) {
     if (tid == 0) {
       int pos = s_pos;
-      while (pos < nvalid && !s_alive[s_order[pos]]) ++pos;
+      while (pos < nvalid && (s_order[pos] < 0 || !s_alive[s_order[pos]])) ++pos;
       s_pos = pos;
       s_top = pos < nvalid ? s_order[pos] : -1;
     }
@@ -113,32 +128,28 @@ __global__ void __launch_bounds__(kDecodeThreads) k_decode_nms(DecodeP p) {
     const int top = s_top, pos0 = s_pos;
     if (top < 0) break;
     double tb[4] = {s_box[4 * top], s_box[4 * top + 1], s_box[4 * top + 2], s_box[4 * top + 3]};
-    double acc[5] = {0, 0, 0, 0, 0};
+    // cluster membership in parallel (s_order of a cluster member is overwritten by -1 - candidate) ...
     for (int j = pos0 + tid; j < nvalid; j += kDecodeThreads) {
       int c = s_order[j];
-      if (!s_alive[c]) continue;
-      bool in = (c == top) || box_iou(&s_box[4 * c], tb) > p.iou_thresh;
-      if (in) {
-        double sc = s_score[c];
-        acc[0] += sc;
-        acc[1] += s_box[4 * c + 0] * sc;
-        acc[2] += s_box[4 * c + 1] * sc;
-        acc[3] += s_box[4 * c + 2] * sc;
-        acc[4] += s_box[4 * c + 3] * sc;
-        s_alive[c] = 0;
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      double v = warp_sum(acc[k]);
-      if (lane == 0) s_red[warp][k] = v;
+      if (c < 0 || !s_alive[c]) continue;
+      if ((c == top) || box_iou(&s_box[4 * c], tb) > p.iou_thresh) { s_alive[c] = 0; s_order[j] = -1 - c; }
     }
     __syncthreads();
+    // ... and the score-weighted sum by ONE thread in sorted order, exactly the reference's sequential f64 accumulation
+    // (a tree reduction would round differently): clusters hold a handful of boxes
     if (tid == 0) {
-      double t[5];
-      for (int k = 0; k < 5; ++k) {
-        t[k] = 0;
-        for (int w = 0; w < kDecodeThreads / 32; ++w) t[k] += s_red[w][k];
+      double t[5] = {0, 0, 0, 0, 0};
+      for (int j = pos0; j < nvalid; ++j) {
+        int e = s_order[j];
+        if (e >= 0 || e == kTaken) continue;
+        int c = -1 - e;
+        s_order[j] = kTaken;
+        double sc = s_score[c];
+        t[0] += sc;
+        t[1] += s_box[4 * c + 0] * sc;
+        t[2] += s_box[4 * c + 1] * sc;
+        t[3] += s_box[4 * c + 2] * sc;
+        t[4] += s_box[4 * c + 3] * sc;
       }
       NmsOut& o = s_out[nout];
       o.box[0] = t[1] / t[0]; o.box[1] = t[2] / t[0];
@@ -158,7 +169,8 @@ __global__ void __launch_bounds__(kDecodeThreads) k_decode_nms(DecodeP p) {
     const NmsOut& o = s_out[f];
     int i = s_idx[o.cand];
     double box[4], kp[12];
-    decode_box(boxes + (size_t)i * 16, p.anchors[2 * i], p.anchors[2 * i + 1], (double)p.input_h, box, kp);
+    if (pre) { for (int k = 0; k < 12; ++k) kp[k] = pre[(size_t)i * 17 + 5 + k]; }
+    else decode_box(boxes + (size_t)i * 16, p.anchors[2 * i], p.anchors[2 * i + 1], (double)p.input_h, box, kp);
     fdt_face fc;
     fc.xmin = (o.box[0] - p.pad_l) / sx;
     fc.ymin = (o.box[1] - p.pad_t) / sy;
@@ -179,7 +191,7 @@ __global__ void __launch_bounds__(kDecodeThreads) k_decode_nms(DecodeP p) {
     }
     double theta, cx, cy, size;
     face_alignment(fc.keypoints, p.img_w, p.img_h, &theta, &cx, &cy, &size);
-    if (!(dart_round(size) > 0)) pass = false;
+    if (!p.skip_roi && !(dart_round(size) > 0)) pass = false;
     s_face[f] = fc;
     s_pass[f] = pass ? 1 : 0;
   }
@@ -198,52 +210,19 @@ __global__ void __launch_bounds__(kDecodeThreads) k_decode_nms(DecodeP p) {
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void k_build_face_list(FaceListP p) {
-  const int skip = p.skip;
-  __shared__ int s_total;
-  if (threadIdx.x == 0) {
-    int run = 0;
-    for (int b = 0; b < p.B; ++b) run += p.counts[b];
-    s_total = run;
-    int t = run - skip;
-    if (t < 0) t = 0;
-    if (t > p.cap) { t = p.cap; *p.overflow = 1; }
-    *p.total = t;
-  }
-  __syncthreads();
-  for (int b = threadIdx.x; b < p.B; b += blockDim.x) {
-    int base = 0;
-    for (int i = 0; i < b; ++i) base += p.counts[i];
-    for (int j = 0; j < p.counts[b]; ++j) {
-      int f = base + j - skip;
-      if (f < 0 || f >= p.cap) continue;
-      const fdt_face& fc = p.faces[(size_t)b * p.max_faces + j];
-      double theta, cx, cy, size;
-      face_alignment(fc.keypoints, p.img_w, p.img_h, &theta, &cx, &cy, &size);
-      p.face_img[f] = b;
-      p.face_slot[f] = j;
-      p.align[4 * f + 0] = theta; p.align[4 * f + 1] = cx;
-      p.align[4 * f + 2] = cy; p.align[4 * f + 3] = size;
-      // face path: extractAlignedSquare(image, cx, cy, size, -theta, outSize: 192)
-      // (lib/src/isolate/face_detector_core.dart:488-494)
-      if (!aligned_square_inverse(cx, cy, size, -theta, p.out_size, &p.affine[6 * f]))
-        for (int k = 0; k < 6; ++k) p.affine[6 * f + k] = 0.0;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 __device__ __forceinline__ long long sat_round_ll(double v) { return (long long)rint(v); }
 
+// One thread per output pixel; blockIdx.y = crop.  The per-row / per-column fixed-point terms of
+// imgproc/imgwarp.cpp WarpAffineInvoker (AB_BITS = 10, INTER_BITS = 5) are evaluated per pixel: two f64 rint each.
 __global__ void k_warp_affine(WarpP p) {
   const int f = blockIdx.y;
-  if (f >= p.nfaces) return;
+  if (f >= p.ncrops) return;
   const int S = p.out_size;
   const double* A = p.affine + 6 * f;
-  const uint8_t* src = p.frames + (size_t)p.face_img[f] * p.frame_stride;
+  const uint8_t* src = p.frames + (size_t)p.crop_img[f] * p.frame_stride;
+  const bool flip = p.flip_odd && (f & 1);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S * S; i += gridDim.x * blockDim.x) {
     int y = i / S, x = i - y * S;
-    // imgproc/imgwarp.cpp WarpAffineInvoker: AB_BITS=10, INTER_BITS=5
     long long adelta = sat_round_ll(A[0] * x * 1024.0);
     long long bdelta = sat_round_ll(A[3] * x * 1024.0);
     long long X0 = sat_round_ll((A[1] * y + A[2]) * 1024.0) + 16;
@@ -273,7 +252,8 @@ __global__ void k_warp_affine(WarpP p) {
       int v = (acc[c] + 16384) >> 15;
       o[c] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
     }
-    reinterpret_cast<uchar4*>(p.crops)[(size_t)f * S * S + i] = make_uchar4(o[0], o[1], o[2], 0);
+    const int xo = flip ? S - 1 - x : x;
+    reinterpret_cast<uchar4*>(p.crops)[(size_t)f * S * S + (size_t)y * S + xo] = make_uchar4(o[0], o[1], o[2], 0);
   }
 }
 
@@ -282,9 +262,9 @@ __global__ void k_mesh_post(MeshPostP p) {
   const int f = blockIdx.x;
   if (f >= p.nfaces) return;
   const float* raw = p.raw + (size_t)f * p.raw_istride;
-  const double theta = p.align[4 * f], cx = p.align[4 * f + 1], cy = p.align[4 * f + 2], size = p.align[4 * f + 3];
-  // transformMeshToAbsolute (lib/src/shared/face_geometry.dart:48-73)
-  const double ct = cos(theta), st = sin(theta);
+  const double cx = p.roi[6 * f + 1], cy = p.roi[6 * f + 2], size = p.roi[6 * f + 3];
+  // transformMeshToAbsolute (lib/src/shared/face_geometry.dart:48-73); cos / sin come from the host libm
+  const double ct = p.roi[6 * f + 4], st = p.roi[6 * f + 5];
   const double sct = size * ct, sst = size * st;
   const double tx = cx - 0.5 * sct + 0.5 * sst;
   const double ty = cy - 0.5 * sst - 0.5 * sct;
@@ -296,13 +276,63 @@ __global__ void k_mesh_post(MeshPostP p) {
     double z = (double)raw[3 * i + 2] * inv_w * inv_sx;
     x = x < 0.0 ? 0.0 : (x > 1.0 ? 1.0 : x);
     y = y < 0.0 ? 0.0 : (y > 1.0 ? 1.0 : y);
+    const double ax = tx + sct * x - sst * y, ay = ty + sst * x + sct * y;
     float* o = p.mesh_out + (size_t)f * FDT_MESH_FLOATS + 3 * i;
-    o[0] = (float)(tx + sct * x - sst * y);
-    o[1] = (float)(ty + sst * x + sct * y);
+    o[0] = (float)ax;
+    o[1] = (float)ay;
     o[2] = (float)(z * size);
+    // eyeRoisFromMesh reads the f64 points 33/133 (left) and 362/263 (right) (face_geometry.dart:155-168)
+    if (p.eye_corners) {
+      const int k = i == 33 ? 0 : (i == 133 ? 1 : (i == 362 ? 2 : (i == 263 ? 3 : -1)));
+      if (k >= 0) { p.eye_corners[8 * f + 2 * k] = ax; p.eye_corners[8 * f + 2 * k + 1] = ay; }
+    }
   }
   if (threadIdx.x == 0)
     p.score_out[f] = sigmoid_clipped((double)p.flag[(size_t)f * p.flag_istride], kRawScoreLimit);
+}
+
+// ------------------------------------------------------------------------------------------
+// One block per face, 152 threads = 2 eyes x 76 points.  IrisLandmark.call unpacks every output in order
+// (71 contour points then 5 iris points, clamp: false, z untouched; lib/src/models/iris_landmark.dart:328-360),
+// transformIrisNormToAbsolute maps them into the frame and un-mirrors the right eye
+// (lib/src/shared/face_geometry.dart:109-125); the detector's eye keypoints are replaced by the iris point closest
+// to the iris centroid (irisCenterFromPoints, face_types.dart:976-997; face_detector_core.dart:356-373).
+__global__ void k_iris_post(IrisPostP p) {
+  const int f = blockIdx.x;
+  if (f >= p.nfaces) return;
+  __shared__ double s_xy[2][5][2];
+  const int t = threadIdx.x;
+  if (t < 2 * 76) {
+    const int eye = t / 76, i = t - eye * 76;
+    const int e = 2 * f + eye;
+    const float* src = i < 71 ? p.contours + (size_t)e * p.contours_istride + 3 * i
+                              : p.iris + (size_t)e * p.iris_istride + 3 * (i - 71);
+    const double inv = 1.0 / p.in_size;
+    const double x = ((double)src[0] * inv - 0.0) * (1.0 / (1.0 - 0.0));
+    const double y = ((double)src[1] * inv - 0.0) * (1.0 / (1.0 - 0.0));
+    const double z = (double)src[2];
+    const double cx = p.roi[6 * e + 1], cy = p.roi[6 * e + 2], s = p.roi[6 * e + 3], ct = p.roi[6 * e + 4], st = p.roi[6 * e + 5];
+    const double px = eye ? (1.0 - x) : x;
+    const double lx2 = (px - 0.5) * s, ly2 = (y - 0.5) * s;
+    const double ax = cx + lx2 * ct - ly2 * st, ay = cy + lx2 * st + ly2 * ct;
+    float* o = p.iris_out + (size_t)f * FDT_IRIS_FLOATS + 3 * t;
+    o[0] = (float)ax; o[1] = (float)ay; o[2] = (float)z;
+    if (i >= 71) { s_xy[eye][i - 71][0] = ax; s_xy[eye][i - 71][1] = ay; }
+  }
+  __syncthreads();
+  if (t < 2) {
+    double mx = 0, my = 0;
+    for (int k = 0; k < 5; ++k) { mx += s_xy[t][k][0]; my += s_xy[t][k][1]; }
+    mx /= 5; my /= 5;
+    int best = 0;
+    double bd = INFINITY;
+    for (int k = 0; k < 5; ++k) {
+      const double dx = s_xy[t][k][0] - mx, dy = s_xy[t][k][1] - my, d = dx * dx + dy * dy;
+      if (d < bd) { bd = d; best = k; }
+    }
+    p.eye_kp[4 * f + 2 * t] = s_xy[t][best][0] / p.img_w;
+    p.eye_kp[4 * f + 2 * t + 1] = s_xy[t][best][1] / p.img_h;
+  }
 }
 
 }  // namespace
@@ -317,19 +347,20 @@ void launch_decode_nms(const DecodeP& p, int B, cudaStream_t s) {
   k_decode_nms<<<B, kDecodeThreads, smem, s>>>(p);
 }
 
-void launch_build_face_list(const FaceListP& p, cudaStream_t s) {
-  k_build_face_list<<<1, 256, 0, s>>>(p);
-}
-
 void launch_warp_affine(const WarpP& p, cudaStream_t s) {
-  if (p.nfaces <= 0) return;
-  dim3 grid((p.out_size * p.out_size + 255) / 256, p.nfaces);
+  if (p.ncrops <= 0) return;
+  dim3 grid((p.out_size * p.out_size + 255) / 256, p.ncrops);
   k_warp_affine<<<grid, 256, 0, s>>>(p);
 }
 
 void launch_mesh_post(const MeshPostP& p, cudaStream_t s) {
   if (p.nfaces <= 0) return;
   k_mesh_post<<<p.nfaces, 128, 0, s>>>(p);
+}
+
+void launch_iris_post(const IrisPostP& p, cudaStream_t s) {
+  if (p.nfaces <= 0) return;
+  k_iris_post<<<p.nfaces, 160, 0, s>>>(p);
 }
 
 }  // namespace fdt

@@ -25,7 +25,7 @@ struct PTensor {
 };
 
 enum StepKind { kStepNormalize, kStepNaiveConv, kStepGemmConv, kStepDwPw, kStepAdd, kStepAct, kStepPadC,
-                kStepMaxPool, kStepResize, kStepStem, kStepDwPwTc, kStepStemTc, kStepBlockWs, kStepStemWs };
+                kStepMaxPool, kStepResize, kStepStem, kStepDwPwTc, kStepStemTc, kStepBlockWs, kStepStemWs, kStepTailWs, kStepFcTc };
 
 struct PStep {
   StepKind kind = kStepAct;
@@ -45,6 +45,7 @@ struct PStep {
   int no = 0, KSo = 0, out_stage_floats = 0;           // TMA-store epilogue (k_block_ws)
   int out2 = -1, c1 = 0, c2 = 0;                        // two heads in one launch: columns [0,c1) -> out, [c1,c1+c2) -> out2   // warp-specialised variant: input stages, A buffers, depthwise warps
   int fh = 1, fw = 1, align = 0, half = 0;
+  std::vector<int> extra_out;   // further tensors the step materialises (k_tail_ws: every graph output of the fused tail)
   double macs = 0;  // per image
 };
 

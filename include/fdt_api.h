@@ -62,7 +62,8 @@ typedef enum fdt_model {
 typedef enum fdt_mode {
   FDT_MODE_FAST = 0,     /* detector + 6 keypoints                            */
   FDT_MODE_STANDARD = 1, /* + aligned crop + 468-point mesh                   */
-  FDT_MODE_FULL = 2      /* reference adds iris/blendshapes: not on this path -> FDT_ERR_UNSUPPORTED */
+  FDT_MODE_FULL = 2      /* + two eye crops + iris_landmark: 152 iris/eye-contour points, iris-refined eye keypoints
+                            (the reference's default mode; its blendshape classifier is outside this path)      */
 } fdt_mode;
 
 /* cv MatType values accepted by detectFacesFromMatBytes (lib/src/face_detector.dart:588-594;
@@ -73,6 +74,7 @@ enum { FDT_MEM_HOST = 0, FDT_MEM_DEVICE = 1 };
 
 enum { FDT_MAX_FACES = 100 };      /* weightedNms maxDet, lib/src/util/helpers.dart:187 */
 enum { FDT_MESH_POINTS = 468, FDT_MESH_FLOATS = 1404 };
+enum { FDT_IRIS_POINTS = 152, FDT_IRIS_FLOATS = 456 }; /* 76 per eye: 71 contour + 5 iris (face_detector.dart:1888-1893) */
 
 /* Named arguments of FaceDetector.create (lib/src/face_detector.dart:84-101) that touch the path. */
 typedef struct fdt_config {
@@ -98,6 +100,9 @@ typedef struct fdt_face {
   double mesh_score;         /* sigmoid(face flag); NaN when no mesh was computed            */
   int32_t has_mesh;
   int32_t anchor_index;      /* anchor of the top detection of the NMS cluster (parity aid)  */
+  int32_t has_iris;          /* 1: iris points were computed and the eye keypoints are iris-refined
+                                (face_detector_core.dart:356-373)                             */
+  int32_t reserved;
 } fdt_face;
 
 FDT_EXPORT void fdt_default_config(fdt_config* cfg);
@@ -108,6 +113,16 @@ FDT_EXPORT void fdt_default_config(fdt_config* cfg);
  * generates the SSD anchors.  mesh_tflite may be NULL (fast mode only). */
 FDT_EXPORT int32_t fdt_create(const fdt_config* cfg, const uint8_t* det_tflite, size_t det_len,
                               const uint8_t* mesh_tflite, size_t mesh_len, fdt_handle** out);
+
+/* As fdt_create, plus the iris model (iris_landmark.tflite; IrisLandmark.createFromBuffer x2,
+ * lib/src/isolate/face_detector_core.dart:172-190; NULL = no FDT_MODE_FULL) and an optional device list:
+ * with num_devices > 1 the handle owns one replica per listed CUDA device and every detect call splits its
+ * batch contiguously across them (one host thread, streams and staging per device, results in frame order;
+ * no collective: frames are independent).  The reference's closest analogue is the interpreter pool inside
+ * one detector object (RoundRobinPool, face_detector_core.dart:151-166).  devices == NULL: cfg->device only. */
+FDT_EXPORT int32_t fdt_create_ex(const fdt_config* cfg, const uint8_t* det_tflite, size_t det_len,
+                                 const uint8_t* mesh_tflite, size_t mesh_len, const uint8_t* iris_tflite,
+                                 size_t iris_len, const int32_t* devices, int32_t num_devices, fdt_handle** out);
 
 /* FaceDetector.dispose (lib/src/face_detector.dart:1061-1081). */
 FDT_EXPORT int32_t fdt_destroy(fdt_handle* h);
@@ -120,18 +135,20 @@ FDT_EXPORT int32_t fdt_destroy(fdt_handle* h);
  * (lib/src/isolate/face_detector_core.dart:215-394, :461-524).
  *   out_faces : [batch * max_faces] fdt_face      (host)
  *   out_counts: [batch] int32                     (host)
- *   out_mesh  : [batch * max_faces * 1404] float  (host; absolute pixels x,y,z) or NULL */
+ *   out_mesh  : [batch * max_faces * 1404] float  (host; absolute pixels x,y,z) or NULL
+ *   out_iris  : [batch * max_faces * 456] float   (host; FDT_MODE_FULL; absolute pixels x,y + raw z) or NULL
+ * Only the first out_counts[b] slots of frame b are written. */
 FDT_EXPORT int32_t fdt_detect_batch(fdt_handle* h, const uint8_t* frames, int32_t batch, int32_t width,
                                     int32_t height, int32_t row_stride, int32_t mat_type, int32_t mode,
                                     int32_t mem_kind, fdt_face* out_faces, int32_t* out_counts,
-                                    float* out_mesh);
+                                    float* out_mesh, float* out_iris);
 
 /* detectFacesFromMatBytes (lib/src/face_detector.dart:588-609): one packed frame of
  * `nbytes` bytes; FDT_ERR_SIZE_MISMATCH when nbytes != width*height*channels
  * (matFromPackedBytes, lib/src/util/helpers.dart:432-450). */
 FDT_EXPORT int32_t fdt_detect_one(fdt_handle* h, const uint8_t* bytes, size_t nbytes, int32_t width,
                                   int32_t height, int32_t mat_type, int32_t mode, fdt_face* out_faces,
-                                  int32_t* out_count, float* out_mesh);
+                                  int32_t* out_count, float* out_mesh, float* out_iris);
 
 /* Throughput variant used by the benchmark: frames already resident in device memory, results
  * left in device memory (no host transfer, no sync); `*d_faces` / `*d_counts` receive internal
@@ -183,6 +200,27 @@ FDT_EXPORT int32_t fdt_debug_get_tensor(fdt_handle* h, int32_t which, int32_t tf
  * mesh outputs f32 [n,1404] + face-flag logits [n], for the first n faces of the last call. */
 FDT_EXPORT int32_t fdt_debug_get_mesh_stage(fdt_handle* h, int32_t n, uint8_t* out_crops,
                                             float* out_raw1404, float* out_flag, int32_t* out_n);
+/* Iris stage taps for the first n faces that reached it in the last call (last pass of the last chunk):
+ * u8 [2n,64,64,3] BGR eye crops (left, right-mirrored), the eye ROIs [2n,4] = cx, cy, size, theta
+ * (eyeRoisFromMesh, face_geometry.dart:155-168), raw outputs f32 [2n,213] contours + [2n,15] iris. */
+FDT_EXPORT int32_t fdt_debug_get_iris_stage(fdt_handle* h, int32_t n, uint8_t* out_crops, double* out_rois,
+                                            float* out_contours, float* out_iris, int32_t* out_n);
+/* Detector post-processing on caller-supplied tensors (host pointers), through the same k_decode_nms the
+ * pipeline runs: crafted inputs and the reference's own unit-test vectors reach the device this way.
+ *  fdt_debug_decode: raw heads boxes [n_images, N, 16] + scores [n_images, N] (Interpreter outputs 0 / 1),
+ *    anchors_xy [N, 2] (NULL: the handle's), scale = model input height, pad4 = top, bottom, left, right
+ *    (normalised; NULL = none).  Outputs faces [n_images, FDT_MAX_FACES] + counts, and optionally the decoded
+ *    candidates before NMS: out_dec [n_images, N, 18] rows (box4, score, kp12, kept) in ascending anchor order
+ *    + out_ndec [n_images] (_collectCandidateScores + _decodeBoxesForIndices + _toDetectionsFiltered,
+ *    face_detection_model.dart:431-516; lib/src/web/detection_decode.dart:44-88).
+ *  fdt_debug_nms: detections [n, 17] rows (xmin, ymin, xmax, ymax, score, kp12) -> weightedNms +
+ *    letterbox removal (testNms / testDetectionLetterboxRemoval, helpers.dart:101-136, :183-221). */
+FDT_EXPORT int32_t fdt_debug_decode(fdt_handle* h, const float* raw_boxes, const float* raw_scores,
+                                    const double* anchors_xy, int32_t n_images, int32_t num_anchors, double scale,
+                                    double score_thresh, double iou_thresh, const double* pad4,
+                                    fdt_face* out_faces, int32_t* out_counts, double* out_dec, int32_t* out_ndec);
+FDT_EXPORT int32_t fdt_debug_nms(fdt_handle* h, const double* dets17, int32_t n, double score_thresh,
+                                 double iou_thresh, const double* pad4, fdt_face* out_faces, int32_t* out_count);
 /* Number of kernel launches issued by the last detect call (bench.py "gpu_launches"). */
 FDT_EXPORT int64_t fdt_last_launch_count(fdt_handle* h);
 /* Bytes copied host->device by the last detect call.  In fast mode only the source rows the
@@ -191,7 +229,7 @@ FDT_EXPORT int64_t fdt_last_launch_count(fdt_handle* h);
 FDT_EXPORT int64_t fdt_last_h2d_bytes(fdt_handle* h);
 /* Device time in ms of the named stage summed over the last call when stage timing was enabled
  * with fdt_set_stage_timing(h,1) (adds cudaEvent records; off by default).
- * stage: 0 letterbox, 1 conv stack, 2 decode+nms, 3 warp, 4 mesh net, 5 mesh post */
+ * stage: 0 letterbox, 1 conv stack, 2 decode+nms, 3 warp, 4 mesh net, 5 mesh post, 6 eye warp, 7 iris net, 8 iris post */
 FDT_EXPORT int32_t fdt_set_stage_timing(fdt_handle* h, int32_t enable);
 FDT_EXPORT int32_t fdt_get_stage_ms(fdt_handle* h, int32_t stage, float* ms, int32_t* launches);
 
@@ -210,6 +248,22 @@ FDT_EXPORT int32_t fdt_profile_chunk(fdt_handle* h, const uint8_t* d_frames, int
                                      float* out_ms, int32_t capacity, int32_t* out_launches);
 FDT_EXPORT int32_t fdt_get_step_info(fdt_handle* h, int32_t launch, char* kernel, char* tensor, int32_t str_cap,
                                      double* macs_per_image, double* bytes_per_image);
+/* Same for the mesh (which = 1) and iris (which = 2) nets: `repeats` passes over the first n crops left in the
+ * stage buffers by the last standard / full call; out_ms[i] = mean duration of plan step i;
+ * fdt_get_net_step_info describes step i of that plan. */
+FDT_EXPORT int32_t fdt_profile_net(fdt_handle* h, int32_t which, int32_t n, int32_t repeats, float* out_ms,
+                                   int32_t capacity, int32_t* out_steps);
+FDT_EXPORT int32_t fdt_get_net_step_info(fdt_handle* h, int32_t which, int32_t step, char* kernel, char* tensor,
+                                         int32_t str_cap, double* macs_per_image, double* bytes_per_image);
+/* extractAlignedSquare on the device (lib/src/util/helpers.dart:583-625) for caller-supplied ROIs of ONE host frame:
+ * rois [n, 4] = cx, cy, size, theta_arg (the function's own `theta` argument: the face path passes -theta, the eye
+ * path +theta, the embedding path -theta with out_size 112, face_detector_core.dart:433-440).  out_crops u8
+ * [n, out_size, out_size, 3] BGR; out_ok[i] = 0 where round(size) <= 0 (the reference returns null there). */
+FDT_EXPORT int32_t fdt_extract_aligned_squares(fdt_handle* h, const uint8_t* frame, int32_t width, int32_t height,
+                                               int32_t row_stride, int32_t mat_type, const double* rois, int32_t n,
+                                               int32_t out_size, uint8_t* out_crops, int32_t* out_ok);
+/* Number of CUDA devices the handle spans (1 unless created with a device list). */
+FDT_EXPORT int32_t fdt_num_devices(fdt_handle* h);
 
 /* ---- host-only helpers (no CUDA device needed; used by the CPU test-suite and by bindings) ----
  * fdt_host_anchors        : generateAnchors for a FaceDetectionModel; returns the anchor count
@@ -220,7 +274,13 @@ FDT_EXPORT int32_t fdt_get_step_info(fdt_handle* h, int32_t launch, char* kernel
  * fdt_host_decode_box     : _decodeBoxesForIndices for one anchor (face_detection_model.dart:431-467).
  * fdt_host_face_roi       : computeFaceAlignment + extractAlignedSquare's inverse affine map
  *                           (face_geometry.dart:17-45, helpers.dart:583-625); out10 =
- *                           theta,cx,cy,size, a00,a01,b0,a10,a11,b1; returns 0 when round(size) <= 0. */
+ *                           theta,cx,cy,size, a00,a01,b0,a10,a11,b1; returns 0 when round(size) <= 0.
+ * fdt_host_eye_rois       : eyeRoisFromMesh (face_geometry.dart:155-168) from the four eye-corner mesh points
+ *                           33, 133, 362, 263 (x,y absolute pixels) -> out8 = (cx, cy, size, theta) x {left, right}.
+ * fdt_host_embedding_roi  : computeEmbeddingAlignment (lib/src/models/face_embedding.dart:362-384) from the two
+ *                           eye points in pixels -> out4 = theta, cx, cy, size (the 112x112 embedding crop is
+ *                           extractAlignedSquare(cx, cy, size, -theta, 112); the MobileFaceNet model itself is
+ *                           not shipped by the reference).                                                  */
 FDT_EXPORT int32_t fdt_host_anchors(int32_t model, double* out_xy, int32_t capacity_pairs);
 FDT_EXPORT int32_t fdt_host_plan_describe(const uint8_t* tflite, size_t len, int32_t fuse_level, char* buf,
                                           size_t buf_len);
@@ -230,6 +290,8 @@ FDT_EXPORT int32_t fdt_host_decode_box(const float* raw16, double ax, double ay,
                                        double* out_kp12);
 FDT_EXPORT int32_t fdt_host_face_roi(const double* kp12, double img_w, double img_h, int32_t out_size,
                                      double* out10);
+FDT_EXPORT int32_t fdt_host_eye_rois(const double* corners8, double* out8);
+FDT_EXPORT int32_t fdt_host_embedding_roi(const double* left_eye_xy, const double* right_eye_xy, double* out4);
 
 FDT_EXPORT const char* fdt_last_error(fdt_handle* h); /* NULL handle -> last create error */
 FDT_EXPORT const char* fdt_version(void);

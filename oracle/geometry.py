@@ -1,7 +1,10 @@
 """ORACLE (test infrastructure, not product code).
 
-Restates lib/src/shared/face_geometry.dart:17-73 (alignment, mesh back-projection) and
-lib/src/util/helpers.dart:138-172 (_unpackLandmarks), all in float64 as Dart doubles.
+Restates lib/src/shared/face_geometry.dart:17-73 (alignment, mesh back-projection), :109-125
+(transformIrisNormToAbsolute), :155-168 (eyeRoisFromMesh), lib/src/util/helpers.dart:138-172
+(_unpackLandmarks), lib/src/shared/face_types.dart:976-997 (irisCenterFromPoints) and
+lib/src/models/face_embedding.dart:362-400 (embedding alignment + L2 normalisation), all in float64
+as Dart doubles.
 """
 from __future__ import annotations
 
@@ -61,3 +64,78 @@ def transform_mesh_to_absolute(lm_norm, cx, cy, size, theta):
     out[:, 1] = ty + sst * lm[:, 0] + sct * lm[:, 1]
     out[:, 2] = lm[:, 2] * size
     return out
+
+
+def eye_rois_from_mesh(mesh_abs):
+    """eyeRoisFromMesh (face_geometry.dart:155-168): [(cx, cy, size, theta)] for the left (33/133) and right
+    (362/263) eye from the absolute-pixel f64 mesh."""
+    def from_corners(a, b):
+        p0, p1 = mesh_abs[a], mesh_abs[b]
+        cx = (float(p0[0]) + float(p1[0])) * 0.5
+        cy = (float(p0[1]) + float(p1[1])) * 0.5
+        dx = float(p1[0]) - float(p0[0])
+        dy = float(p1[1]) - float(p0[1])
+        eye_dist = math.sqrt(dx * dx + dy * dy)
+        return (cx, cy, eye_dist * 2.3, math.atan2(dy, dx))
+    return [from_corners(33, 133), from_corners(362, 263)]
+
+
+def transform_iris_norm_to_absolute(lm_norm, roi, is_right: bool):
+    """transformIrisNormToAbsolute (face_geometry.dart:109-125); roi = (cx, cy, size, theta)."""
+    cx, cy, s, theta = roi
+    ct, st = math.cos(theta), math.sin(theta)
+    out = []
+    for p in lm_norm:
+        px = (1.0 - float(p[0])) if is_right else float(p[0])
+        lx2 = (px - 0.5) * s
+        ly2 = (float(p[1]) - 0.5) * s
+        out.append([cx + lx2 * ct - ly2 * st, cy + lx2 * st + ly2 * ct, float(p[2])])
+    return np.array(out, np.float64).reshape(-1, 3)
+
+
+def iris_center_from_points(pts):
+    """irisCenterFromPoints (face_types.dart:976-997): the point closest to the centroid (first on ties)."""
+    pts = [tuple(float(v) for v in p) for p in pts]
+    if not pts:
+        return (0.0, 0.0, 0.0)
+    if len(pts) == 1:
+        return pts[0]
+    cx = cy = 0.0
+    for p in pts:
+        cx += p[0]
+        cy += p[1]
+    cx /= len(pts)
+    cy /= len(pts)
+    best, best_d = 0, float("inf")
+    for i, p in enumerate(pts):
+        dx, dy = p[0] - cx, p[1] - cy
+        d = dx * dx + dy * dy
+        if d < best_d:
+            best_d, best = d, i
+    return pts[best]
+
+
+def compute_embedding_alignment(left_eye, right_eye):
+    """computeEmbeddingAlignment (face_embedding.dart:362-384) -> (theta, cx, cy, size)."""
+    dx = float(right_eye[0]) - float(left_eye[0])
+    dy = float(right_eye[1]) - float(left_eye[1])
+    theta = math.atan2(dy, dx)
+    eye_dist = math.sqrt(dx * dx + dy * dy)
+    size = eye_dist * 2.5
+    ecx = (float(left_eye[0]) + float(right_eye[0])) * 0.5
+    ecy = (float(left_eye[1]) + float(right_eye[1])) * 0.5
+    ct, st = math.cos(theta), math.sin(theta)
+    oy = size * 0.15
+    return theta, ecx - oy * st, ecy + oy * ct, size
+
+
+def normalize_embedding(e):
+    """_normalizeEmbeddingImpl (face_embedding.dart:386-400): f64 norm accumulated in order, f32 result."""
+    e = np.asarray(e, np.float32)
+    norm = 0.0
+    for v in e:
+        norm += float(v) * float(v)
+    norm = math.sqrt(norm)
+    if norm > 0:
+        return np.array([float(v) / norm for v in e], np.float32)
+    return e

@@ -27,7 +27,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 def test_struct_layouts_match_header():
     from face_detection_tflite_b200 import _ffi
-    assert C.sizeof(_ffi.FdtFace) == 18 * 8 + 8      # static_assert in csrc/fdt_api.cu
+    assert C.sizeof(_ffi.FdtFace) == 18 * 8 + 16     # static_assert in csrc/fdt_api.cu
     assert C.sizeof(_ffi.FdtConfig) == 6 * 4 + 3 * 8
 
 
@@ -59,7 +59,7 @@ def test_create_argument_validation(lib, model_bytes):
     assert lib.fdt_create(C.byref(cfg), d, len(d), None, 0, C.byref(h)) == _ffi.FDT_ERR_UNSUPPORTED
     cfg.model = 2
     assert lib.fdt_create(C.byref(cfg), None, 0, None, 0, C.byref(h)) == _ffi.FDT_ERR_BAD_ARG
-    assert lib.fdt_detect_batch(None, None, 0, 1, 1, 3, 16, 0, 0, None, None, None) == _ffi.FDT_ERR_NOT_READY
+    assert lib.fdt_detect_batch(None, None, 0, 1, 1, 3, 16, 0, 0, None, None, None, None) == _ffi.FDT_ERR_NOT_READY
 
 
 @pytest.mark.parametrize("model,name", [(0, "frontCamera"), (1, "backCamera"), (2, "shortRange"), (3, "full")])
