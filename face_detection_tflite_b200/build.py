@@ -27,6 +27,7 @@ SOURCES = {
     "kernels_tiled.cu": [],
     "kernels_tc.cu": [],
     "kernels_ws.cu": [],
+    "kernels_tail.cu": [],
     "kernels_pre.cu": [],
     # f64 geometry must be evaluated operation by operation (no fused multiply-add contraction)
     "kernels_post.cu": ["-fmad=false"],

@@ -8,6 +8,7 @@ namespace fdt {
 
 Engine::~Engine() {
   if (d_blob_) cudaFree(d_blob_);
+  for (TailLayerD* p : d_tail_) if (p) cudaFree(p);
 }
 
 bool Engine::init(const uint8_t* tflite, size_t len, int fuse_level, std::string* err, bool use_tc) {
@@ -19,6 +20,16 @@ bool Engine::init(const uint8_t* tflite, size_t len, int fuse_level, std::string
   if (cudaMemcpy(d_blob_, plan_.blob.data(), plan_.blob.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
     *err = "weight upload failed";
     return false;
+  }
+  d_tail_.assign(plan_.steps.size(), nullptr);
+  for (size_t i = 0; i < plan_.steps.size(); ++i) {
+    const PStep& st = plan_.steps[i];
+    if (st.kind != kStepTailWs) continue;
+    if (cudaMalloc(&d_tail_[i], st.tail.size() * sizeof(TailLayerD)) != cudaSuccess ||
+        cudaMemcpy(d_tail_[i], st.tail.data(), st.tail.size() * sizeof(TailLayerD), cudaMemcpyHostToDevice) != cudaSuccess) {
+      *err = "tail program upload failed";
+      return false;
+    }
   }
   return true;
 }
@@ -222,6 +233,23 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         }
         break;
       }
+      case kStepTailWs: {
+        TailP p;
+        TV iv = view(ctx, st.in);
+        p.in = iv.p; p.in_istride = iv.istride; p.H = iv.H; p.W = iv.W; p.CinS = iv.Cs;
+        p.blob = blob; p.layers = d_tail_[&st - plan_.steps.data()]; p.nlayers = (int)st.tail.size();
+        p.KSA = st.tail_ksa; p.KSB = st.tail_ksb; p.PA = st.tail_pa; p.PB = st.tail_pb;
+        p.last_a_layer = st.tail_last_a; p.wbuf_bytes = st.tail_wbuf; p.smem_bytes = st.smem;
+        for (int k = 0; k < 4; ++k) { p.outs[k] = nullptr; p.out_istride[k] = 0; p.out_pix[k] = 0; }
+        for (size_t k = 0; k < st.tail_outs.size(); ++k) {
+          TV ov = view(ctx, st.tail_outs[k]);
+          p.outs[k] = ov.p; p.out_istride[k] = ov.istride; p.out_pix[k] = ov.Cs;
+        }
+        if (!launch_tail_ws(p, B, ctx.cap, s)) { failed_ = true; fprintf(stderr, "fdt: k_tail_ws could not be launched for step '%s'\n", st.name.c_str()); }
+        break;
+      }
+      case kStepFcTc:
+        break;
       case kStepAdd: case kStepAct: case kStepPadC: {
         EltP p;
         p.a = view(ctx, st.in);

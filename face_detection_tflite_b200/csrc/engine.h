@@ -41,6 +41,7 @@ class Engine {
   TfModel model_;
   Plan plan_;
   float* d_blob_ = nullptr;
+  std::vector<TailLayerD*> d_tail_;     // per plan step: device copy of a k_tail_ws layer program (or null)
   int max_ctas_ = 148 * 4;
   mutable bool failed_ = false;
 };

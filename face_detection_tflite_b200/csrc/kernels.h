@@ -6,6 +6,7 @@
 #include <cstdint>
 
 #include "../../include/fdt_api.h"
+#include "tail_layer.h"
 
 namespace fdt {
 
@@ -176,6 +177,21 @@ struct StemWsP {
   size_t smem_bytes;
 };
 bool launch_stem_ws(const StemWsP& p, int B, int cap, cudaStream_t s);
+
+// ---- image-resident tail (kernels_tail.cu): every 16x16 / 8x8 BlazeBlock and both head pairs in one launch ----
+struct TailP {
+  const float* in; long long in_istride; int H, W, CinS;   // first layer's input activation (HBM, NHWC f32)
+  const float* blob;            // the engine's weight blob
+  const TailLayerD* layers;     // device copy of the layer program
+  int nlayers;
+  int KSA, KSB;                 // pixel strides (floats) of the two shared-memory activation buffers: odd numbers of 16-byte quads
+  int PA, PB;                   // pixels they hold
+  int last_a_layer;             // last layer that reads buffer A (the next image's input is fetched after it)
+  int wbuf_bytes;               // one weight buffer (two are kept: the next layer's record streams in during the current layer)
+  float* outs[4]; long long out_istride[4]; int out_pix[4];   // graph outputs the heads write: image 0, floats per image / per pixel
+  size_t smem_bytes;
+};
+bool launch_tail_ws(const TailP& p, int B, int cap, cudaStream_t s);
 
 // ---- detector post-processing: one block per image ----
 struct DecodeP {

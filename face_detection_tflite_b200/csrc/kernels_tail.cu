@@ -1,0 +1,415 @@
+// k_tail_ws — the low-resolution tail of a BlazeFace detector (every 16x16 / 8x8 BlazeBlock and both head pairs)
+// in ONE launch with the activations of an image resident in shared memory.
+//
+// Launched layer by layer these steps move ~1.2 MB per image through HBM at 1-4 tiles per CTA and are bound by launch
+// prologues and pipeline fill, not by bandwidth (round-1 profile: 12 launches = 32 % of the step at 0.16-0.31 of the
+// HBM roofline).  Here a persistent CTA per SM takes one image at a time:
+//
+//   input (16x16xC, HBM) --TMA--> buffer A [256 px][KSA] -- blocks @16x16 (in place) --> heads@16x16 -> HBM outputs
+//                                  '-- stride-2 block --> buffer B [64 px][KSB] -- blocks @8x8 (in place) --> heads@8x8 -> HBM
+//
+//   warps 0..11 (compute): per layer and 128-pixel tile, thread = (pixel = TMEM lane, a third of the channel quads):
+//       depthwise 3x3 from shared memory (fp32 FFMA2) -> fp16 hi + lo split -> tcgen05.st straight into TENSOR MEMORY
+//       (the A operand never touches shared memory); then the epilogue of the same tile: tcgen05.ld -> + bias
+//       + residual (same pixel / 2x2 max-pool of the source buffer) -> ReLU -> back into the activation buffer
+//       (heads: + bias -> graph outputs in HBM).
+//   warp 12, one lane (control): TMA of the next image, one bulk copy per layer of its weight record
+//       [W fp16 | depthwise taps | depthwise bias] into a two-deep ring (the next layer's weights stream in from L2
+//       during the current layer), and the tcgen05.mma issue: kind::f16, A from TMEM, W from shared memory, two
+//       passes (A_hi, A_lo) - the detector's weights are fp16-origin and therefore exact, so the products carry
+//       ~22 mantissa bits like the TF32 hi/lo split of k_block_ws at half the MMA count.
+//
+// Hand-offs are mbarriers: w_full[2] (weights landed), a_full[2] (operand tile written, 384 arrivals), d_full[2]
+// (tcgen05.commit), in_full / a_free (image buffer).  One named barrier per layer orders the in-place epilogue
+// against the next layer's depthwise reads.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "kernels.h"
+
+namespace fdt {
+namespace {
+
+constexpr int kTC = 12;                       // compute warps
+constexpr int kTComputeThreads = kTC * 32;
+constexpr int kTThreads = (kTC + 1) * 32;
+// TMEM columns: accumulators of tile 0 / 1 at 0 / 128 (Npad <= 128); operand of tile 0 / 1 at 256 / 384: hi halves at +0,
+// lo halves at +64 (K16 / 2 <= 64 columns)
+__device__ __forceinline__ uint32_t col_d(int t) { return t ? 128u : 0u; }
+__device__ __forceinline__ uint32_t col_a(int t) { return t ? 384u : 256u; }
+constexpr uint32_t kLBO = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ float4 lds4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts4(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// two packed fp32 FMAs (sm_100 FFMA2): same rounding as four scalar fmaf
+__device__ __forceinline__ void fma4(float4& a, const float4& v, const float4& w) {
+  asm("{\n\t.reg .b64 ra, rv, rw;\n\t"
+      "mov.b64 ra, {%0, %1};\n\tmov.b64 rv, {%4, %5};\n\tmov.b64 rw, {%8, %9};\n\t"
+      "fma.rn.f32x2 ra, rv, rw, ra;\n\tmov.b64 {%0, %1}, ra;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rv, {%6, %7};\n\tmov.b64 rw, {%10, %11};\n\t"
+      "fma.rn.f32x2 ra, rv, rw, ra;\n\tmov.b64 {%2, %3}, ra;\n\t}"
+      : "+f"(a.x), "+f"(a.y), "+f"(a.z), "+f"(a.w)
+      : "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "f"(w.x), "f"(w.y), "f"(w.z), "f"(w.w));
+}
+__device__ __forceinline__ float4 max4(const float4& a, const float4& b) {
+  return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+// (e0, e1) -> packed fp16 pair, low half = e0; saturating (an activation beyond the fp16 range must not turn into inf)
+__device__ __forceinline__ uint32_t pack_h2(float e0, float e1) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(e1), "f"(e0));
+  return d;
+}
+// a = hi + lo with hi, lo fp16: ~22 mantissa bits; written as two 2-column TMEM stores (4 halves each)
+__device__ __forceinline__ void split_store_tmem(uint32_t taddr_hi, const float4& a) {
+  const uint32_t h0 = pack_h2(a.x, a.y), h1 = pack_h2(a.z, a.w);
+  const __half2 hh0 = *reinterpret_cast<const __half2*>(&h0), hh1 = *reinterpret_cast<const __half2*>(&h1);
+  const float2 f0 = __half22float2(hh0), f1 = __half22float2(hh1);
+  const uint32_t l0 = pack_h2(a.x - f0.x, a.y - f0.y), l1 = pack_h2(a.z - f1.x, a.w - f1.y);
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr_hi), "r"(h0), "r"(h1) : "memory");
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr_hi + 64u), "r"(l0), "r"(l1) : "memory");
+}
+__device__ __forceinline__ void mma_ts_f16(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tmov.b64 db, {%2, %3};\n\tsetp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}\n" ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc));
+}
+
+// Shared-memory carve-up (must match tail_smem_bytes below):
+//   [layers 16 x 128 B] [bias 16 x 128 floats] [barriers 16 x 8 B] | 128-byte aligned: [buffer A PA x KSA] [buffer B PB x KSB]
+//   [zero slot 128 floats] | 128-byte aligned: [weight ring 2 x wbuf_bytes]
+__global__ void __launch_bounds__(kTThreads, 1) k_tail_ws(const __grid_constant__ CUtensorMap tmap, TailP p, int B) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  TailLayerD* sL = reinterpret_cast<TailLayerD*>(smem_raw);
+  float* sBias = reinterpret_cast<float*>(smem_raw + kTailMaxLayers * sizeof(TailLayerD));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + kTailMaxLayers * 128);
+  float* bufA = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(bars + 16) + 127) & ~(uintptr_t)127);
+  float* bufB = bufA + (size_t)p.PA * p.KSA;
+  float* zslot = bufB + (size_t)p.PB * p.KSB;
+  unsigned char* wring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(zslot + 128) + 127) & ~(uintptr_t)127);
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t in_full = bar0, a_free = bar0 + 8u, w_full = bar0 + 16u, a_full = bar0 + 32u, d_full = bar0 + 48u;
+  const int nl = p.nlayers;
+  const uint32_t in_bytes = (uint32_t)p.PA * (uint32_t)p.KSA * 4u;
+  const int my_images = blockIdx.x < B ? (B - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  // ---- prologue ---------------------------------------------------------------------------------------------------
+  for (int i = tid; i < nl * (int)(sizeof(TailLayerD) / 16); i += kTThreads)
+    reinterpret_cast<uint4*>(sL)[i] = reinterpret_cast<const uint4*>(p.layers)[i];
+  for (int i = tid; i < p.PB * p.KSB + 128; i += kTThreads) bufB[i] = 0.f;           // buffer B's channel pad and the zero slot stay zero
+  if (warp == kTC) {
+    if (lane == 0) {
+      mbar_init(in_full, 1);
+      mbar_init(a_free, kTC);
+      for (int i = 0; i < 2; ++i) { mbar_init(w_full + 8u * i, 1); mbar_init(a_full + 8u * i, kTComputeThreads); mbar_init(d_full + 8u * i, 1); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  __syncthreads();
+  for (int l = 0; l < nl; ++l)
+    for (int i = tid; i < sL[l].Npad; i += kTThreads) sBias[l * 128 + i] = p.blob[(size_t)sL[l].bias_off + i];
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t bufA_a = smem_u32(bufA), bufB_a = smem_u32(bufB), zero_a = smem_u32(zslot), wring_a = smem_u32(wring);
+  const uint32_t ksa_b = (uint32_t)p.KSA * 4u, ksb_b = (uint32_t)p.KSB * 4u;
+
+  if (warp < kTC) {
+    // =============================== compute warps ==============================================================
+    const int lq = warp & 3, g = warp >> 2;                // TMEM lane quarter (hardware: warp % 4), channel-quad / column group
+    const int r = lq * 32 + lane;                           // row of the 128-pixel tile = TMEM lane
+    const uint32_t tm_lane = tmem_base + ((uint32_t)(lq * 32) << 16);
+    uint32_t ph_a[2] = {0u, 0u}, ph_d[2] = {0u, 0u};
+    int gl = 0, it = 0;
+    for (int img = blockIdx.x; img < B; img += gridDim.x, ++it) {
+      mbar_wait(in_full, (uint32_t)(it & 1));
+      for (int l = 0; l < nl; ++l, ++gl) {
+        const TailLayerD& L = sL[l];
+        const uint32_t src_a = L.src ? bufB_a : bufA_a, dst_a = L.dst ? bufB_a : bufA_a;
+        const uint32_t kss_b = L.src ? ksb_b : ksa_b, ksd_b = L.dst ? ksb_b : ksa_b;
+        const int src_q = (int)(kss_b >> 4), dst_q = (int)(ksd_b >> 4);       // quads per pixel record
+        const int npix = L.OH * L.OW, ntiles = (npix + 127) >> 7;
+        const int nq = L.K16 >> 2, nq_real = (L.Cin + 3) >> 2;
+        const uint32_t wb_a = wring_a + (uint32_t)(gl & 1) * (uint32_t)p.wbuf_bytes;
+        const uint32_t dww_a = wb_a + (uint32_t)(L.Npad * L.K16) * 2u, dwb_a = dww_a + 9u * (uint32_t)L.K16 * 4u;
+        const uint32_t k16_b = (uint32_t)L.K16 * 4u;
+        mbar_wait(w_full + 8u * (uint32_t)(gl & 1), (uint32_t)((gl >> 1) & 1));
+        // ---- operand tiles: depthwise 3x3 (blocks) or the activation itself (heads) -> fp16 hi / lo -> TMEM ------------
+        for (int t = 0; t < ntiles; ++t) {
+          const int pix = t * 128 + r;
+          const bool act = pix < npix;
+          const uint32_t acol = tm_lane + col_a(t);
+          if (L.kind == 0) {
+            const int oy = act ? pix / L.OW : 0, ox = act ? pix - oy * L.OW : 0;
+            uint32_t off[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+              const int iy = oy * L.stride - L.pad + k / 3, ix = ox * L.stride - L.pad + k % 3;
+              const bool ok = act && (unsigned)iy < (unsigned)L.IH && (unsigned)ix < (unsigned)L.IW;
+              off[k] = ok ? src_a + (uint32_t)(iy * L.IW + ix) * kss_b : zero_a;      // SAME padding reads the zero slot
+            }
+            for (int q = g; q < nq; q += 3) {
+              float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (q < nq_real) {
+                const uint32_t qo = 16u * (uint32_t)q;
+                a = lds4(dwb_a + qo);                                             // bias, then the taps in (ky, kx) order
+#pragma unroll
+                for (int k = 0; k < 9; ++k) fma4(a, lds4(off[k] + qo), lds4(dww_a + (uint32_t)k * k16_b + qo));
+              }
+              split_store_tmem(acol + 2u * (uint32_t)q, a);
+            }
+          } else {
+            const uint32_t px_a = act ? src_a + (uint32_t)pix * kss_b : zero_a;
+            for (int q = g; q < nq; q += 3) {
+              const float4 a = q < src_q ? lds4(px_a + 16u * (uint32_t)q) : make_float4(0.f, 0.f, 0.f, 0.f);
+              split_store_tmem(acol + 2u * (uint32_t)q, a);
+            }
+          }
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(a_full + 8u * (uint32_t)t);
+        }
+        // ---- epilogue ---------------------------------------------------------------------------------------------------
+        const uint32_t bias_a = smem_u32(sBias + l * 128);
+        for (int t = 0; t < ntiles; ++t) {
+          if (t == 0) {
+            // in-place layers: every depthwise read of the layer (both tiles, all threads) must precede the first write
+            for (int u = 0; u < ntiles; ++u) { mbar_wait(a_full + 8u * (uint32_t)u, ph_a[u]); ph_a[u] ^= 1u; }
+          }
+          mbar_wait(d_full + 8u * (uint32_t)t, ph_d[t]);
+          ph_d[t] ^= 1u;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const int pix = t * 128 + r;
+          const bool act = pix < npix;
+          const uint32_t dcol = tm_lane + col_d(t);
+          // residual source pixel(s)
+          uint32_t res_a = zero_a;
+          if (act && L.res == 1) res_a = src_a + (uint32_t)pix * kss_b;
+          if (act && L.res == 2) { const int oy = pix / L.OW, ox = pix - oy * L.OW; res_a = src_a + (uint32_t)((2 * oy) * L.IW + 2 * ox) * kss_b; }
+          const uint32_t row_b = (uint32_t)L.IW * kss_b;
+          const uint32_t out_a = dst_a + (uint32_t)(act ? pix : 0) * ksd_b;
+          float* o1 = nullptr; float* o2 = nullptr;
+          if (L.kind == 1) {
+            o1 = p.outs[L.o1] + (size_t)img * p.out_istride[L.o1] + (size_t)(act ? pix : 0) * p.out_pix[L.o1];
+            if (L.o2 >= 0) o2 = p.outs[L.o2] + (size_t)img * p.out_istride[L.o2] + (size_t)(act ? pix : 0) * p.out_pix[L.o2];
+          }
+          for (int c16 = g; c16 < (L.Npad >> 4); c16 += 3) {
+            uint32_t u[16];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                  "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+                : "r"(dcol + 16u * (uint32_t)c16));
+            float4 bv[4], rv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int cq = 4 * c16 + j;
+              const uint32_t qo = 16u * (uint32_t)cq;
+              bv[j] = lds4(bias_a + qo);
+              rv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (L.res == 1) {
+                if (cq < src_q) rv[j] = lds4(res_a + qo);
+              } else if (L.res == 2) {
+                if (cq < src_q) rv[j] = max4(max4(lds4(res_a + qo), lds4(res_a + kss_b + qo)), max4(lds4(res_a + row_b + qo), lds4(res_a + row_b + kss_b + qo)));
+              }
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int cq = 4 * c16 + j;
+              float4 v = make_float4(__uint_as_float(u[4 * j]) + bv[j].x, __uint_as_float(u[4 * j + 1]) + bv[j].y,
+                                     __uint_as_float(u[4 * j + 2]) + bv[j].z, __uint_as_float(u[4 * j + 3]) + bv[j].w);
+              if (L.kind == 0) {
+                v.x += rv[j].x; v.y += rv[j].y; v.z += rv[j].z; v.w += rv[j].w;
+                if (L.relu) v = max4(v, make_float4(0.f, 0.f, 0.f, 0.f));
+                if (act && cq < dst_q) sts4(out_a + 16u * (uint32_t)cq, v);       // columns >= Cout come out as exact zeros
+              } else if (act) {
+                const int c = 4 * cq;
+                if (c + 4 <= L.c1) {
+                  *reinterpret_cast<float4*>(o1 + c) = v;
+                } else {
+                  const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e)
+                    if (c + e >= L.c1 && c + e - L.c1 < L.c2) o2[c + e - L.c1] = vv[e];
+                }
+              }
+            }
+          }
+        }
+        // the layer's writes (shared memory: generic proxy; TMEM reads done) before anybody starts the next layer
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kTComputeThreads) : "memory");
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (l == p.last_a_layer && lane == 0) mbar_arrive(a_free);              // buffer A may take the next image
+      }
+    }
+  } else if (lane == 0) {
+    // =============================== control lane: TMA + weight ring + MMA issue ======================================
+    const int total = my_images * nl;
+    auto load_weights = [&](int glayer) {
+      const TailLayerD& L = sL[glayer % nl];
+      const uint32_t bar = w_full + 8u * (uint32_t)(glayer & 1);
+      mbar_expect_tx(bar, (uint32_t)L.rec_bytes);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(wring_a + (uint32_t)(glayer & 1) * (uint32_t)p.wbuf_bytes), "l"(p.blob + (size_t)L.rec_off), "r"((uint32_t)L.rec_bytes), "r"(bar) : "memory");
+    };
+    auto load_image = [&](int img) {
+      mbar_expect_tx(in_full, in_bytes);
+      asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                   ::"r"(bufA_a), "l"(&tmap), "r"(0), "r"(0), "r"(0), "r"(img), "r"(in_full) : "memory");
+    };
+    if (my_images > 0) {
+      load_image(blockIdx.x);
+      load_weights(0);
+      if (total > 1) load_weights(1);
+    }
+    uint32_t ph_a[2] = {0u, 0u}, ph_d[2] = {0u, 0u};
+    int gl = 0, it = 0;
+    for (int img = blockIdx.x; img < B; img += gridDim.x, ++it) {
+      for (int l = 0; l < nl; ++l, ++gl) {
+        const TailLayerD& L = sL[l];
+        const int ntiles = (L.OH * L.OW + 127) >> 7;
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(L.Npad >> 3) << 17) | ((128u >> 4) << 24);     // D f32, A / B f16, K-major
+        const uint32_t sbo = (uint32_t)(L.K16 >> 3) * 128u;
+        const uint32_t b_hi = ((sbo >> 4) & 0x3FFFu) | (1u << 14);
+        const uint32_t wb_a = wring_a + (uint32_t)(gl & 1) * (uint32_t)p.wbuf_bytes;
+        const uint32_t b_lo0 = ((wb_a & 0x3FFFFu) >> 4) | ((kLBO >> 4) << 16);
+        const int ksteps = L.K16 >> 4;
+        mbar_wait(w_full + 8u * (uint32_t)(gl & 1), (uint32_t)((gl >> 1) & 1));
+        for (int t = 0; t < ntiles; ++t) {
+          mbar_wait(a_full + 8u * (uint32_t)t, ph_a[t]);
+          ph_a[t] ^= 1u;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t dcol = tmem_base + col_d(t), acol = tmem_base + col_a(t);
+          uint32_t acc = 0u;
+#pragma unroll 1
+          for (int part = 0; part < 2; ++part)
+#pragma unroll 1
+            for (int ks = 0; ks < ksteps; ++ks) {
+              mma_ts_f16(dcol, acol + 64u * (uint32_t)part + 8u * (uint32_t)ks, b_lo0 + 16u * (uint32_t)ks, b_hi, idesc, acc);
+              acc = 1u;
+            }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(d_full + 8u * (uint32_t)t) : "memory");
+        }
+        // this layer's MMAs have read the weight buffer and every thread has read its taps: stream in the layer after next
+        for (int t = 0; t < ntiles; ++t) { mbar_wait(d_full + 8u * (uint32_t)t, ph_d[t]); ph_d[t] ^= 1u; }
+        if (gl + 2 < total) load_weights(gl + 2);
+        if (l == p.last_a_layer && img + (int)gridDim.x < B) {
+          mbar_wait(a_free, (uint32_t)(it & 1));
+          load_image(img + (int)gridDim.x);
+        }
+      }
+    }
+  }
+  __syncwarp();
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == kTC) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+
+// f32 [cap][H][W][CinS], box {KSA, W, H, 1}: channels >= CinS are zero-filled (the residual's zero channel pad)
+bool tail_tensor_map(const TailP& p, int cap, CUtensorMap* out) {
+  typedef std::tuple<const void*, int, int, int, int, int, long long> Key;
+  static std::mutex mu;
+  static std::map<Key, CUtensorMap> cache;
+  Key key(p.in, cap, p.H, p.W, p.CinS, p.KSA, p.in_istride);
+  std::lock_guard<std::mutex> g(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return true; }
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t gdim[4] = {(cuuint64_t)p.CinS, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)cap};
+  cuuint64_t gstr[3] = {(cuuint64_t)p.CinS * 4, (cuuint64_t)p.W * p.CinS * 4, (cuuint64_t)p.in_istride * 4};
+  cuuint32_t box[4] = {(cuuint32_t)p.KSA, (cuuint32_t)p.W, (cuuint32_t)p.H, 1u};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap tm;
+  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.in), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  if (cache.size() > 256) cache.clear();
+  cache[key] = tm;
+  *out = tm;
+  return true;
+}
+
+}  // namespace
+
+size_t tail_smem_bytes(int PA, int KSA, int PB, int KSB, int wbuf_bytes) {
+  size_t head = (size_t)kTailMaxLayers * sizeof(TailLayerD) + (size_t)kTailMaxLayers * 128 * 4 + 16 * 8 + 128;
+  size_t bufs = ((size_t)PA * KSA + (size_t)PB * KSB + 128) * 4 + 128;
+  return head + bufs + 2 * (size_t)wbuf_bytes;
+}
+
+bool launch_tail_ws(const TailP& p, int B, int cap, cudaStream_t s) {
+  if (B <= 0) return true;
+  CUtensorMap tm;
+  if (!tail_tensor_map(p, cap, &tm)) return false;
+  static std::mutex mu;
+  static std::map<int, size_t> cur;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  {
+    std::lock_guard<std::mutex> g(mu);
+    size_t& c = cur[dev];
+    if (p.smem_bytes > c) {
+      if (cudaFuncSetAttribute(k_tail_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes) != cudaSuccess) return false;
+      c = p.smem_bytes;
+    }
+  }
+  const int grid = std::min(B, sms);
+  k_tail_ws<<<grid, kTThreads, p.smem_bytes, s>>>(tm, p, B);
+  return true;
+}
+
+}  // namespace fdt

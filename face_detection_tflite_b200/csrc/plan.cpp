@@ -787,6 +787,162 @@ struct Builder {
     return true;
   }
 
+  // ---- image-resident tail ---------------------------------------------------------------------------
+  // The maximal suffix of the plan made of warp-specialised BlazeBlock / head steps on feature maps of at most 256
+  // pixels becomes ONE k_tail_ws step (kernels_tail.cu): activations stay in shared memory from the first block to
+  // the heads, weights (exact in fp16: the detectors ship fp16 weights) stream in per layer.  Anything the kernel
+  // does not cover (fp32-only weights, residuals from other tensors, branching chains, > 128 channels, more than
+  // kTailMaxLayers layers) leaves the plan as it is.
+  static int odd_quads(int c) { int q = ru(c, 4) / 4; if (q % 2 == 0) ++q; return q * 4; }
+
+  void fuse_tail() {
+    const int S = (int)P.steps.size();
+    auto block_ok = [&](const PStep& s) {
+      if (s.kind != kStepBlockWs || s.w_parts != 1 || s.in < 0) return false;
+      const PTensor& in = P.tensors[s.in];
+      const PTensor& out = P.tensors[s.out];
+      if (in.H * in.W > 256 || in.root >= 0 || in.C > 128 || s.Cout > 128) return false;
+      if (s.has_dw) {
+        if (s.c2 > 0 || out.root >= 0 || (s.act != kActRelu && s.act != kActNone)) return false;
+        if (s.in2 >= 0 && (s.res_mode != 1 || s.in2 != s.in)) return false;
+        if (s.dws != 1 && s.dws != 2) return false;
+        if (s.dws == 2 && (in.H % 2 || in.W % 2 || s.dpt != 0 || s.dpl != 0)) return false;
+        if (s.dws == 1 && (s.dpt != 1 || s.dpl != 1)) return false;
+        return true;
+      }
+      // head (pair): pointwise only, dense graph-output views
+      if (s.in2 >= 0 || s.act != kActNone || out.root < 0) return false;
+      if (s.c2 > 0 ? (s.c1 % 4 != 0 || s.out2 < 0 || P.tensors[s.out2].root < 0) : (s.Cout % 4 != 0)) return false;
+      return true;
+    };
+    int f = S;
+    while (f > 0 && block_ok(P.steps[f - 1])) --f;
+    // the chain must start at a block and be closed: inputs come from inside it (or are the first block's input)
+    for (; f < S; ++f) {
+      if (!P.steps[f].has_dw) continue;
+      const int X = P.steps[f].in;
+      std::vector<int> produced{X};
+      bool ok = true;
+      for (int i = f; i < S && ok; ++i) {
+        ok = std::find(produced.begin(), produced.end(), P.steps[i].in) != produced.end();
+        produced.push_back(P.steps[i].out);
+      }
+      // nothing before the chain may be read after it started, and no tensor of the chain feeds two blocks
+      for (int i = f; i < S && ok; ++i)
+        for (int j = i + 1; j < S && ok; ++j)
+          if (P.steps[i].has_dw && P.steps[j].has_dw && P.steps[i].in == P.steps[j].in) ok = false;
+      if (ok) break;
+    }
+    if (S - f < 3) return;
+    const int X = P.steps[f].in;
+    // layer order: blocks as planned, every head right after the block that produces its input
+    std::vector<int> order;
+    for (int i = f; i < S; ++i) {
+      if (!P.steps[i].has_dw) continue;
+      order.push_back(i);
+      for (int j = f; j < S; ++j)
+        if (!P.steps[j].has_dw && P.steps[j].in == P.steps[i].out) order.push_back(j);
+    }
+    if ((int)order.size() != S - f || (int)order.size() > kTailMaxLayers) return;
+    // buffers: A until the stride-2 block, B after it
+    std::map<int, int> buf_of;
+    buf_of[X] = 0;
+    int maxA = P.tensors[X].Cs, maxB = 4, PA = P.tensors[X].H * P.tensors[X].W, PB = 1, n_s2 = 0, last_a = 0;
+    PStep t;
+    t.kind = kStepTailWs;
+    size_t wbuf = 0;
+    for (size_t li = 0; li < order.size(); ++li) {
+      const PStep& s = P.steps[order[li]];
+      const PTensor& in = P.tensors[s.in];
+      const PTensor& out = P.tensors[s.out];
+      auto bi = buf_of.find(s.in);
+      if (bi == buf_of.end()) return;
+      TailLayerD L = {};
+      L.kind = s.has_dw ? 0 : 1;
+      L.src = bi->second;
+      L.IH = in.H; L.IW = in.W; L.OH = out.H; L.OW = out.W;
+      L.Cin = in.C; L.Cout = s.Cout; L.K16 = ru(in.C, 16); L.Npad = ru(s.Cout, 16);
+      L.o1 = L.o2 = -1;
+      if (L.src == 0) last_a = (int)li;
+      if (s.has_dw) {
+        L.stride = s.dws; L.pad = s.dpt;
+        L.res = s.in2 >= 0 ? (s.res_pool ? 2 : 1) : 0;
+        L.relu = s.act == kActRelu ? 1 : 0;
+        if (s.dws == 2) {
+          if (L.src != 0 || ++n_s2 > 1) return;
+          L.dst = 1;
+          PB = out.H * out.W;
+        } else {
+          L.dst = L.src;
+          if (L.res == 2) return;
+        }
+        buf_of[s.out] = L.dst;
+        (L.dst ? maxB : maxA) = std::max(L.dst ? maxB : maxA, ru(s.Cout, 4));
+      } else {
+        L.dst = L.src;
+        L.c1 = s.c2 > 0 ? s.c1 : s.Cout; L.c2 = s.c2;
+        L.o1 = (int)t.tail_outs.size(); t.tail_outs.push_back(s.out);
+        if (s.c2 > 0) { L.o2 = (int)t.tail_outs.size(); t.tail_outs.push_back(s.out2); }
+        if (t.tail_outs.size() > 4) return;
+      }
+      if (L.OH * L.OW > 256) return;
+      // the step's tensor-core operands back to plain arrays: W [Cout][Cin] (exact values), taps [9][K8], biases
+      const size_t SBO8 = (size_t)(s.K8 / 4) * 128;
+      const int K16 = L.K16;
+      std::vector<uint16_t> wh((size_t)L.Npad * K16, 0);
+      const size_t SBO16 = (size_t)(K16 / 8) * 128;
+      for (int n = 0; n < s.Cout; ++n)
+        for (int k = 0; k < in.C; ++k) {
+          const float v = P.blob[(size_t)s.w + ((size_t)(n >> 3) * SBO8 + (size_t)(k >> 2) * 128 + (size_t)(n & 7) * 16 + (size_t)(k & 3) * 4) / 4];
+          const uint16_t hbits = f32_to_f16(v);
+          if (f16_to_f32(hbits) != v) return;                 // not an fp16-origin model: keep the TF32 hi/lo kernels
+          wh[((size_t)(n >> 3) * SBO16 + (size_t)(k >> 3) * 128 + (size_t)(n & 7) * 16 + (size_t)(k & 7) * 2) / 2] = hbits;
+        }
+      std::vector<float> rec((wh.size() + 1) / 2 + (s.has_dw ? (size_t)10 * K16 : 0), 0.f);
+      std::memcpy(rec.data(), wh.data(), wh.size() * 2);
+      if (s.has_dw) {
+        float* dw = rec.data() + wh.size() / 2;
+        for (int k = 0; k < 9; ++k)
+          for (int c = 0; c < in.C; ++c) dw[(size_t)k * K16 + c] = P.blob[(size_t)s.dww + (size_t)k * s.K8 + c];
+        for (int c = 0; c < in.C; ++c) dw[(size_t)9 * K16 + c] = P.blob[(size_t)s.dwb + c];
+      }
+      L.rec_bytes = (int)(rec.size() * 4);
+      if (L.rec_bytes % 16) return;
+      wbuf = std::max(wbuf, (size_t)L.rec_bytes);
+      L.rec_off = (int)push(rec, rec.size());
+      // pointwise bias [Npad]: the step's own array is zero-padded past Cout already (Npad16 >= Npad here)
+      std::vector<float> bias((size_t)L.Npad, 0.f);
+      for (int n = 0; n < s.Cout; ++n) bias[n] = P.blob[(size_t)s.bias + n];
+      L.bias_off = (int)push(bias, bias.size());
+      t.macs += s.macs;
+      t.tail.push_back(L);
+    }
+    t.tail_ksa = odd_quads(maxA); t.tail_ksb = odd_quads(maxB); t.tail_pa = PA; t.tail_pb = PB; t.tail_last_a = last_a;
+    t.tail_wbuf = (int)((wbuf + 127) / 128 * 128);
+    if (t.tail_ksa > 256 || t.tail_outs.empty()) return;
+    t.smem = (size_t)kTailMaxLayers * sizeof(TailLayerD) + (size_t)kTailMaxLayers * 512 + 256 +
+             ((size_t)PA * t.tail_ksa + (size_t)PB * t.tail_ksb + 128) * 4 + 128 + 2 * (size_t)t.tail_wbuf;     // = tail_smem_bytes()
+    if (t.smem > (size_t)225 * 1024) return;
+    t.in = X;
+    t.out = t.tail_outs[0];
+    for (size_t k = 1; k < t.tail_outs.size(); ++k) t.extra_out.push_back(t.tail_outs[k]);
+    t.name = "tail:" + P.steps[order.front()].name + ".." + P.steps[order.back()].name;
+    // replace the suffix and redo the liveness bookkeeping
+    P.steps.resize(f);
+    P.steps.push_back(t);
+    for (PTensor& x : P.tensors) { x.materialized = false; x.def_step = -1; x.last_use = -1; }
+    for (size_t i = 0; i < P.steps.size(); ++i) {
+      const PStep& s = P.steps[i];
+      P.tensors[s.out].materialized = true;
+      if (s.out2 >= 0) P.tensors[s.out2].materialized = true;
+      for (int e : s.extra_out) { P.tensors[e].materialized = true; use((int)i, e); }
+      if (!s.in_u8) use((int)i, s.in);
+      use((int)i, s.in2);
+      use((int)i, s.out);
+      use((int)i, s.out2);
+    }
+  }
+
   // ---- emission ---------------------------------------------------------------------------------
   void use(int step, int t) {
     if (t < 0) return;
@@ -947,6 +1103,8 @@ struct Builder {
       int t = pt(o);
       P.outputs.push_back(t);
     }
+    static const int want_tail = [] { const char* e = std::getenv("FDT_TAIL"); return e ? std::atoi(e) : 0; }();
+    if (fuse == 1 && use_tc && want_tail) fuse_tail();
     // arena allocation
     struct Block { long long off, size; int free_after; };
     std::vector<Block> blocks;
@@ -993,7 +1151,7 @@ bool Plan::build(const TfModel& m, int fuse, std::string* err, bool use_tc) {
 }
 
 std::string Plan::describe() const {
-  static const char* kn[] = {"normalize", "naive_conv", "gemm_conv", "dwpw", "add", "act", "padc", "maxpool", "resize", "stem", "dwpw_tc", "stem_tc", "block_ws", "stem_ws"};
+  static const char* kn[] = {"normalize", "naive_conv", "gemm_conv", "dwpw", "add", "act", "padc", "maxpool", "resize", "stem", "dwpw_tc", "stem_tc", "block_ws", "stem_ws", "tail_ws", "fc_tc"};
   std::string s;
   char buf[512];
   double macs = 0;
@@ -1007,6 +1165,12 @@ std::string Plan::describe() const {
              st.res_pool ? "(pool)" : "", st.res_mode, o.tf, o.H, o.W, o.C, o.Cs, o.root >= 0 ? "view" : "arena", st.act,
              (int)st.has_dw, st.dws, st.K, st.NC, st.nchunks, st.TM, st.NPG, st.TH, st.TW, st.G, st.RS, st.nd, st.ns, st.na, st.no, st.smem, st.name.c_str());
     s += buf;
+    for (size_t l = 0; l < st.tail.size(); ++l) {
+      const TailLayerD& L = st.tail[l];
+      snprintf(buf, sizeof buf, "      tail %2zu %s buf %d->%d %dx%d->%dx%d s%d C %d->%d K16=%d Npad=%d res=%d relu=%d rec=%dB\n", l, L.kind ? "heads" : "block",
+               L.src, L.dst, L.IH, L.IW, L.OH, L.OW, L.stride, L.Cin, L.Cout, L.K16, L.Npad, L.res, L.relu, L.rec_bytes);
+      s += buf;
+    }
   }
   snprintf(buf, sizeof buf, "steps=%zu  MACs/image=%.3fM  arena/image=%.1f KB  weights=%.1f KB\n", steps.size(),
            macs / 1e6, arena_per_image * 4.0 / 1024, blob.size() * 4.0 / 1024);

@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 
+#include "tail_layer.h"
 #include "tflite_model.h"
 
 namespace fdt {
@@ -46,6 +47,10 @@ struct PStep {
   int out2 = -1, c1 = 0, c2 = 0;                        // two heads in one launch: columns [0,c1) -> out, [c1,c1+c2) -> out2   // warp-specialised variant: input stages, A buffers, depthwise warps
   int fh = 1, fw = 1, align = 0, half = 0;
   std::vector<int> extra_out;   // further tensors the step materialises (k_tail_ws: every graph output of the fused tail)
+  // k_tail_ws: the layer program and its shared-memory geometry (see kernels_tail.cu)
+  std::vector<TailLayerD> tail;
+  std::vector<int> tail_outs;   // PTensor ids the heads write, indexed by TailLayerD::o1 / o2
+  int tail_ksa = 0, tail_ksb = 0, tail_pa = 0, tail_pb = 0, tail_last_a = 0, tail_wbuf = 0;
   double macs = 0;  // per image
 };
 

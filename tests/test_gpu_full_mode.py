@@ -80,7 +80,9 @@ def test_full_mode_matches_oracle(fdt, model_bytes, iris_bytes, images, model):
         for e in range(2):
             sl = slice(76 * e, 76 * e + 76)
             assert np.abs(g.irisPacked[sl, :2] - r.iris_px[sl, :2]).max() <= 2 * COORD_TOL * r.eye_rois[e][2]
-            assert np.abs(g.irisPacked[sl, 2] - r.iris_px[sl, 2]).max() <= HEAD_REL_TOL * 64 * 10
+            # z is the model's raw depth output (not geometric, face_geometry.dart:123): it moves with the crop's sub-pixel
+            # placement, i.e. with the fp32 mesh; like-for-like (same crop) it is within 1e-4 above
+            assert np.abs(g.irisPacked[sl, 2] - r.iris_px[sl, 2]).max() <= 2e-2 * max(1.0, np.abs(r.iris_px[sl, 2]).max())
         assert np.abs(np.array(g.detectionData.keypointsXY) - np.array(r.det.kp)).max() <= COORD_TOL
         # the refined keypoints ARE iris points (closest to the centroid), the others are the detector's
         lc = geo.iris_center_from_points(g.irisPacked[71:76].astype(np.float64))
