@@ -250,6 +250,19 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
       }
       case kStepFcTc:
         break;
+      case kStepBlockTs: {
+        BlockTsP p;
+        TV iv = view(ctx, st.in);
+        p.in = iv.p; p.in_istride = iv.istride; p.H = iv.H; p.W = iv.W; p.CinS = iv.Cs;
+        p.out = out.p; p.out_istride = out.istride; p.OH = out.H; p.OW = out.W; p.CoutS = out.Cs;
+        p.rec = blob + st.ts_rec; p.bias = blob + st.ts_bias; p.rec_bytes = st.ts_rec_bytes;
+        p.Cin = iv.C; p.K16 = st.ts_k16; p.Npad = st.ts_npad; p.KS = st.ts_ks;
+        p.stride = st.dws; p.res = st.ts_res; p.relu = st.ts_relu;
+        p.wide = (out.Cs % 8 == 0 && out.istride % 8 == 0 && ((size_t)out.p % 32 == 0)) ? 1 : 0;
+        p.ns = st.ts_ns; p.stage_bytes = st.ts_stage_bytes; p.smem_bytes = st.smem;
+        if (!launch_block_ts(p, B, ctx.cap, s)) { failed_ = true; fprintf(stderr, "fdt: k_block_ts could not be launched for step '%s'\n", st.name.c_str()); }
+        break;
+      }
       case kStepAdd: case kStepAct: case kStepPadC: {
         EltP p;
         p.a = view(ctx, st.in);

@@ -1357,7 +1357,7 @@ int32_t fdt_profile_chunk(fdt_handle* h, const uint8_t* d_frames, int32_t n, int
 }
 
 static const char* kKernelNames[] = {"k_normalize", "k_naive_conv", "k_gemm_conv", "k_dwpw", "k_add", "k_act", "k_padc", "k_maxpool",
-                                     "k_resize_bilinear", "k_stem", "k_dwpw_tc", "k_stem_tc", "k_block_ws", "k_stem_ws", "k_tail_ws", "k_fc_tc"};
+                                     "k_resize_bilinear", "k_stem", "k_dwpw_tc", "k_stem_tc", "k_block_ws", "k_stem_ws", "k_tail_ws", "k_fc_tc", "k_block_ts"};
 
 static void step_info(const Plan& p, const PStep& st, int in_w, int in_h, std::string* kname, std::string* tname, double* macs, double* bytes) {
   *kname = kKernelNames[st.kind]; *tname = st.name; *macs = st.macs;

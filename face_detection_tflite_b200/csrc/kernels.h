@@ -178,6 +178,23 @@ struct StemWsP {
 };
 bool launch_stem_ws(const StemWsP& p, int B, int cap, cudaStream_t s);
 
+// ---- BlazeBlock with the GEMM operand in tensor memory (kernels_ts.cu): fp16-weight detectors, K16 <= 64, Npad <= 64 ----
+struct BlockTsP {
+  const float* in; long long in_istride; int H, W, CinS;
+  float* out; long long out_istride; int OH, OW, CoutS;
+  const float* rec;         // [W fp16 Npad x K16 (UMMA K-major core matrices) | depthwise taps 9 x K16 | depthwise bias K16]
+  const float* bias;        // pointwise bias [Npad]
+  int rec_bytes;
+  int Cin, K16, Npad, KS;   // KS: staged pixel stride (floats), an odd number of 16-byte quads
+  int stride;               // depthwise stride 1 (16x16 output tiles) or 2 (8x16)
+  int res;                  // 0 none, 1 the block input, 2 its 2x2 max-pool (stride 2); zero channel pad either way
+  int relu, wide;           // wide: pixel records 32-byte aligned -> 256-bit stores
+  int ns, stage_bytes;      // input ring
+  size_t smem_bytes;
+};
+size_t ts_smem_bytes(int rec_bytes, int Npad, int ns, int stage_bytes);
+bool launch_block_ts(const BlockTsP& p, int B, int cap, cudaStream_t s);
+
 // ---- image-resident tail (kernels_tail.cu): every 16x16 / 8x8 BlazeBlock and both head pairs in one launch ----
 struct TailP {
   const float* in; long long in_istride; int H, W, CinS;   // first layer's input activation (HBM, NHWC f32)

@@ -1,0 +1,384 @@
+// k_block_ts — BlazeBlock (depthwise 3x3 -> pointwise 1x1 -> + residual -> ReLU) for the high-resolution layers of the
+// fp16-weight detectors, with the pointwise GEMM's A operand written straight into TENSOR MEMORY.
+//
+// Why a second block kernel: ncu shows k_block_ws limited by the L1 / shared-memory pipe (l1tex 69-81 %, DRAM 32 %).
+// Per output element it moves through shared memory: the TMA fill, the depthwise taps, the TF32 hi / lo operand STORES,
+// the tensor core's operand READS, the residual.  Here the operand never touches shared memory (tcgen05.st -> TMEM,
+// tcgen05.mma reads A from TMEM), it is split into two fp16 terms instead of two TF32 terms (the detectors' weights are
+// fp16-origin, i.e. exact: same ~22-bit products at HALF the MMA count), and the two 128-pixel M-tiles of a 16x16 output
+// tile are the tile's even and odd rows, so that every thread (= one TMEM lane of both M-tiles) owns two vertically
+// adjacent pixels and feeds both from ONE 4 x 3 window of loads (6 instead of 9 LDS.128 per output quad).
+//
+//   warps 0..11  compute : thread = (TMEM lane = pixel column x / row pair yy, one third of the channel quads);
+//                          per tile: depthwise -> fp16 hi / lo -> TMEM operand of slot i & 1 -> arrive a_full;
+//                          then the epilogue of the PREVIOUS tile (its MMAs ran meanwhile): tcgen05.ld -> + bias
+//                          + residual from the still-staged input tile -> ReLU -> 256-bit stores to HBM.
+//   warp 12 lane 0 producer: TMA of input tile + halo into a ring of `ns` stages (out-of-bounds zero fill = SAME padding
+//                          and channel pad).
+//   warp 13 lane 0 MMA   : tcgen05.mma.kind::f16, A from TMEM, W from shared memory; two passes (hi, lo); one commit per tile.
+// No __syncthreads and no named barrier in the steady state: tiles are independent, all hand-offs are mbarriers.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "kernels.h"
+
+namespace fdt {
+namespace {
+
+constexpr int kC = 12;                        // compute warps
+constexpr int kThreads = (kC + 2) * 32;
+constexpr uint32_t kLBO = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ float4 lds4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void fma4(float4& a, const float4& v, const float4& w) {
+  asm("{\n\t.reg .b64 ra, rv, rw;\n\t"
+      "mov.b64 ra, {%0, %1};\n\tmov.b64 rv, {%4, %5};\n\tmov.b64 rw, {%8, %9};\n\t"
+      "fma.rn.f32x2 ra, rv, rw, ra;\n\tmov.b64 {%0, %1}, ra;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rv, {%6, %7};\n\tmov.b64 rw, {%10, %11};\n\t"
+      "fma.rn.f32x2 ra, rv, rw, ra;\n\tmov.b64 {%2, %3}, ra;\n\t}"
+      : "+f"(a.x), "+f"(a.y), "+f"(a.z), "+f"(a.w)
+      : "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "f"(w.x), "f"(w.y), "f"(w.z), "f"(w.w));
+}
+__device__ __forceinline__ float4 max4(const float4& a, const float4& b) {
+  return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+__device__ __forceinline__ uint32_t pack_h2(float e0, float e1) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(e1), "f"(e0));
+  return d;
+}
+// a = hi + lo (fp16 each) -> two 2-column TMEM stores; lo_off = column distance of the lo half
+__device__ __forceinline__ void split_store_tmem(uint32_t taddr_hi, uint32_t lo_off, const float4& a) {
+  const uint32_t h0 = pack_h2(a.x, a.y), h1 = pack_h2(a.z, a.w);
+  const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&h0)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&h1));
+  const uint32_t l0 = pack_h2(a.x - f0.x, a.y - f0.y), l1 = pack_h2(a.z - f1.x, a.w - f1.y);
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr_hi), "r"(h0), "r"(h1) : "memory");
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr_hi + lo_off), "r"(l0), "r"(l1) : "memory");
+}
+__device__ __forceinline__ void mma_ts_f16(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tmov.b64 db, {%2, %3};\n\tsetp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}\n" ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc));
+}
+__device__ __forceinline__ void stg8(float* p, const float4& a, const float4& b) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
+
+// TMEM columns: accumulators at (slot * 2 + t) * 64, operands at 256 + (slot * 2 + t) * 64 (hi halves +0, lo halves +32):
+// K16 <= 64 and Npad <= 64 (plan_ts), two tile slots in flight.
+__device__ __forceinline__ uint32_t col_d(int slot, int t) { return (uint32_t)(slot * 2 + t) * 64u; }
+__device__ __forceinline__ uint32_t col_a(int slot, int t) { return 256u + (uint32_t)(slot * 2 + t) * 64u; }
+
+// Shared-memory carve-up (must match ts_smem_bytes): [W fp16 Npad x K16 | dww 9 x K16 | dwb K16] [bias Npad] [barriers 32 x 8 B]
+//   | 128-byte aligned: [input ring ns x stage_bytes]
+// S = depthwise stride.  S == 1: output tile 16 x 16 (M-tiles = even / odd rows), staged 18 x 18.  S == 2: output tile 8 x 16
+// (one M-tile), staged 17 x 33.
+template <int S>
+__global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant__ CUtensorMap tmap, BlockTsP p, int B) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint32_t tmem_base_s;
+  constexpr int NT = S == 1 ? 2 : 1;                         // M-tiles per output tile
+  constexpr int TH = S == 1 ? 16 : 8, TW = 16;
+  constexpr int IW = S == 1 ? 18 : 33;                       // staged row length (pixels)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* sRec = reinterpret_cast<float*>(smem_raw);
+  float* sBias = sRec + (p.rec_bytes >> 2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + p.Npad);
+  unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(bars + 32) + 127) & ~(uintptr_t)127);
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t in_full = bar0, in_empty = bar0 + 64u, a_full = bar0 + 128u, d_full = bar0 + 144u;   // [8] [8] [2] [2]
+  const int NS = p.ns;
+  const int tiles_x = p.OW / TW, tiles_y = p.OH / TH, tpi = tiles_x * tiles_y;
+  const int ntiles = B * tpi;
+  const int n_my = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  // ---- prologue ---------------------------------------------------------------------------------------------------
+  for (int i = tid; i < (p.rec_bytes >> 4); i += kThreads) reinterpret_cast<uint4*>(sRec)[i] = reinterpret_cast<const uint4*>(p.rec)[i];
+  for (int i = tid; i < p.Npad; i += kThreads) sBias[i] = p.bias[i];
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(in_full + 8u * i, 1); mbar_init(in_empty + 8u * i, kC); }
+    for (int i = 0; i < 2; ++i) { mbar_init(a_full + 8u * i, kC); mbar_init(d_full + 8u * i, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+  }
+  if (warp == kC + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // W was written by the generic proxy, the MMA reads it through the async proxy
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t ring_a = smem_u32(ring), ks_b = (uint32_t)p.KS * 4u, row_b = (uint32_t)IW * ks_b;
+  const uint32_t stage_b = (uint32_t)p.stage_bytes;
+
+  if (warp < kC) {
+    // =============================== compute warps ==============================================================
+    const int lq = warp & 3, g = warp >> 2;
+    const int L = lq * 32 + lane;                            // TMEM lane
+    const int yy = L >> 4, x = L & 15;                       // S == 1: row pair / column of the 16 x 16 tile; S == 2: row / column of the 8 x 16 tile
+    const uint32_t tm_lane = tmem_base + ((uint32_t)(lq * 32) << 16);
+    // top-left of this thread's input window inside a stage: S == 1 rows 2yy .. 2yy + 3, cols x .. x + 2 (halo included);
+    // S == 2 rows 2yy .. 2yy + 2, cols 2x .. 2x + 2
+    const uint32_t win = (uint32_t)((2 * yy) * IW + (S == 1 ? x : 2 * x)) * ks_b;
+    const int nq = p.K16 >> 2, nq_real = (p.Cin + 3) >> 2, ks_q = p.KS >> 2;
+    const uint32_t rec_a = smem_u32(sRec), dww_a = rec_a + (uint32_t)(p.Npad * p.K16) * 2u, dwb_a = dww_a + 9u * (uint32_t)p.K16 * 4u;
+    const uint32_t k16_b = (uint32_t)p.K16 * 4u, bias_a = smem_u32(sBias);
+    const int nc8 = p.Npad >> 3, couts = p.CoutS;
+
+    auto epilogue = [&](int i) {
+      const int slot = i & 1, stage = i % NS;
+      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+      const int b = tile / tpi, trem = tile - b * tpi, ty = trem / tiles_x, tx = trem - ty * tiles_x;
+      mbar_wait(d_full + 8u * (uint32_t)slot, (uint32_t)((i >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t st_a = ring_a + (uint32_t)stage * stage_b + win;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const int oy = ty * TH + (S == 1 ? 2 * yy + t : yy), ox = tx * TW + x;
+        float* orow = p.out + (size_t)b * p.out_istride + ((size_t)oy * p.OW + ox) * couts;
+        // residual: S == 1 the centre of the window of output row t; S == 2 the 2x2 max-pool at the window's top-left
+        const uint32_t res_a = S == 1 ? st_a + (uint32_t)(t + 1) * row_b + ks_b : st_a;
+        const uint32_t dcol = tm_lane + col_d(slot, t);
+        for (int c8 = g; c8 < nc8; c8 += 3) {
+          uint32_t u[8];
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                       : "r"(dcol + 8u * (uint32_t)c8));
+          float4 bv[2], rv[2];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int cq = 2 * c8 + j;
+            const uint32_t qo = 16u * (uint32_t)cq;
+            bv[j] = lds4(bias_a + qo);
+            rv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.res == 1) {
+              if (cq < ks_q) rv[j] = lds4(res_a + qo);
+            } else if (p.res == 2) {
+              if (cq < ks_q) rv[j] = max4(max4(lds4(res_a + qo), lds4(res_a + ks_b + qo)), max4(lds4(res_a + row_b + qo), lds4(res_a + row_b + ks_b + qo)));
+            }
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float4 v[2];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            v[j] = make_float4(__uint_as_float(u[4 * j]) + bv[j].x + rv[j].x, __uint_as_float(u[4 * j + 1]) + bv[j].y + rv[j].y,
+                               __uint_as_float(u[4 * j + 2]) + bv[j].z + rv[j].z, __uint_as_float(u[4 * j + 3]) + bv[j].w + rv[j].w);
+            if (p.relu) v[j] = max4(v[j], make_float4(0.f, 0.f, 0.f, 0.f));
+          }
+          const int c = 8 * c8;                                  // columns >= Cout inside CoutS are exact zeros
+          if (c + 8 <= couts) {
+            if (p.wide) stg8(orow + c, v[0], v[1]);
+            else { *reinterpret_cast<float4*>(orow + c) = v[0]; *reinterpret_cast<float4*>(orow + c + 4) = v[1]; }
+          } else if (c + 4 <= couts) {
+            *reinterpret_cast<float4*>(orow + c) = v[0];
+          }
+        }
+      }
+      // this tile's accumulators and input stage are consumed
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(in_empty + 8u * (uint32_t)stage);
+    };
+
+    for (int i = 0; i < n_my; ++i) {
+      const int slot = i & 1, stage = i % NS;
+      mbar_wait(in_full + 8u * (uint32_t)stage, (uint32_t)((i / NS) & 1));
+      const uint32_t st_a = ring_a + (uint32_t)stage * stage_b + win;
+      const uint32_t acol0 = tm_lane + col_a(slot, 0), acol1 = tm_lane + col_a(slot, 1);
+      for (int q = g; q < nq; q += 3) {
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+        if (q < nq_real) {
+          const uint32_t qo = 16u * (uint32_t)q;
+          float4 w[9];
+#pragma unroll
+          for (int k = 0; k < 9; ++k) w[k] = lds4(dww_a + (uint32_t)k * k16_b + qo);
+          const float4 bias = lds4(dwb_a + qo);
+          const uint32_t pa = st_a + qo;
+          if (S == 1) {
+            // rows 0..3 of the window feed output rows 0 (rows 0-2) and 1 (rows 1-3); each output: bias, then taps in (ky, kx) order
+            float4 v[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c] = lds4(pa + (uint32_t)c * ks_b);
+            a0 = bias;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) fma4(a0, v[c], w[c]);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c] = lds4(pa + row_b + (uint32_t)c * ks_b);
+            a1 = bias;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { fma4(a0, v[c], w[3 + c]); fma4(a1, v[c], w[c]); }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c] = lds4(pa + 2u * row_b + (uint32_t)c * ks_b);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { fma4(a0, v[c], w[6 + c]); fma4(a1, v[c], w[3 + c]); }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c] = lds4(pa + 3u * row_b + (uint32_t)c * ks_b);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) fma4(a1, v[c], w[6 + c]);
+          } else {
+            a0 = bias;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) fma4(a0, lds4(pa + (uint32_t)(k / 3) * row_b + (uint32_t)(k % 3) * ks_b), w[k]);
+          }
+        }
+        split_store_tmem(acol0 + 2u * (uint32_t)q, 32u, a0);
+        if (S == 1) split_store_tmem(acol1 + 2u * (uint32_t)q, 32u, a1);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full + 8u * (uint32_t)slot);
+      if (i > 0) epilogue(i - 1);                      // the previous tile's MMAs ran during this tile's depthwise
+    }
+    if (n_my > 0) epilogue(n_my - 1);
+  } else if (warp == kC) {
+    // =============================== TMA producer ===============================================================
+    if (lane == 0) {
+      for (int i = 0; i < n_my; ++i) {
+        const int stage = i % NS;
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int b = tile / tpi, trem = tile - b * tpi, ty = trem / tiles_x, tx = trem - ty * tiles_x;
+        if (i >= NS) mbar_wait(in_empty + 8u * (uint32_t)stage, (uint32_t)(((i / NS) - 1) & 1));
+        const uint32_t bar = in_full + 8u * (uint32_t)stage;
+        mbar_expect_tx(bar, (uint32_t)((S == 1 ? 18 * 18 : 17 * 33) * p.KS) * 4u);
+        const int ix0 = S == 1 ? tx * TW - 1 : tx * TW * 2, iy0 = S == 1 ? ty * TH - 1 : ty * TH * 2;
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                     ::"r"(ring_a + (uint32_t)stage * stage_b), "l"(&tmap), "r"(0), "r"(ix0), "r"(iy0), "r"(b), "r"(bar) : "memory");
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== MMA issuer =================================================================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Npad >> 3) << 17) | ((128u >> 4) << 24);       // D f32, A / B f16, K-major
+      const uint32_t sbo = (uint32_t)(p.K16 >> 3) * 128u;
+      const uint32_t b_hi = ((sbo >> 4) & 0x3FFFu) | (1u << 14);
+      const uint32_t b_lo0 = ((smem_u32(sRec) & 0x3FFFFu) >> 4) | ((kLBO >> 4) << 16);
+      const int ksteps = p.K16 >> 4;
+      for (int i = 0; i < n_my; ++i) {
+        const int slot = i & 1;
+        mbar_wait(a_full + 8u * (uint32_t)slot, (uint32_t)((i >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const uint32_t dcol = tmem_base + col_d(slot, t), acol = tmem_base + col_a(slot, t);
+          uint32_t acc = 0u;
+#pragma unroll 1
+          for (int part = 0; part < 2; ++part)
+#pragma unroll 1
+            for (int ks = 0; ks < ksteps; ++ks) {
+              mma_ts_f16(dcol, acol + 32u * (uint32_t)part + 8u * (uint32_t)ks, b_lo0 + 16u * (uint32_t)ks, b_hi, idesc, acc);
+              acc = 1u;
+            }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(d_full + 8u * (uint32_t)slot) : "memory");
+      }
+    }
+    __syncwarp();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == kC + 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+
+bool ts_tensor_map(const BlockTsP& p, int cap, CUtensorMap* out) {
+  typedef std::tuple<const void*, int, int, int, int, int, int, long long> Key;
+  static std::mutex mu;
+  static std::map<Key, CUtensorMap> cache;
+  Key key(p.in, cap, p.H, p.W, p.CinS, p.KS, p.stride, p.in_istride);
+  std::lock_guard<std::mutex> g(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return true; }
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t gdim[4] = {(cuuint64_t)p.CinS, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)cap};
+  cuuint64_t gstr[3] = {(cuuint64_t)p.CinS * 4, (cuuint64_t)p.W * p.CinS * 4, (cuuint64_t)p.in_istride * 4};
+  cuuint32_t box[4] = {(cuuint32_t)p.KS, p.stride == 1 ? 18u : 33u, p.stride == 1 ? 18u : 17u, 1u};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap tm;
+  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.in), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  if (cache.size() > 256) cache.clear();
+  cache[key] = tm;
+  *out = tm;
+  return true;
+}
+
+template <int S>
+bool launch_ts(const CUtensorMap& tm, const BlockTsP& p, int B, cudaStream_t s) {
+  static std::mutex mu;
+  static std::map<int, size_t> cur;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  {
+    std::lock_guard<std::mutex> g(mu);
+    size_t& c = cur[dev];
+    if (p.smem_bytes > c) {
+      if (cudaFuncSetAttribute(k_block_ts<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes) != cudaSuccess) return false;
+      c = p.smem_bytes;
+    }
+  }
+  const int ntiles = B * (p.OW / 16) * (p.OH / (S == 1 ? 16 : 8));
+  const int grid = std::max(1, std::min(ntiles, sms));
+  k_block_ts<S><<<grid, kThreads, p.smem_bytes, s>>>(tm, p, B);
+  return true;
+}
+
+}  // namespace
+
+size_t ts_smem_bytes(int rec_bytes, int Npad, int ns, int stage_bytes) {
+  return (size_t)rec_bytes + (size_t)Npad * 4 + 32 * 8 + 128 + (size_t)ns * stage_bytes + 128;
+}
+
+bool launch_block_ts(const BlockTsP& p, int B, int cap, cudaStream_t s) {
+  if (B <= 0) return true;
+  CUtensorMap tm;
+  if (!ts_tensor_map(p, cap, &tm)) return false;
+  return p.stride == 1 ? launch_ts<1>(tm, p, B, s) : launch_ts<2>(tm, p, B, s);
+}
+
+}  // namespace fdt

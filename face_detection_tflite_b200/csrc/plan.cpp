@@ -399,7 +399,61 @@ struct Builder {
       F->st.dwb = push(dbv, kp);
     }
     F->st.macs = (double)OH * OW * ((double)Cin * st.Cout + (st.has_dw ? 9.0 * Cin : 0.0));
+    if (tc && F->st.kind == kStepBlockWs) plan_ts(&F->st, st_in, OH, OW, alpha_tf >= 0);
     return true;
+  }
+
+  // Re-plans a kStepBlockWs BlazeBlock for k_block_ts (kernels_ts.cu) when the layer qualifies: fp16-exact weights, at most
+  // 64 input / output channels (two tile slots of operand + accumulator fit the 512 TMEM columns), output tiled by 16 x 16
+  // (stride 1) or 8 x 16 (stride 2), residual = the block's own input.  The k_block_ws record stays in the blob (the tail
+  // fusion and FDT_TS=0 use it).
+  void plan_ts(PStep* st, const TfTensor& in, int OH, int OW, bool prelu) {
+    static const int want = [] { const char* e = std::getenv("FDT_TS"); return e ? std::atoi(e) : 0; }();
+    if (!want || !st->has_dw || st->c2 > 0 || st->w_parts != 1 || prelu) return;
+    if (st->act != kActRelu && st->act != kActNone) return;
+    const int Cin = in.dim(3), K16 = ru(Cin, 16), Npad = ru(st->Cout, 16);
+    if (K16 > 64 || Npad > 64) return;
+    if (st->dws == 1 ? (OH % 16 || OW % 16 || st->dpt != 1 || st->dpl != 1)
+                     : (OH % 8 || OW % 16 || st->dpt != 0 || st->dpl != 0 || in.dim(1) != 2 * OH || in.dim(2) != 2 * OW)) return;
+    int res = 0;
+    if (st->res_mode != 0) {
+      if (st->res_mode != 1) return;
+      res = st->res_pool ? 2 : 1;
+      if ((res == 2) != (st->dws == 2)) return;
+    }
+    // weights back from the k_block_ws operand layout (exact values) -> fp16 UMMA K-major core matrices
+    const size_t SBO8 = (size_t)(st->K8 / 4) * 128, SBO16 = (size_t)(K16 / 8) * 128;
+    std::vector<uint16_t> wh((size_t)Npad * K16, 0);
+    for (int n = 0; n < st->Cout; ++n)
+      for (int k = 0; k < Cin; ++k) {
+        const float v = P.blob[(size_t)st->w + ((size_t)(n >> 3) * SBO8 + (size_t)(k >> 2) * 128 + (size_t)(n & 7) * 16 + (size_t)(k & 3) * 4) / 4];
+        const uint16_t hbits = f32_to_f16(v);
+        if (f16_to_f32(hbits) != v) return;
+        wh[((size_t)(n >> 3) * SBO16 + (size_t)(k >> 3) * 128 + (size_t)(n & 7) * 16 + (size_t)(k & 7) * 2) / 2] = hbits;
+      }
+    std::vector<float> rec(wh.size() / 2 + (size_t)10 * K16, 0.f);
+    std::memcpy(rec.data(), wh.data(), wh.size() * 2);
+    float* dw = rec.data() + wh.size() / 2;
+    for (int k = 0; k < 9; ++k)
+      for (int c = 0; c < Cin; ++c) dw[(size_t)k * K16 + c] = P.blob[(size_t)st->dww + (size_t)k * st->K8 + c];
+    for (int c = 0; c < Cin; ++c) dw[(size_t)9 * K16 + c] = P.blob[(size_t)st->dwb + c];
+    std::vector<float> bias((size_t)Npad, 0.f);
+    for (int n = 0; n < st->Cout; ++n) bias[n] = P.blob[(size_t)st->bias + n];
+    const int KS = odd_quads(ru(Cin, 4));
+    const int px = st->dws == 1 ? 18 * 18 : 17 * 33;
+    const int stage_bytes = (px * KS * 4 + 127) / 128 * 128;
+    const size_t head = rec.size() * 4 + (size_t)Npad * 4 + 32 * 8 + 256;
+    int ns = (int)(((size_t)220 * 1024 - head) / stage_bytes);
+    if (ns < 2) return;
+    if (ns > 4) ns = 4;
+    st->ts_rec = push(rec, rec.size());
+    st->ts_bias = push(bias, bias.size());
+    st->ts_rec_bytes = (int)(rec.size() * 4);
+    st->ts_k16 = K16; st->ts_npad = Npad; st->ts_ks = KS; st->ts_ns = ns; st->ts_stage_bytes = stage_bytes;
+    st->ts_res = res; st->ts_relu = st->act == kActRelu ? 1 : 0;
+    st->TH = st->dws == 1 ? 16 : 8; st->TW = 16; st->G = 1;
+    st->smem = head + (size_t)ns * stage_bytes;
+    st->kind = kStepBlockTs;
   }
 
   // ---- tensor-core variant of a fused pointwise step -------------------------------------------
@@ -798,7 +852,7 @@ struct Builder {
   void fuse_tail() {
     const int S = (int)P.steps.size();
     auto block_ok = [&](const PStep& s) {
-      if (s.kind != kStepBlockWs || s.w_parts != 1 || s.in < 0) return false;
+      if ((s.kind != kStepBlockWs && s.kind != kStepBlockTs) || s.w_parts != 1 || s.in < 0) return false;
       const PTensor& in = P.tensors[s.in];
       const PTensor& out = P.tensors[s.out];
       if (in.H * in.W > 256 || in.root >= 0 || in.C > 128 || s.Cout > 128) return false;
@@ -1151,7 +1205,7 @@ bool Plan::build(const TfModel& m, int fuse, std::string* err, bool use_tc) {
 }
 
 std::string Plan::describe() const {
-  static const char* kn[] = {"normalize", "naive_conv", "gemm_conv", "dwpw", "add", "act", "padc", "maxpool", "resize", "stem", "dwpw_tc", "stem_tc", "block_ws", "stem_ws", "tail_ws", "fc_tc"};
+  static const char* kn[] = {"normalize", "naive_conv", "gemm_conv", "dwpw", "add", "act", "padc", "maxpool", "resize", "stem", "dwpw_tc", "stem_tc", "block_ws", "stem_ws", "tail_ws", "fc_tc", "block_ts"};
   std::string s;
   char buf[512];
   double macs = 0;

@@ -26,7 +26,7 @@ struct PTensor {
 };
 
 enum StepKind { kStepNormalize, kStepNaiveConv, kStepGemmConv, kStepDwPw, kStepAdd, kStepAct, kStepPadC,
-                kStepMaxPool, kStepResize, kStepStem, kStepDwPwTc, kStepStemTc, kStepBlockWs, kStepStemWs, kStepTailWs, kStepFcTc };
+                kStepMaxPool, kStepResize, kStepStem, kStepDwPwTc, kStepStemTc, kStepBlockWs, kStepStemWs, kStepTailWs, kStepFcTc, kStepBlockTs };
 
 struct PStep {
   StepKind kind = kStepAct;
@@ -47,6 +47,9 @@ struct PStep {
   int out2 = -1, c1 = 0, c2 = 0;                        // two heads in one launch: columns [0,c1) -> out, [c1,c1+c2) -> out2   // warp-specialised variant: input stages, A buffers, depthwise warps
   int fh = 1, fw = 1, align = 0, half = 0;
   std::vector<int> extra_out;   // further tensors the step materialises (k_tail_ws: every graph output of the fused tail)
+  // k_block_ts (kernels_ts.cu): fp16 weight record, staged pixel stride, input ring
+  long long ts_rec = -1, ts_bias = -1;
+  int ts_rec_bytes = 0, ts_k16 = 0, ts_npad = 0, ts_ks = 0, ts_ns = 0, ts_stage_bytes = 0, ts_res = 0, ts_relu = 0;
   // k_tail_ws: the layer program and its shared-memory geometry (see kernels_tail.cu)
   std::vector<TailLayerD> tail;
   std::vector<int> tail_outs;   // PTensor ids the heads write, indexed by TailLayerD::o1 / o2

@@ -34,21 +34,31 @@ struct Reader {
   size_t n;
   bool ok = true;
 
+  // every offset comes from untrusted model bytes: compare without forming o + size (which could wrap)
   template <typename T> T rd(size_t o) {
-    if (o + sizeof(T) > n) { ok = false; return T(0); }
+    if (o > n || sizeof(T) > n - o) { ok = false; return T(0); }
     T v;
     std::memcpy(&v, b + o, sizeof(T));
     return v;
   }
-  size_t indirect(size_t o) { return o + rd<uint32_t>(o); }
+  size_t indirect(size_t o) {
+    const uint32_t d = rd<uint32_t>(o);
+    if (!ok || d > n - o) { ok = false; return n; }      // n: a position every later read rejects
+    return o + d;
+  }
   // absolute position of `slot` in table, 0 if absent
   size_t field(size_t table, int slot) {
     int32_t so = rd<int32_t>(table);
-    size_t vt = (size_t)((long long)table - so);
+    if (!ok) return 0;
+    const long long vtl = (long long)table - so;
+    if (vtl < 0 || (unsigned long long)vtl > n || n - (size_t)vtl < 4) { ok = false; return 0; }   // vtable must lie inside the buffer
+    size_t vt = (size_t)vtl;
     uint16_t vsize = rd<uint16_t>(vt);
+    if (vsize < 4 || vsize > n - vt) { ok = false; return 0; }
     size_t e = 4 + 2 * (size_t)slot;
     if (e + 2 > vsize) return 0;
     uint16_t off = rd<uint16_t>(vt + e);
+    if (off && off > n - table) { ok = false; return 0; }
     return off ? table + off : 0;
   }
   bool vec(size_t table, int slot, size_t* start, uint32_t* len) {
@@ -56,6 +66,7 @@ struct Reader {
     if (!p) { *start = 0; *len = 0; return false; }
     size_t v = indirect(p);
     *len = rd<uint32_t>(v);
+    if (!ok) { *start = 0; *len = 0; return false; }
     *start = v + 4;
     return ok;
   }
@@ -63,7 +74,7 @@ struct Reader {
     size_t s; uint32_t l;
     std::vector<size_t> r;
     if (!vec(table, slot, &s, &l)) return r;
-    if (s + 4ull * l > n) { ok = false; return r; }
+    if (s > n || 4ull * l > n - s) { ok = false; return r; }
     for (uint32_t i = 0; i < l; ++i) r.push_back(indirect(s + 4ull * i));
     return r;
   }
@@ -71,7 +82,7 @@ struct Reader {
     size_t s; uint32_t l;
     std::vector<int> r;
     if (!vec(table, slot, &s, &l)) return r;
-    if (s + 4ull * l > n) { ok = false; return r; }
+    if (s > n || 4ull * l > n - s) { ok = false; return r; }
     for (uint32_t i = 0; i < l; ++i) r.push_back(rd<int32_t>(s + 4ull * i));
     return r;
   }
@@ -100,7 +111,7 @@ bool TfModel::parse(const uint8_t* data, size_t len, std::string* err) {
   for (size_t t : r.tables(root, 4)) {
     Buf b{0, 0};
     r.vec(t, 0, &b.s, &b.l);
-    if (b.s + b.l > blob.size()) return fail("buffer out of range");
+    if (!r.ok || b.s > blob.size() || b.l > blob.size() - b.s) return fail("buffer out of range");
     bufs.push_back(b);
   }
   auto sgs = r.tables(root, 2);
@@ -112,8 +123,20 @@ bool TfModel::parse(const uint8_t* data, size_t len, std::string* err) {
     x.dtype = r.scalar<int8_t>(t, 1, 0);
     uint32_t bi = r.scalar<uint32_t>(t, 2, 0);
     size_t s; uint32_t l;
-    if (r.vec(t, 3, &s, &l) && s + l <= blob.size()) x.name.assign((const char*)blob.data() + s, l);
+    if (r.vec(t, 3, &s, &l) && s <= blob.size() && l <= blob.size() - s) x.name.assign((const char*)blob.data() + s, l);
     if (bi < bufs.size() && bufs[bi].l) { x.data = blob.data() + bufs[bi].s; x.nbytes = bufs[bi].l; }
+    // shapes size every device buffer downstream: positive dims, bounded element count, constant payload of the right size
+    if (x.shape.size() > 6) return fail("tensor rank above 6");
+    unsigned long long numel = 1;
+    for (int d : x.shape) {
+      if (d <= 0) return fail("tensor with a non-positive dimension");
+      numel *= (unsigned long long)d;
+      if (numel > (1ull << 31)) return fail("tensor too large");
+    }
+    if (x.data) {
+      const unsigned long long esz = x.dtype == kTfF16 ? 2 : 4;
+      if ((x.dtype == kTfF32 || x.dtype == kTfF16 || x.dtype == kTfI32) && x.nbytes != numel * esz) return fail("constant tensor payload does not match its shape");
+    }
     tensors.push_back(std::move(x));
   }
   inputs = r.ints(sg, 1);
@@ -153,12 +176,30 @@ bool TfModel::parse(const uint8_t* data, size_t len, std::string* err) {
         default: break;
       }
     }
-    for (int i : op.in) if (i >= (int)tensors.size()) return fail("op input out of range");
+    for (int i : op.in) if (i < -1 || i >= (int)tensors.size()) return fail("op input out of range");   // -1 = optional input absent
+    if (op.code != kOpDequantize && op.code != kOpReshape && !op.in.empty() && op.in[0] < 0) return fail("op without a data input");
+    if (op.stride_w < 1 || op.stride_h < 1 || op.stride_w > 16 || op.stride_h > 16 || op.filter_w < 1 || op.filter_h < 1 || op.filter_w > 64 ||
+        op.filter_h > 64 || op.dil_w < 1 || op.dil_h < 1) return fail("op with out-of-range stride / filter / dilation");
     for (int i : op.out) if (i < 0 || i >= (int)tensors.size()) return fail("op output out of range");
+    // arity of the ops the planner dereferences: required inputs present and not the "absent" marker
+    auto need = [&](size_t k) {
+      if (op.in.size() < k) return false;
+      for (size_t j = 0; j < k; ++j) if (op.in[j] < 0) return false;
+      return true;
+    };
+    bool arity = !op.out.empty();
+    switch (op.code) {
+      case kOpConv2D: case kOpDwConv2D: case kOpPrelu: case kOpPad: case kOpAdd: arity = arity && need(2); break;
+      case kOpConcat: arity = arity && !op.in.empty() && need(op.in.size()); break;
+      default: arity = arity && need(1); break;
+    }
+    if (!arity) return fail("op with missing inputs / outputs");
     ops.push_back(std::move(op));
   }
   if (!r.ok) return fail("truncated flatbuffer");
   if (inputs.empty() || outputs.empty()) return fail("graph without inputs/outputs");
+  for (int i : inputs) if (i < 0 || i >= (int)tensors.size()) return fail("graph input out of range");
+  for (int i : outputs) if (i < 0 || i >= (int)tensors.size()) return fail("graph output out of range");
   return true;
 }
 
@@ -180,7 +221,7 @@ bool TfModel::const_f32(int tensor, std::vector<float>* out) const {
   const TfTensor* t = &tensors[tensor];
   if (!t->data) {  // follow DEQUANTIZE
     int p = producer(tensor);
-    if (p < 0 || ops[p].code != kOpDequantize || ops[p].in.empty()) return false;
+    if (p < 0 || ops[p].code != kOpDequantize || ops[p].in.empty() || ops[p].in[0] < 0) return false;
     t = &tensors[ops[p].in[0]];
     if (!t->data) return false;
   }

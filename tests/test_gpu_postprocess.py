@@ -1,8 +1,9 @@
 """k_decode_nms (threshold -> decode -> degenerate filter -> weighted NMS -> letterbox removal) on caller-supplied
 tensors through fdt_debug_decode / fdt_debug_nms: the reference's own unit-test vectors, verbatim, and crafted edge
 cases (NaN, degenerate boxes, score ties, more than maxDet clusters, IoU exactly at the threshold) — each compared
-with the oracle on the same inputs.  Integer / index results are bit-exact; boxes are f64-identical because the
-kernel accumulates a cluster in the same order as the reference (sorted order, one thread)."""
+with the oracle on the same inputs.  Integer / index results are bit-exact; from decoded detections (fdt_debug_nms) boxes
+are f64-identical because the kernel accumulates a cluster in the same order as the reference (sorted order, one
+thread); from raw heads the score goes through exp(), whose last bit differs between CUDA and glibc."""
 import math
 
 import numpy as np
@@ -38,6 +39,17 @@ def assert_same(got, want):
         assert g["index"] == w.anchor
         assert g["box"] == (w.xmin, w.ymin, w.xmax, w.ymax)          # f64-identical
         assert g["score"] == w.score and g["kp"] == list(w.kp)
+
+
+def assert_close(got, want):
+    """From raw heads the score passes through exp(): CUDA's f64 exp is within 1 ulp of glibc's, not identical, and the
+    score weights the cluster sums - indices stay exact, values agree to ~1e-15."""
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert g["index"] == w.anchor
+        assert abs(g["score"] - w.score) <= 4e-16
+        for a, b in zip(list(g["box"]) + g["kp"], [w.xmin, w.ymin, w.xmax, w.ymax] + list(w.kp)):
+            assert abs(a - b) <= 1e-13 * max(1.0, abs(b))
 
 
 # ---- the reference's vectors, verbatim ------------------------------------------------------------------
@@ -80,8 +92,8 @@ def test_web_decode_vectors(det, case):
     want = dp.to_detections_filtered(dp.decode_boxes(boxes, np.array(rv.DECODE_ANCHORS), idx, int(rv.DECODE_SCALE)), sc, idx)
     assert [d.anchor for d in want] == case["expect_anchors"]
     assert len(dec) == len(idx) and len(kept) == len(want)
-    for row, w in zip(kept, want):                               # decoded candidates: bit-identical to the oracle
-        assert tuple(row[:4]) == (w.xmin, w.ymin, w.xmax, w.ymax) and row[4] == w.score and list(row[5:17]) == w.kp
+    for row, w in zip(kept, want):                               # decoded candidates: boxes / keypoints bit-identical to the oracle
+        assert tuple(row[:4]) == (w.xmin, w.ymin, w.xmax, w.ymax) and abs(row[4] - w.score) <= 4e-16 and list(row[5:17]) == w.kp
     if "expect_xmin1" in case:
         assert kept[1][0] == pytest.approx(case["expect_xmin1"], abs=case["tol"])
     assert sorted(f["index"] for f in faces[0]) == case["expect_anchors"]      # IoU threshold 1.0: nothing merges
@@ -109,12 +121,7 @@ def test_nan_and_degenerate_inputs(det):
     assert hot[0] not in idx and hot[1] in idx and hot[2] in idx and hot[3] not in idx
     assert list(dec[0][:, 17].nonzero()[0]) == [k for k, i in enumerate(idx) if not (boxes[i, 2] <= 0 or boxes[i, 3] <= 0)]
     want = dp.weighted_nms(dp.to_detections_filtered(dp.decode_boxes(boxes, anchors, idx, 128), sc, idx))
-    got = faces[0]
-    assert len(got) == len(want)
-    for g, w in zip(got, want):
-        assert g["index"] == w.anchor and g["score"] == w.score
-        for a, b in zip(g["box"], (w.xmin, w.ymin, w.xmax, w.ymax)):
-            assert (a == b) or (math.isnan(a) and math.isnan(b))
+    assert_close(faces[0], want)
 
 
 def test_score_ties_keep_anchor_order(det):
@@ -179,5 +186,5 @@ def test_random_heads_full_range_anchor_count(lib):
     for b in range(B):
         want = dp.postprocess(boxes[b], scores[b], anchors, 192, (42 / 192, 42 / 192, 0.0, 0.0))
         assert len(want) >= 20
-        assert_same(faces[b], want)
+        assert_close(faces[b], want)
     d.dispose()

@@ -161,3 +161,43 @@ def test_warp_specialised_plans_respect_the_hardware_limits(lib, model_bytes, mo
             assert nd in (8, 12) and rs in (1, 2, 4) and g * th * tw <= 128, line
             assert (th - 1) * 2 + 3 <= 256 and (tw - 1) * 2 + 3 <= 256 and g <= 256, line
     assert n_ws >= 10, "the conv stack should run on the warp-specialised kernels"
+
+
+def test_malformed_models_are_rejected_not_crashed(model_bytes):
+    """The model bytes reach the flatbuffer reader through the public API (fdt_create / FaceDetector.create
+    detectorBytes): truncated and bit-flipped buffers must come back as FDT_ERR_MODEL (or parse), never crash.
+    Runs in a subprocess so that a wild read fails the test instead of killing the suite."""
+    import subprocess
+    import sys
+    script = r"""
+import sys, ctypes as C
+sys.path.insert(0, %r)
+import numpy as np
+from face_detection_tflite_b200 import _ffi
+lib = _ffi.load()
+buf = C.create_string_buffer(1 << 16)
+rng = np.random.default_rng(7)
+n_ok = n_bad = 0
+for name in ("face_detection_short_range.tflite", "face_landmark.tflite", "iris_landmark.tflite"):
+    good = open(%r + "/assets/models/" + name, "rb").read()
+    assert lib.fdt_host_plan_describe(good, len(good), 1, buf, len(buf)) == 0
+    cases = [good[:k] for k in (0, 3, 16, 64, 1000, len(good) // 2, len(good) - 1)]
+    head = min(len(good), 200000)
+    for _ in range(250):
+        b = bytearray(good)
+        for _ in range(int(rng.integers(1, 6))):
+            # structural bytes live at the head (root, vtables of operators / tensors near the end): hit both regions
+            pos = int(rng.integers(0, 4096)) if rng.random() < 0.3 else int(len(good) - 1 - rng.integers(0, min(len(good), 60000)))
+            b[pos] = int(rng.integers(0, 256))
+        cases.append(bytes(b))
+    for c in cases:
+        rc = lib.fdt_host_plan_describe(c, len(c), 1, buf, len(buf))
+        assert rc in (0, _ffi.FDT_ERR_MODEL), rc
+        n_ok += rc == 0
+        n_bad += rc != 0
+print("survived", n_ok, n_bad)
+""" % (str(ROOT), str(ROOT))
+    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "survived" in r.stdout, (r.returncode, r.stdout[-300:], r.stderr[-1500:])
+    n_bad = int(r.stdout.split()[-1])
+    assert n_bad >= 30            # the mutations do reach the validation paths

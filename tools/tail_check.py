@@ -15,9 +15,10 @@ from oracle.pipeline import OraclePipeline
 
 out = ROOT / "gpurun_out"
 out.mkdir(exist_ok=True)
-tail = os.environ.get("FDT_TAIL", "0")
+tail = os.environ.get("FDT_TAIL", "0") + "/ts" + os.environ.get("FDT_TS", "0")
+base_run = os.environ.get("FDT_TAIL", "0") == "0" and os.environ.get("FDT_TS", "0") == "0"
 for model, f in (("shortRange", "face_detection_short_range.tflite"), ("backCamera", "face_detection_back.tflite")):
-    d = fdt.FaceDetector.create(fdt.FaceDetectionModel[model], withMesh=False, maxBatch=int(os.environ.get("CHUNK", "16")))
+    d = fdt.FaceDetector.create(fdt.FaceDetectionModel[model], withMesh=False, maxBatch=int(os.environ.get("CHUNK", "64")))
     img = cv2.imread(str(ROOT / "assets/samples/landmark-ex1.jpg"))
     img = cv2.resize(img, (1280, 720))
     frames = np.concatenate([np.stack([img, img[:, ::-1].copy(), img[::-1].copy()]), synth.face_frames(34, 1280, 720, start=2), synth.noise_frames(3, 1280, 720)])
@@ -27,7 +28,7 @@ for model, f in (("shortRange", "face_detection_short_range.tflite"), ("backCame
     boxes, scores = d.debugRawHeads(min(n, d.maxBatch))
     print(model, "tail", tail, "launches", d.lastLaunchCount(), "faces", int(counts.sum()), "%.2fs" % (time.time() - t), flush=True)
     ref = out / ("heads_%s.npz" % model)
-    if tail == "0":
+    if base_run:
         np.savez(ref, boxes=boxes, scores=scores, counts=counts)
     elif ref.exists():
         r = np.load(ref)
