@@ -347,8 +347,9 @@ def main():
             ndet = len(kernels)
             if standard:
                 # mesh net: per-step timing over the crops the last call left in the stage buffers (units = faces)
-                ns = C.c_int32()
-                nf = min(faces_found, 2 * n)
+                ns, got = C.c_int32(), C.c_int32()
+                lib.fdt_debug_get_mesh_stage(h, 0, None, None, None, C.byref(got))     # crops the last mesh pass left in the stage buffers
+                nf = got.value
                 if nf > 0 and lib.fdt_profile_net(h, 1, nf, 10, arr, cap, C.byref(ns)) == 0:
                     for i in range(ns.value):
                         lib.fdt_get_net_step_info(h, 1, i, kn, tn, 160, C.byref(macs), C.byref(byt))

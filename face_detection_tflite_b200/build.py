@@ -25,7 +25,6 @@ SOURCES = {
     "fdt_api.cu": [],
     "kernels_naive.cu": [],
     "kernels_tiled.cu": [],
-    "kernels_tc.cu": [],
     "kernels_ws.cu": [],
     "kernels_tail.cu": [],
     "kernels_ts.cu": [],

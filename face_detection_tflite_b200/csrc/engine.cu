@@ -106,18 +106,6 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         launch_stem(p, B, s, cta_cap(st.smem, 32 * (st.NC / 4)));
         break;
       }
-      case kStepStemTc: {
-        StemTcP p;
-        const PTensor& it = plan_.tensors[st.in];
-        p.in8 = in_u8; p.H = it.H; p.W = it.W; p.OH = out.H; p.OW = out.W;
-        p.kw = st.kw; p.pt = st.pt; p.pl = st.pl;
-        p.out = out.p; p.out_istride = out.istride; p.Cout = st.Cout; p.CoutS = out.Cs;
-        p.vec_store = (out.Cs % 4 == 0 && out.istride % 4 == 0 && ((size_t)out.p % 16 == 0)) ? ((out.Cs % 8 == 0 && out.istride % 8 == 0 && ((size_t)out.p % 32 == 0)) ? 2 : 1) : 0;   // 2: 32-byte stores allowed
-        p.wB = blob + st.w; p.bias = blob + st.bias; p.alpha = st.alpha >= 0 ? blob + st.alpha : nullptr;
-        p.act = st.act; p.Npad = st.Npad; p.tmem_cols = st.tmem_cols; p.w_parts = st.w_parts; p.smem_bytes = st.smem;
-        launch_stem_tc(p, B, s);
-        break;
-      }
       case kStepStemWs: {
         StemWsP p;
         const PTensor& it = plan_.tensors[st.in];
@@ -186,7 +174,7 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         launch_dwpw(p, B, s, cta_cap(st.smem, st.NPG * (st.NC / 4)));
         break;
       }
-      case kStepDwPwTc: case kStepBlockWs: {
+      case kStepBlockWs: {
         DwPwTcP p;
         TV iv = view(ctx, st.in);
         p.in = iv.p; p.in_istride = iv.istride; p.H = iv.H; p.W = iv.W; p.Cin = iv.C; p.CinS = iv.Cs;
@@ -225,12 +213,8 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
           p.out2 = o2.p; p.out2_istride = o2.istride; p.Cs2 = o2.Cs; p.c1 = st.c1; p.c2 = st.c2;
           p.Cout = st.c1;                       // columns of the first output
         }
-        if (st.kind == kStepBlockWs) {
-          p.in_floats = st.in_stage_floats;
-          if (!launch_block_ws(p, B, ctx.cap, s)) { failed_ = true; fprintf(stderr, "fdt: cuTensorMapEncodeTiled failed for step '%s'\n", st.name.c_str()); }
-        } else {
-          launch_dwpw_tc(p, B, s, cta_cap(st.smem, 256));
-        }
+        p.in_floats = st.in_stage_floats;
+        if (!launch_block_ws(p, B, ctx.cap, s)) { failed_ = true; fprintf(stderr, "fdt: k_block_ws could not be launched for step '%s'\n", st.name.c_str()); }
         break;
       }
       case kStepTailWs: {

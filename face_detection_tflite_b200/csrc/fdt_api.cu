@@ -1357,7 +1357,7 @@ int32_t fdt_profile_chunk(fdt_handle* h, const uint8_t* d_frames, int32_t n, int
 }
 
 static const char* kKernelNames[] = {"k_normalize", "k_naive_conv", "k_gemm_conv", "k_dwpw", "k_add", "k_act", "k_padc", "k_maxpool",
-                                     "k_resize_bilinear", "k_stem", "k_dwpw_tc", "k_stem_tc", "k_block_ws", "k_stem_ws", "k_tail_ws", "k_fc_tc", "k_block_ts"};
+                                     "k_resize_bilinear", "k_stem", "k_block_ws", "k_stem_ws", "k_tail_ws", "k_fc_tc", "k_block_ts"};
 
 static void step_info(const Plan& p, const PStep& st, int in_w, int in_h, std::string* kname, std::string* tname, double* macs, double* bytes) {
   *kname = kKernelNames[st.kind]; *tname = st.name; *macs = st.macs;
@@ -1406,7 +1406,9 @@ int32_t fdt_profile_net(fdt_handle* h, int32_t which, int32_t n, int32_t repeats
   const int S = (int)e.plan().steps.size();
   if (out_steps) *out_steps = S;
   const int have = which == 1 ? h->last_mesh_faces : 2 * h->last_iris_faces;
-  if (n <= 0 || n > have || repeats <= 0) return fail(h, FDT_ERR_BAD_ARG, "n exceeds the crops left by the last call");
+  if (n <= 0 || n > have) n = have;                  // n <= 0: every crop the last call left
+  if (out_steps) out_steps[0] = S;
+  if (n <= 0 || repeats <= 0) return fail(h, FDT_ERR_BAD_ARG, "the last call left no crops in the stage buffers");
   if (!out_ms || capacity < S) return fail(h, FDT_ERR_SIZE_MISMATCH, "out_ms too small");
   cudaSetDevice(h->cfg.device);
   Slot& sl = h->slots[which == 1 ? h->last_mesh_slot : h->last_iris_slot];

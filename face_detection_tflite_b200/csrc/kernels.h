@@ -148,22 +148,9 @@ struct DwPwTcP {
   FastDiv fd_Q8, fd_IW, fd_IH, fd_TW, fd_thw, fd_tpg, fd_tilesX, fd_nstrips, fd_nslots;
   size_t smem_bytes;
 };
-void launch_dwpw_tc(const DwPwTcP& p, int B, cudaStream_t s, int max_ctas);
 // warp-specialised TMA / mbarrier pipeline version (kernels_ws.cu); `cap` = images the input tensor is allocated for.
 // Returns false when the tensor map could not be encoded (nothing launched).
 bool launch_block_ws(const DwPwTcP& p, int B, int cap, cudaStream_t s);
-
-// ---- stem on tensor cores: im2col GEMM from the u8x4 patch ----
-struct StemTcP {
-  const uint8_t* in8;       // [B][H][W][4] BGRX
-  int H, W, OH, OW, kw, pt, pl;
-  float* out; long long out_istride; int Cout, CoutS, vec_store;
-  const float* wB;          // [Npad x K8] UMMA K-major core-matrix layout, k = (ky*kw + kx)*3 + c
-  const float* bias; const float* alpha;
-  int act, Npad, tmem_cols, w_parts;
-  size_t smem_bytes;
-};
-void launch_stem_tc(const StemTcP& p, int B, cudaStream_t s);
 
 // ---- stem, warp-specialised: TMA patch ring -> exact fp16 im2col (16-byte copies) -> tcgen05 kind::f16 ----
 struct StemWsP {

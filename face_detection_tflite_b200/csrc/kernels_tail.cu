@@ -8,9 +8,11 @@
 //   input (16x16xC, HBM) --TMA--> buffer A [256 px][KSA] -- blocks @16x16 (in place) --> heads@16x16 -> HBM outputs
 //                                  '-- stride-2 block --> buffer B [64 px][KSB] -- blocks @8x8 (in place) --> heads@8x8 -> HBM
 //
-//   warps 0..11 (compute): per layer and 128-pixel tile, thread = (pixel = TMEM lane, a third of the channel quads):
-//       depthwise 3x3 from shared memory (fp32 FFMA2) -> fp16 hi + lo split -> tcgen05.st straight into TENSOR MEMORY
-//       (the A operand never touches shared memory); then the epilogue of the same tile: tcgen05.ld -> + bias
+//   warps 0..11 (compute): per layer, thread = (TMEM lane, a third of the channel quads).  A 16x16 map is two M-tiles, its
+//       even and its odd rows, so a thread owns two vertically adjacent pixels and feeds both depthwise outputs from one
+//       4 x 3 window of loads; an 8x8 map is one M-tile.  depthwise 3x3 from shared memory (fp32 FFMA2) -> fp16 hi + lo
+//       split -> tcgen05.st straight into TENSOR MEMORY (the A operand never touches shared memory), in two K halves so
+//       that the first half's MMAs overlap the second half's depthwise; then the epilogue: tcgen05.ld -> + bias
 //       + residual (same pixel / 2x2 max-pool of the source buffer) -> ReLU -> back into the activation buffer
 //       (heads: + bias -> graph outputs in HBM).
 //   warp 12, one lane (control): TMA of the next image, one bulk copy per layer of its weight record
@@ -19,8 +21,8 @@
 //       passes (A_hi, A_lo) - the detector's weights are fp16-origin and therefore exact, so the products carry
 //       ~22 mantissa bits like the TF32 hi/lo split of k_block_ws at half the MMA count.
 //
-// Hand-offs are mbarriers: w_full[2] (weights landed), a_full[2] (operand tile written, 384 arrivals), d_full[2]
-// (tcgen05.commit), in_full / a_free (image buffer).  One named barrier per layer orders the in-place epilogue
+// Hand-offs are mbarriers: w_full[2] (weights landed), a_full[2] (first / second K half of the operand written, one
+// arrival per warp), d_full (tcgen05.commit), in_full / a_free (image buffer).  One named barrier per layer orders the in-place epilogue
 // against the next layer's depthwise reads.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_tail_ws(const __grid_constant_
     if (lane == 0) {
       mbar_init(in_full, 1);
       mbar_init(a_free, kTC);
-      for (int i = 0; i < 2; ++i) { mbar_init(w_full + 8u * i, 1); mbar_init(a_full + 8u * i, kTComputeThreads); mbar_init(d_full + 8u * i, 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(w_full + 8u * i, 1); mbar_init(a_full + 8u * i, kTC); mbar_init(d_full + 8u * i, 1); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     }
@@ -148,76 +150,131 @@ __global__ void __launch_bounds__(kTThreads, 1) k_tail_ws(const __grid_constant_
   if (warp < kTC) {
     // =============================== compute warps ==============================================================
     const int lq = warp & 3, g = warp >> 2;                // TMEM lane quarter (hardware: warp % 4), channel-quad / column group
-    const int r = lq * 32 + lane;                           // row of the 128-pixel tile = TMEM lane
+    const int r = lq * 32 + lane;                           // row of the 128-pixel M-tile = TMEM lane
     const uint32_t tm_lane = tmem_base + ((uint32_t)(lq * 32) << 16);
-    uint32_t ph_a[2] = {0u, 0u}, ph_d[2] = {0u, 0u};
+    uint32_t ph_d = 0u;
     int gl = 0, it = 0;
     for (int img = blockIdx.x; img < B; img += gridDim.x, ++it) {
       mbar_wait(in_full, (uint32_t)(it & 1));
       for (int l = 0; l < nl; ++l, ++gl) {
-        const TailLayerD& L = sL[l];
+        const TailLayerD L = sL[l];                           // registers: the loops below must not re-read it from shared memory
         const uint32_t src_a = L.src ? bufB_a : bufA_a, dst_a = L.dst ? bufB_a : bufA_a;
         const uint32_t kss_b = L.src ? ksb_b : ksa_b, ksd_b = L.dst ? ksb_b : ksa_b;
         const int src_q = (int)(kss_b >> 4), dst_q = (int)(ksd_b >> 4);       // quads per pixel record
-        const int npix = L.OH * L.OW, ntiles = (npix + 127) >> 7;
-        const int nq = L.K16 >> 2, nq_real = (L.Cin + 3) >> 2;
+        const int npix = L.OH * L.OW;
+        // 256-pixel maps are split into the M-tiles "even rows" / "odd rows": a thread then owns the vertically adjacent
+        // pixels (2yy, x) and (2yy + 1, x) and feeds both depthwise outputs from ONE 4 x 3 window (6 instead of 9 LDS.128
+        // per output quad); smaller maps are one M-tile in row-major order
+        const bool paired = npix == 256 && L.OW == 16;
+        const int ntiles = paired ? 2 : 1;
+        const int nq = L.K16 >> 2, nq_real = (L.Cin + 3) >> 2, nq_half = (L.K16 >> 5) << 2;   // quads of the first K half (whole 16-wide K steps)
         const uint32_t wb_a = wring_a + (uint32_t)(gl & 1) * (uint32_t)p.wbuf_bytes;
         const uint32_t dww_a = wb_a + (uint32_t)(L.Npad * L.K16) * 2u, dwb_a = dww_a + 9u * (uint32_t)L.K16 * 4u;
         const uint32_t k16_b = (uint32_t)L.K16 * 4u;
+        const uint32_t acol0 = tm_lane + col_a(0), acol1 = tm_lane + col_a(1);
+        // this thread's output pixel(s): (oy, ox) of tile 0; tile 1 is (oy + 1, ox) when paired
+        int oy, ox;
+        if (paired) { oy = 2 * (r >> 4); ox = r & 15; }
+        else { oy = r / L.OW; ox = r - oy * L.OW; }
+        const bool act = paired || r < npix;
+        const int pix0 = oy * L.OW + ox;
         mbar_wait(w_full + 8u * (uint32_t)(gl & 1), (uint32_t)((gl >> 1) & 1));
         // ---- operand tiles: depthwise 3x3 (blocks) or the activation itself (heads) -> fp16 hi / lo -> TMEM ------------
-        for (int t = 0; t < ntiles; ++t) {
-          const int pix = t * 128 + r;
-          const bool act = pix < npix;
-          const uint32_t acol = tm_lane + col_a(t);
-          if (L.kind == 0) {
-            const int oy = act ? pix / L.OW : 0, ox = act ? pix - oy * L.OW : 0;
-            uint32_t off[9];
+        // The K range is produced in two halves with an mbarrier each, so that the MMAs of the first half run while the
+        // second half is still being computed.
+        if (L.kind == 0) {
+          // window offsets: rows oy*s - pad .. (+2, +3 when paired), cols ox*s - pad .. +2; SAME padding reads the zero slot
+          uint32_t off[12];
+          const int iy0 = oy * L.stride - L.pad, ix0 = ox * L.stride - L.pad;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) {
-              const int iy = oy * L.stride - L.pad + k / 3, ix = ox * L.stride - L.pad + k % 3;
-              const bool ok = act && (unsigned)iy < (unsigned)L.IH && (unsigned)ix < (unsigned)L.IW;
-              off[k] = ok ? src_a + (uint32_t)(iy * L.IW + ix) * kss_b : zero_a;      // SAME padding reads the zero slot
+          for (int k = 0; k < 12; ++k) {
+            const int iy = iy0 + k / 3, ix = ix0 + k % 3;
+            const bool ok = act && (unsigned)iy < (unsigned)L.IH && (unsigned)ix < (unsigned)L.IW;
+            off[k] = ok ? src_a + (uint32_t)(iy * L.IW + ix) * kss_b : zero_a;
+          }
+          bool half_done = false;
+          for (int q = g; q < nq; q += 3) {
+            if (!half_done && q >= nq_half) {
+              half_done = true;
+              asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) mbar_arrive(a_full);
             }
-            for (int q = g; q < nq; q += 3) {
-              float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (q < nq_real) {
-                const uint32_t qo = 16u * (uint32_t)q;
-                a = lds4(dwb_a + qo);                                             // bias, then the taps in (ky, kx) order
+            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+            if (q < nq_real) {
+              const uint32_t qo = 16u * (uint32_t)q;
+              float4 w[9];
 #pragma unroll
-                for (int k = 0; k < 9; ++k) fma4(a, lds4(off[k] + qo), lds4(dww_a + (uint32_t)k * k16_b + qo));
+              for (int k = 0; k < 9; ++k) w[k] = lds4(dww_a + (uint32_t)k * k16_b + qo);
+              const float4 bias = lds4(dwb_a + qo);
+              float4 v[3];
+              // each output: bias, then the taps in (ky, kx) order
+#pragma unroll
+              for (int c = 0; c < 3; ++c) v[c] = lds4(off[c] + qo);
+              a0 = bias;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) fma4(a0, v[c], w[c]);
+#pragma unroll
+              for (int c = 0; c < 3; ++c) v[c] = lds4(off[3 + c] + qo);
+              a1 = bias;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) { fma4(a0, v[c], w[3 + c]); if (paired) fma4(a1, v[c], w[c]); }
+#pragma unroll
+              for (int c = 0; c < 3; ++c) v[c] = lds4(off[6 + c] + qo);
+#pragma unroll
+              for (int c = 0; c < 3; ++c) { fma4(a0, v[c], w[6 + c]); if (paired) fma4(a1, v[c], w[3 + c]); }
+              if (paired) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[c] = lds4(off[9 + c] + qo);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) fma4(a1, v[c], w[6 + c]);
               }
-              split_store_tmem(acol + 2u * (uint32_t)q, a);
             }
-          } else {
-            const uint32_t px_a = act ? src_a + (uint32_t)pix * kss_b : zero_a;
-            for (int q = g; q < nq; q += 3) {
-              const float4 a = q < src_q ? lds4(px_a + 16u * (uint32_t)q) : make_float4(0.f, 0.f, 0.f, 0.f);
-              split_store_tmem(acol + 2u * (uint32_t)q, a);
-            }
+            split_store_tmem(acol0 + 2u * (uint32_t)q, a0);
+            if (paired) split_store_tmem(acol1 + 2u * (uint32_t)q, a1);
           }
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          mbar_arrive(a_full + 8u * (uint32_t)t);
+          __syncwarp();
+          if (lane == 0) { if (!half_done) mbar_arrive(a_full); mbar_arrive(a_full + 8u); }
+        } else {
+          const uint32_t px0 = act ? src_a + (uint32_t)pix0 * kss_b : zero_a;
+          const uint32_t px1 = px0 + (uint32_t)L.OW * kss_b;
+          bool half_done = false;
+          for (int q = g; q < nq; q += 3) {
+            if (!half_done && q >= nq_half) {
+              half_done = true;
+              asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) mbar_arrive(a_full);
+            }
+            const bool in = q < src_q;
+            split_store_tmem(acol0 + 2u * (uint32_t)q, in ? lds4(px0 + 16u * (uint32_t)q) : make_float4(0.f, 0.f, 0.f, 0.f));
+            if (paired) split_store_tmem(acol1 + 2u * (uint32_t)q, in ? lds4(px1 + 16u * (uint32_t)q) : make_float4(0.f, 0.f, 0.f, 0.f));
+          }
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) { if (!half_done) mbar_arrive(a_full); mbar_arrive(a_full + 8u); }
         }
         // ---- epilogue ---------------------------------------------------------------------------------------------------
+        // In-place layers: every depthwise read of the layer (all threads) must precede the first write; d_full implies it
+        // (the MMAs were issued after both operand barriers completed).
         const uint32_t bias_a = smem_u32(sBias + l * 128);
+        mbar_wait(d_full, ph_d);
+        ph_d ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t row_b = (uint32_t)L.IW * kss_b;
+#pragma unroll 1
         for (int t = 0; t < ntiles; ++t) {
-          if (t == 0) {
-            // in-place layers: every depthwise read of the layer (both tiles, all threads) must precede the first write
-            for (int u = 0; u < ntiles; ++u) { mbar_wait(a_full + 8u * (uint32_t)u, ph_a[u]); ph_a[u] ^= 1u; }
-          }
-          mbar_wait(d_full + 8u * (uint32_t)t, ph_d[t]);
-          ph_d[t] ^= 1u;
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const int pix = t * 128 + r;
-          const bool act = pix < npix;
+          const int pix = pix0 + t * L.OW;                     // tile 1 = the row below
           const uint32_t dcol = tm_lane + col_d(t);
           // residual source pixel(s)
           uint32_t res_a = zero_a;
           if (act && L.res == 1) res_a = src_a + (uint32_t)pix * kss_b;
-          if (act && L.res == 2) { const int oy = pix / L.OW, ox = pix - oy * L.OW; res_a = src_a + (uint32_t)((2 * oy) * L.IW + 2 * ox) * kss_b; }
-          const uint32_t row_b = (uint32_t)L.IW * kss_b;
+          if (act && L.res == 2) res_a = src_a + (uint32_t)((2 * oy) * L.IW + 2 * ox) * kss_b;
           const uint32_t out_a = dst_a + (uint32_t)(act ? pix : 0) * ksd_b;
           float* o1 = nullptr; float* o2 = nullptr;
           if (L.kind == 1) {
@@ -295,36 +352,37 @@ __global__ void __launch_bounds__(kTThreads, 1) k_tail_ws(const __grid_constant_
       load_weights(0);
       if (total > 1) load_weights(1);
     }
-    uint32_t ph_a[2] = {0u, 0u}, ph_d[2] = {0u, 0u};
+    uint32_t ph_a = 0u, ph_d = 0u;
     int gl = 0, it = 0;
     for (int img = blockIdx.x; img < B; img += gridDim.x, ++it) {
       for (int l = 0; l < nl; ++l, ++gl) {
         const TailLayerD& L = sL[l];
-        const int ntiles = (L.OH * L.OW + 127) >> 7;
+        const int ntiles = (L.OH * L.OW == 256 && L.OW == 16) ? 2 : 1;
         const uint32_t idesc = (1u << 4) | ((uint32_t)(L.Npad >> 3) << 17) | ((128u >> 4) << 24);     // D f32, A / B f16, K-major
         const uint32_t sbo = (uint32_t)(L.K16 >> 3) * 128u;
         const uint32_t b_hi = ((sbo >> 4) & 0x3FFFu) | (1u << 14);
         const uint32_t wb_a = wring_a + (uint32_t)(gl & 1) * (uint32_t)p.wbuf_bytes;
         const uint32_t b_lo0 = ((wb_a & 0x3FFFFu) >> 4) | ((kLBO >> 4) << 16);
-        const int ksteps = L.K16 >> 4;
+        const int ksteps = L.K16 >> 4, khalf = L.K16 >> 5;          // K steps of the first operand half
         mbar_wait(w_full + 8u * (uint32_t)(gl & 1), (uint32_t)((gl >> 1) & 1));
-        for (int t = 0; t < ntiles; ++t) {
-          mbar_wait(a_full + 8u * (uint32_t)t, ph_a[t]);
-          ph_a[t] ^= 1u;
+        for (int half = 0; half < 2; ++half) {
+          mbar_wait(a_full + 8u * (uint32_t)half, ph_a);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t dcol = tmem_base + col_d(t), acol = tmem_base + col_a(t);
-          uint32_t acc = 0u;
+          const int k0 = half ? khalf : 0, k1 = half ? ksteps : khalf;
+          for (int t = 0; t < ntiles; ++t) {
+            const uint32_t dcol = tmem_base + col_d(t), acol = tmem_base + col_a(t);
 #pragma unroll 1
-          for (int part = 0; part < 2; ++part)
-#pragma unroll 1
-            for (int ks = 0; ks < ksteps; ++ks) {
-              mma_ts_f16(dcol, acol + 64u * (uint32_t)part + 8u * (uint32_t)ks, b_lo0 + 16u * (uint32_t)ks, b_hi, idesc, acc);
-              acc = 1u;
+            for (int ks = k0; ks < k1; ++ks) {
+              mma_ts_f16(dcol, acol + 8u * (uint32_t)ks, b_lo0 + 16u * (uint32_t)ks, b_hi, idesc, ks ? 1u : 0u);
+              mma_ts_f16(dcol, acol + 64u + 8u * (uint32_t)ks, b_lo0 + 16u * (uint32_t)ks, b_hi, idesc, 1u);
             }
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(d_full + 8u * (uint32_t)t) : "memory");
+          }
         }
+        ph_a ^= 1u;
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(d_full) : "memory");
         // this layer's MMAs have read the weight buffer and every thread has read its taps: stream in the layer after next
-        for (int t = 0; t < ntiles; ++t) { mbar_wait(d_full + 8u * (uint32_t)t, ph_d[t]); ph_d[t] ^= 1u; }
+        mbar_wait(d_full, ph_d);
+        ph_d ^= 1u;
         if (gl + 2 < total) load_weights(gl + 2);
         if (l == p.last_a_layer && img + (int)gridDim.x < B) {
           mbar_wait(a_free, (uint32_t)(it & 1));

@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
     const int nq = p.K16 >> 2, nq_real = (p.Cin + 3) >> 2, ks_q = p.KS >> 2;
     const uint32_t rec_a = smem_u32(sRec), dww_a = rec_a + (uint32_t)(p.Npad * p.K16) * 2u, dwb_a = dww_a + 9u * (uint32_t)p.K16 * 4u;
     const uint32_t k16_b = (uint32_t)p.K16 * 4u, bias_a = smem_u32(sBias);
-    const int nc8 = p.Npad >> 3, couts = p.CoutS;
+    const int couts = p.CoutS, nc8 = (couts + 7) >> 3;             // 8-column groups that hold real channels
 
     auto epilogue = [&](int i) {
       const int slot = i & 1, stage = i % NS;

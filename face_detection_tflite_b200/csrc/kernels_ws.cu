@@ -1067,22 +1067,11 @@ __global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUte
   }
 }
 
-// Launch with programmatic stream serialization (PDL): the kernel may become resident while the previous kernel of the
-// stream drains; it orders itself with griddepcontrol.wait.  enabled with FDT_PDL=1 (off by default: with two streams the gaps are already filled and early residency costs more than it saves).
 template <typename Kern, typename... Args>
 void launch_pdl(Kern kern, int grid, int block, size_t smem, cudaStream_t s, Args... args) {
-  static const bool pdl = [] { const char* e = std::getenv("FDT_PDL"); return e && e[0] == '1'; }();   // measured slower with two streams: off by default
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3((unsigned)block);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, kern, args...);
+  // (programmatic dependent launch was measured slower with two streams - the other stream already fills the gaps - so the
+  //  kernels are launched plainly; their griddepcontrol instructions are no-ops then)
+  kern<<<grid, block, smem, s>>>(args...);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1170,7 +1159,7 @@ void launch_ws_k(const CUtensorMap& tm, const CUtensorMap& tmo, const DwPwTcP& p
 }
 
 template <int ND>
-void launch_ws_nd(const CUtensorMap& tm, const CUtensorMap& tmo, const DwPwTcP& p, int B, int ntiles, cudaStream_t s) {
+bool launch_ws_nd(const CUtensorMap& tm, const CUtensorMap& tmo, const DwPwTcP& p, int B, int ntiles, cudaStream_t s) {
   const int S = p.has_dw ? p.s : 0;
   switch (S * 16 + (S ? p.RS : 1)) {
     case 1: launch_ws_k<ND, 0, 1>(tm, tmo, p, B, ntiles, s); break;
@@ -1180,8 +1169,9 @@ void launch_ws_nd(const CUtensorMap& tm, const CUtensorMap& tmo, const DwPwTcP& 
     case 32 + 1: launch_ws_k<ND, 2, 1>(tm, tmo, p, B, ntiles, s); break;
     case 32 + 2: launch_ws_k<ND, 2, 2>(tm, tmo, p, B, ntiles, s); break;
     case 32 + 4: launch_ws_k<ND, 2, 4>(tm, tmo, p, B, ntiles, s); break;
-    default: break;
+    default: return false;      // no instantiation for this (stride, rows per item): the caller marks the engine failed
   }
+  return true;
 }
 
 // Tensor map of the letterboxed u8x4 image: u32 [cap][H][W], box {40, PH, 1} (x start 16-byte aligned)
@@ -1200,9 +1190,7 @@ bool stem_tensor_map(const StemWsP& p, int cap, int PH, CUtensorMap* out) {
   cuuint32_t box[3] = {40u, (cuuint32_t)PH, 1u};
   cuuint32_t estr[3] = {1, 1, 1};
   CUtensorMap tm;
-  static const int ty = [] { const char* e = std::getenv("FDT_STEM_TMTYPE"); return e ? std::atoi(e) : 0; }();
-  const CUtensorMapDataType dt = ty == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (ty == 2 ? CU_TENSOR_MAP_DATA_TYPE_INT32 : CU_TENSOR_MAP_DATA_TYPE_UINT32);
-  CUresult r = enc(&tm, dt, 3, const_cast<uint8_t*>(p.in8), gdim, gstr, box, estr,
+  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(p.in8), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return false;
@@ -1240,8 +1228,6 @@ void launch_stem_ws_kw(const CUtensorMap& tm, const StemWsP& p, int B, cudaStrea
     }
     per_sm = it->second;
   }
-  static const int force_per_sm = [] { const char* e = std::getenv("FDT_STEM_PERSM"); return e ? std::atoi(e) : 0; }();
-  if (force_per_sm > 0) per_sm = force_per_sm;
   const int ntiles = ((p.OW + 15) / 16) * ((p.OH + 7) / 8) * B;
   int grid = std::min(ntiles, 148 * per_sm);
   if (grid < 1) grid = 1;
@@ -1273,8 +1259,7 @@ bool launch_block_ws(const DwPwTcP& p0, int B, int cap, cudaStream_t s) {
     cudaMemsetAsync(d_trace, 0, 7 * 64 * 3 * sizeof(long long), s);
     p.trace = d_trace;
   }
-  if (p.nd == 12) launch_ws_nd<12>(tm, tmo, p, B, ntiles, s);
-  else launch_ws_nd<8>(tm, tmo, p, B, ntiles, s);
+  if (!(p.nd == 12 ? launch_ws_nd<12>(tm, tmo, p, B, ntiles, s) : launch_ws_nd<8>(tm, tmo, p, B, ntiles, s))) return false;
   if (trace) {
     static long long h[7 * 64 * 3];
     cudaStreamSynchronize(s);

@@ -314,8 +314,7 @@ struct Builder {
     // Two heads of one scale (classificator + regressor read the same tensor and write dense graph outputs): one launch.
     // The head whose channel count is a multiple of 4 comes first so that its columns keep their float4 stores; the kernel
     // writes columns [0, c1) to its output and [c1, c1 + c2) to the other head's.
-    static const int want_dual = [] { const char* e = std::getenv("FDT_WS_DUAL"); return e ? std::atoi(e) : 1; }();
-    if (use_tc && want_dual && !st.has_dw && res < 0 && st.act == kActNone && is_view(cur)) {
+    if (use_tc && !st.has_dw && res < 0 && st.act == kActNone && is_view(cur)) {
       int sib = -1;
       for (size_t j = 0; j < m.ops.size() && sib < 0; ++j) {
         const TfOp& o2 = m.ops[j];
@@ -362,8 +361,12 @@ struct Builder {
       }
     }
     const int w_parts = tf32_exact(w) ? 1 : 2;
-    bool tc = use_tc && plan_tc(&F->st, Cin, OH, OW, w_parts);
-    if (tc) plan_ws(&F->st, OH, OW);
+    bool tc = false;
+    if (use_tc) {
+      PStep t = F->st;                       // shapes the warp-specialised kernel cannot take stay on the CUDA-core kernel
+      tc = plan_tc(&t, Cin, OH, OW, w_parts) && plan_ws(&t, OH, OW);
+      if (tc) F->st = t;
+    }
     if (F->st.c2 > 0 && F->st.kind != kStepBlockWs) return fail("internal: merged heads need the warp-specialised kernel");
     const PStep& fs = F->st;
     if (tc) {
@@ -408,8 +411,11 @@ struct Builder {
   // (stride 1) or 8 x 16 (stride 2), residual = the block's own input.  The k_block_ws record stays in the blob (the tail
   // fusion and FDT_TS=0 use it).
   void plan_ts(PStep* st, const TfTensor& in, int OH, int OW, bool prelu) {
-    static const int want = [] { const char* e = std::getenv("FDT_TS"); return e ? std::atoi(e) : 0; }();
+    static const int want = [] { const char* e = std::getenv("FDT_TS"); return e ? std::atoi(e) : 1; }();      // FDT_TS=0: A/B against k_block_ws
     if (!want || !st->has_dw || st->c2 > 0 || st->w_parts != 1 || prelu) return;
+    // up to 24 channels k_block_ws keeps a thread's depthwise taps in registers for the whole kernel (one work item per
+    // thread) and measures faster (0.136 vs 0.147 ms per 512 frames on the 64x64x24 block); from 28 channels on this kernel wins
+    if (in.dim(3) < 28 && want < 2) return;
     if (st->act != kActRelu && st->act != kActNone) return;
     const int Cin = in.dim(3), K16 = ru(Cin, 16), Npad = ru(st->Cout, 16);
     if (K16 > 64 || Npad > 64) return;
@@ -488,12 +494,8 @@ struct Builder {
     s.KS = s.K8 + (((s.K8 / 4) % 2 == 0) ? 4 : 0);
     s.tmem_cols = 32;
     while (s.tmem_cols < s.Npad) s.tmem_cols *= 2;
-    // First choice: the largest tile within the preferred footprint (FDT_TC_SMEMCAP KB, tuning knob);
-    // fallback: the largest tile that fits at all.
-    static const size_t pref_cap = [] { const char* e = std::getenv("FDT_TC_SMEMCAP"); return (size_t)(e ? std::atoi(e) : 220) * 1024; }();
-    for (int pass = 0; pass < 2; ++pass)
     for (int Pn = 128; Pn >= 32; Pn /= 2) {
-      const size_t cap = pass == 0 ? pref_cap : (size_t)220 * 1024;
+      const size_t cap = (size_t)220 * 1024;
       s.TM = 1; s.NPG = Pn;                       // slot budget of this candidate
       int bestTH = 0, bestTW = 0, bestG = 1;
       double best = -1;
@@ -533,13 +535,10 @@ struct Builder {
       // two CTAs per SM, i.e. <= 113 KB each; a CTA that is alone on its SM anyway may use up to 220 KB
       size_t smem1 = (head + a + in) * 4 + (n_chunks + n_items) * 8 + 128;
       size_t smem2 = smem1 + in * 4;
-      static const int want_nbuf = [] { const char* e = std::getenv("FDT_TC_NBUF"); return e ? std::atoi(e) : 0; }();
-      bool dbl = want_nbuf == 2 ? smem2 <= 220 * 1024
-               : want_nbuf == 1 ? false
-               : (smem2 <= 113 * 1024 || (smem1 > 113 * 1024 && smem2 <= 220 * 1024));
+      bool dbl = smem2 <= 113 * 1024 || (smem1 > 113 * 1024 && smem2 <= 220 * 1024);
       s.nbuf = dbl ? 2 : 1;
       s.smem = dbl ? smem2 : smem1;
-      if (s.smem <= cap) { s.kind = kStepDwPwTc; *st = s; return true; }
+      if (s.smem <= cap) { *st = s; return true; }      // (plan_ws sets the kind)
     }
     return false;
   }
@@ -548,11 +547,7 @@ struct Builder {
   // into a ring of `ns` stages, the A operand (hi + lo, always 128 rows) is double-buffered when it fits.
   // Shared-memory formula mirrors the kernel's carve-up.
   bool plan_ws(PStep* st, int OH, int OW) {
-    static const int want = [] { const char* e = std::getenv("FDT_WS"); return e ? std::atoi(e) : 1; }();
-    static const int want_nd = [] { const char* e = std::getenv("FDT_WS_ND"); return e ? std::atoi(e) : 0; }();
-    static const int max_ns = [] { const char* e = std::getenv("FDT_WS_NS"); return e ? std::atoi(e) : 6; }();
-    static const int max_na = [] { const char* e = std::getenv("FDT_WS_NA"); return e ? std::atoi(e) : 4; }();
-    if (!want) return false;
+    constexpr int max_ns = 6, max_na = 4;
     PStep s = *st;
     // staged pixel stride: >= K8 (and >= CoutS when the residual is read from the stage, so the epilogue needs no
     // channel guard: the TMA zero-fills everything past CinS), an odd number of 16-byte quads (conflict-free LDS.128)
@@ -597,7 +592,6 @@ struct Builder {
       if (s.has_dw) {
         double best_cost = 1e30;
         for (int nd : {12, 8}) {
-          if (want_nd && nd != want_nd) continue;
           for (int rs : {1, 2, 4}) {
             if (s.TH % rs || rs > (nd == 12 ? 2 : 4)) continue;
             int items = s.G * (s.K8 / 4) * (s.TH / rs) * s.TW;
@@ -607,8 +601,6 @@ struct Builder {
             if (cost < best_cost - 1e-9) { best_cost = cost; s.RS = rs; s.nd = nd; }
           }
         }
-      } else if (want_nd == 12) {
-        s.nd = 12;
       }
       size_t n_items = s.has_dw ? (size_t)s.G * (s.K8 / 4) * (s.TH / s.RS) * s.TW : 0;
       size_t head = ((size_t)s.w_parts * s.Npad * s.K8 + 2 * (size_t)s.Npad + (s.has_dw ? 10 * (size_t)s.K8 : 0)) * 4 + (n_items + 1) / 2 * 8 + 32 * 8 + 128;
@@ -752,8 +744,7 @@ struct Builder {
     if (!m.const_f32(conv.in[1], &w)) return fail("conv weights are not constant");
     if (conv.in.size() > 2 && conv.in[2] >= 0) { if (!m.const_f32(conv.in[2], &b)) return fail("conv bias is not constant"); }
     b.resize(st.Cout, 0.f);
-    static const int want_stem_ws = [] { const char* e = std::getenv("FDT_STEM_WS"); return e ? std::atoi(e) : 1; }();
-    if (st.kind == kStepStem && use_tc && want_stem_ws && ru(st.Cout, 16) <= 64) {
+    if (st.kind == kStepStem && use_tc && ru(st.Cout, 16) <= 64) {
       // k_stem_ws: im2col GEMM with exact fp16 operands.  A holds (u8 - 127.5) (half-integers, exact in fp16), laid out
       // per tap row ky as SEGP pixels x {B,G,R,X} halves; W is scaled by a power of two and split into w_parts fp16
       // terms (1 when the weights are fp16-origin, 3 for fp32 weights); out = D * out_scale + bias.
@@ -799,26 +790,6 @@ struct Builder {
       st.ns = 6; st.na = 2;   // must match FDT_STEM_NA in kernels_ws.cu
       st.smem = (size_t)parts * st.Npad * st.K8 * 2 + 2 * (size_t)st.Npad * 4 + 32 * 8 + 128     // W, bias, alpha, barriers
                 + (size_t)st.na * 128 * st.K8 * 2 + 2 * (size_t)PH * 36 * 8 + (size_t)st.ns * ((PH * 160 + 127) / 128 * 128) + 256;
-      st.w = push(wb, wb.size());
-      st.bias = push(b, (size_t)st.Npad + 8);
-      if (alpha_tf >= 0 && !pack_alpha(alpha_tf, (size_t)st.Npad + 8, &st.alpha)) return false;
-    } else if (st.kind == kStepStem && use_tc && ru(st.Cout, 16) <= 128) {
-      st.w_parts = tf32_exact(w) ? 1 : 2;
-      // tensor-core stem: B operand [Npad x K8] in the UMMA K-major core-matrix layout
-      st.kind = kStepStemTc;
-      st.K8 = ru(st.K, 8);
-      st.Npad = ru(st.Cout, 16);
-      st.tmem_cols = 32;
-      while (st.tmem_cols < st.Npad) st.tmem_cols *= 2;
-      const size_t SBO = (size_t)(st.K8 / 4) * 128, LBO = 128;
-      std::vector<float> wb((size_t)st.w_parts * st.Npad * st.K8, 0.f);
-      for (int n = 0; n < st.Cout; ++n)
-        for (int k = 0; k < st.K; ++k) {
-          size_t o = ((size_t)(n >> 3) * SBO + (size_t)(k >> 2) * LBO + (size_t)(n & 7) * 16 + (size_t)(k & 3) * 4) / 4;
-          split_w(w[(size_t)n * st.K + k], st.w_parts, &wb[o], &wb[o + (st.w_parts > 1 ? (size_t)st.Npad * st.K8 : 0)]);
-        }
-      int PH = 14 + st.kw, PW = 30 + st.kw;
-      st.smem = ((size_t)st.w_parts * st.Npad * st.K8 + 2 * (size_t)st.Npad + 2 * 128 * (size_t)st.K8 + (size_t)PH * PW * 3 + 2 * (size_t)PH * PW) * 4 + 128;
       st.w = push(wb, wb.size());
       st.bias = push(b, (size_t)st.Npad + 8);
       if (alpha_tf >= 0 && !pack_alpha(alpha_tf, (size_t)st.Npad + 8, &st.alpha)) return false;
@@ -939,7 +910,8 @@ struct Builder {
         if (s.c2 > 0) { L.o2 = (int)t.tail_outs.size(); t.tail_outs.push_back(s.out2); }
         if (t.tail_outs.size() > 4) return;
       }
-      if (L.OH * L.OW > 256) return;
+      // the kernel's M-tile maps: a 16-wide 256-pixel map (two tiles: even / odd rows) or at most 128 pixels (one tile)
+      if (!((L.OH * L.OW == 256 && L.OW == 16) || L.OH * L.OW <= 128)) return;
       // the step's tensor-core operands back to plain arrays: W [Cout][Cin] (exact values), taps [9][K8], biases
       const size_t SBO8 = (size_t)(s.K8 / 4) * 128;
       const int K16 = L.K16;
@@ -1157,7 +1129,7 @@ struct Builder {
       int t = pt(o);
       P.outputs.push_back(t);
     }
-    static const int want_tail = [] { const char* e = std::getenv("FDT_TAIL"); return e ? std::atoi(e) : 0; }();
+    static const int want_tail = [] { const char* e = std::getenv("FDT_TAIL"); return e ? std::atoi(e) : 1; }();   // FDT_TAIL=0: A/B, one launch per layer
     if (fuse == 1 && use_tc && want_tail) fuse_tail();
     // arena allocation
     struct Block { long long off, size; int free_after; };
@@ -1205,7 +1177,7 @@ bool Plan::build(const TfModel& m, int fuse, std::string* err, bool use_tc) {
 }
 
 std::string Plan::describe() const {
-  static const char* kn[] = {"normalize", "naive_conv", "gemm_conv", "dwpw", "add", "act", "padc", "maxpool", "resize", "stem", "dwpw_tc", "stem_tc", "block_ws", "stem_ws", "tail_ws", "fc_tc", "block_ts"};
+  static const char* kn[] = {"normalize", "naive_conv", "gemm_conv", "dwpw", "add", "act", "padc", "maxpool", "resize", "stem", "block_ws", "stem_ws", "tail_ws", "fc_tc", "block_ts"};
   std::string s;
   char buf[512];
   double macs = 0;

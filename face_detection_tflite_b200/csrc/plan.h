@@ -26,7 +26,7 @@ struct PTensor {
 };
 
 enum StepKind { kStepNormalize, kStepNaiveConv, kStepGemmConv, kStepDwPw, kStepAdd, kStepAct, kStepPadC,
-                kStepMaxPool, kStepResize, kStepStem, kStepDwPwTc, kStepStemTc, kStepBlockWs, kStepStemWs, kStepTailWs, kStepFcTc, kStepBlockTs };
+                kStepMaxPool, kStepResize, kStepStem, kStepBlockWs, kStepStemWs, kStepTailWs, kStepFcTc, kStepBlockTs };
 
 struct PStep {
   StepKind kind = kStepAct;

@@ -249,7 +249,8 @@ FDT_EXPORT int32_t fdt_profile_chunk(fdt_handle* h, const uint8_t* d_frames, int
 FDT_EXPORT int32_t fdt_get_step_info(fdt_handle* h, int32_t launch, char* kernel, char* tensor, int32_t str_cap,
                                      double* macs_per_image, double* bytes_per_image);
 /* Same for the mesh (which = 1) and iris (which = 2) nets: `repeats` passes over the first n crops left in the
- * stage buffers by the last standard / full call; out_ms[i] = mean duration of plan step i;
+ * stage buffers by the last standard / full call (n <= 0 or too large: all of them; fdt_debug_get_mesh_stage /
+ * fdt_debug_get_iris_stage report how many there are); out_ms[i] = mean duration of plan step i;
  * fdt_get_net_step_info describes step i of that plan. */
 FDT_EXPORT int32_t fdt_profile_net(fdt_handle* h, int32_t which, int32_t n, int32_t repeats, float* out_ms,
                                    int32_t capacity, int32_t* out_steps);

@@ -460,7 +460,7 @@ def test_c_abi_status_codes(fdt, lib):
     iw, ih, na, mf, mb = (C.c_int32() for _ in range(5))
     assert lib.fdt_get_info(h, C.byref(iw), C.byref(ih), C.byref(na), C.byref(mf), C.byref(mb)) == 0
     assert (iw.value, ih.value, na.value, mf.value) == (128, 128, 896, 100)
-    assert lib.fdt_last_h2d_bytes(h) == 48 and lib.fdt_last_launch_count(h) == 21   # letterbox + stem + 16 blocks + 2 head pairs + decode
+    assert lib.fdt_last_h2d_bytes(h) == 48 and lib.fdt_last_launch_count(h) == 10   # letterbox + stem + 6 blocks + image-resident tail (10 blocks, 2 head pairs) + decode
 
 
 # ---- alternative kernel paths (environment switches are read once per process -> subprocesses) ----------
@@ -478,7 +478,8 @@ from oracle.pipeline import OraclePipeline
 from pathlib import Path
 root = Path(%r)
 img = cv2.imread(str(root / "assets/samples/group-shot-bounding-box-ex1.jpeg"))
-for model, f in (("shortRange", "face_detection_short_range.tflite"), ("full", "face_detection_full_range.tflite")):
+for model, f in (("shortRange", "face_detection_short_range.tflite"), ("backCamera", "face_detection_back.tflite"),
+                 ("full", "face_detection_full_range.tflite")):
     det_bytes = (root / "assets/models" / f).read_bytes()
     d = fdt.FaceDetector.create(fdt.FaceDetectionModel[model], withMesh=False)
     frames = np.stack([img, img[:, ::-1].copy(), img[::-1].copy()])
@@ -496,13 +497,11 @@ print("variant ok")
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("env", [{"FDT_WS_NO": "2"},          # TMA-store epilogue (output tile in shared memory + store warp)
-                                 {"FDT_WS": "0"},             # k_dwpw_tc (bulk-synchronous tcgen05 kernel) instead of k_block_ws
-                                 {"FDT_STEM_WS": "0"},        # k_stem_tc (TF32 hi/lo im2col) instead of the fp16 stem
-                                 {"FDT_WS_ND": "8"},          # 8 depthwise warps everywhere
-                                 {"FDT_WS_NA": "1", "FDT_WS_NS": "2"},   # minimal rings, single MMA issuer
-                                 {"FDT_PDL": "1"},            # programmatic dependent launch
-                                 {"FDT_WS_DUAL": "0"}])       # one launch per head instead of one per head pair
+@pytest.mark.parametrize("env", [{"FDT_WS_NO": "2"},                 # k_block_ws with the TMA-store epilogue (output tile in shared memory + store warp)
+                                 {"FDT_TS": "0"},                    # k_block_ws (TF32 hi/lo, operand in shared memory) for every BlazeBlock
+                                 {"FDT_TS": "2"},                    # k_block_ts (fp16 hi/lo, operand in TMEM) also for the 24-channel blocks
+                                 {"FDT_TAIL": "0"},                  # one launch per 16x16 / 8x8 block and head pair instead of k_tail_ws
+                                 {"FDT_TAIL": "0", "FDT_TS": "0"}])  # the round-1 plan: k_block_ws everywhere
 def test_kernel_variants_match_the_oracle(env):
     """Every tuning switch selects code that must stay parity-green: raw heads of two models vs the fp64 oracle."""
     import subprocess

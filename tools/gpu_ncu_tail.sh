@@ -1,7 +1,6 @@
 #!/bin/bash
 # ncu --set full of one chunk (10 launches with the tail kernel) + SASS-level stall samples of k_tail_ws.  $1 = tag
 TAG=${1:-x}
-export FDT_TAIL=1
 mkdir -p gpurun_out
 python tools/prof_target.py > gpurun_out/prof_plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -s 20 -c 10 -o /tmp/prof_$TAG -f python tools/prof_target.py > gpurun_out/ncu2.log 2>&1
