@@ -269,6 +269,8 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
       case kStepResize: {
         ResizeP p;
         p.in = view(ctx, st.in); p.out = out; p.align_corners = st.align; p.half_pixel = st.half;
+        p.has_add = st.in2 >= 0 ? 1 : 0; p.act = st.act;
+        p.add = st.in2 >= 0 ? view(ctx, st.in2) : p.in;
         launch_resize_bilinear(p, B, s);
         break;
       }

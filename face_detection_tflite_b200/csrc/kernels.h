@@ -50,7 +50,7 @@ struct EltP {
   int act;
 };
 struct PoolP { TV in, out; int fh, fw, sh, sw, pt, pl; };
-struct ResizeP { TV in, out; int align_corners, half_pixel; };
+struct ResizeP { TV in, out; int align_corners, half_pixel; TV add; int has_add, act; };   // has_add: out = resize(in) + add [ReLU]
 
 void launch_naive_conv(const NaiveConvP& p, int B, cudaStream_t s);
 void launch_add(const EltP& p, int B, cudaStream_t s);

@@ -59,9 +59,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
 }
+// Plain (non-volatile) shared-memory load: the compiler may batch these ahead of the FMAs that use them (the depthwise
+// loop is LDS-latency bound with three warps per scheduler); mbarrier waits / named barriers carry "memory" clobbers, so
+// no load moves across a hand-off.
 __device__ __forceinline__ float4 lds4(uint32_t addr) {
   float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
 }
 __device__ __forceinline__ void sts4(uint32_t addr, const float4& v) {

@@ -1112,10 +1112,28 @@ struct Builder {
           s.in = pt(op.in[0]); s.out = pt(op.out[0]);
           break;
         }
-        case kOpResizeBilinear:
+        case kOpResizeBilinear: {
           s.kind = kStepResize; s.align = op.align_corners; s.half = op.half_pixel;
           s.in = pt(op.in[0]); s.out = pt(op.out[0]);
+          // RESIZE_BILINEAR -> ADD(skip, resized) [ReLU] (the FPN up-path): one kernel, the upsampled tensor never reaches HBM
+          const int c = fuse >= 1 && !is_view(op.out[0]) ? sole_consumer(op.out[0]) : -1;
+          if (c >= 0 && !done[c] && m.ops[c].code == kOpAdd && m.ops[c].in.size() == 2 && (m.ops[c].act == 0 || m.ops[c].act == 1)) {
+            const TfOp& add = m.ops[c];
+            const int other = add.in[0] == op.out[0] ? add.in[1] : add.in[0];
+            auto it = P.tf2pt.find(other);
+            const bool vec = P.tensors[s.out].Cs % 4 == 0 && it != P.tf2pt.end() && P.tensors[it->second].materialized &&
+                             P.tensors[it->second].Cs == P.tensors[s.out].Cs && other != op.out[0] && numel(other) == numel(op.out[0]) &&
+                             !is_view(other) && !is_view(add.out[0]);
+            if (vec) {
+              s.in2 = it->second;
+              s.out = pt(add.out[0]);
+              s.act = add.act == 1 ? kActRelu : kActNone;
+              s.name = m.tensors[add.out[0]].name;
+              done[c] = 1;
+            }
+          }
           break;
+        }
         default: {
           char buf[96];
           snprintf(buf, sizeof buf, "unsupported TFLite op %d in graph", op.code);
