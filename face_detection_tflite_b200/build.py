@@ -28,6 +28,7 @@ SOURCES = {
     "kernels_ws.cu": [],
     "kernels_tail.cu": [],
     "kernels_ts.cu": [],
+    "kernels_fc.cu": [],
     "kernels_pre.cu": [],
     # f64 geometry must be evaluated operation by operation (no fused multiply-add contraction)
     "kernels_post.cu": ["-fmad=false"],

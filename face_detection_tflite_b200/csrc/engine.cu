@@ -222,8 +222,13 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         TV iv = view(ctx, st.in);
         p.in = iv.p; p.in_istride = iv.istride; p.H = iv.H; p.W = iv.W; p.CinS = iv.Cs;
         p.blob = blob; p.layers = d_tail_[&st - plan_.steps.data()]; p.nlayers = (int)st.tail.size();
-        p.KSA = st.tail_ksa; p.KSB = st.tail_ksb; p.PA = st.tail_pa; p.PB = st.tail_pb;
-        p.last_a_layer = st.tail_last_a; p.wbuf_bytes = st.tail_wbuf; p.smem_bytes = st.smem;
+        p.nbuf = st.tail_nbuf;
+        for (int k = 0; k < kTailMaxBufs; ++k) { p.buf_off[k] = st.tail_buf_off[k]; p.buf_ks[k] = st.tail_buf_ks[k]; }
+        p.act_floats = st.tail_act_floats; p.in_bytes = st.tail_in_bytes;
+        p.generic = 0;
+        for (const TailLayerD& L : st.tail)
+          if (L.kind >= 2 || L.act == 2 || L.w_parts != 1 || L.wscale != 1.f || L.rbuf != L.src || (L.kind != 1 && L.o1 >= 0)) p.generic = 1;
+        p.last_a_layer = st.tail_last_a; p.wbuf_bytes = st.tail_wbuf; p.wdepth = st.tail_wdepth; p.tbuf_bytes = st.tail_tbuf; p.smem_bytes = st.smem;
         for (int k = 0; k < 4; ++k) { p.outs[k] = nullptr; p.out_istride[k] = 0; p.out_pix[k] = 0; }
         for (size_t k = 0; k < st.tail_outs.size(); ++k) {
           TV ov = view(ctx, st.tail_outs[k]);
@@ -232,8 +237,16 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         if (!launch_tail_ws(p, B, ctx.cap, s)) { failed_ = true; fprintf(stderr, "fdt: k_tail_ws could not be launched for step '%s'\n", st.name.c_str()); }
         break;
       }
-      case kStepFcTc:
+      case kStepFcTc: {
+        FcP p;
+        TV iv = view(ctx, st.in);
+        p.in = iv.p; p.in_istride = iv.istride;
+        p.out = out.p; p.out_istride = out.istride;
+        p.w = blob + st.w; p.bias = blob + st.bias;
+        p.K = st.K; p.K16 = st.K8; p.N = st.Cout; p.w_parts = st.w_parts; p.tile_bytes = st.ts_rec_bytes; p.wscale = (float)st.out_scale;
+        if (!launch_fc_tc(p, B, s)) { failed_ = true; fprintf(stderr, "fdt: k_fc_tc could not be launched for step '%s'\n", st.name.c_str()); }
         break;
+      }
       case kStepBlockTs: {
         BlockTsP p;
         TV iv = view(ctx, st.in);

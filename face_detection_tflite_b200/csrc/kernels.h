@@ -184,18 +184,35 @@ bool launch_block_ts(const BlockTsP& p, int B, int cap, cudaStream_t s);
 
 // ---- image-resident tail (kernels_tail.cu): every 16x16 / 8x8 BlazeBlock and both head pairs in one launch ----
 struct TailP {
-  const float* in; long long in_istride; int H, W, CinS;   // first layer's input activation (HBM, NHWC f32)
+  const float* in; long long in_istride; int H, W, CinS;   // first layer's input activation (HBM, NHWC f32) -> buffer 0 by TMA
   const float* blob;            // the engine's weight blob
   const TailLayerD* layers;     // device copy of the layer program
   int nlayers;
-  int KSA, KSB;                 // pixel strides (floats) of the two shared-memory activation buffers: odd numbers of 16-byte quads
-  int PA, PB;                   // pixels they hold
-  int last_a_layer;             // last layer that reads buffer A (the next image's input is fetched after it)
-  int wbuf_bytes;               // one weight buffer (two are kept: the next layer's record streams in during the current layer)
-  float* outs[4]; long long out_istride[4]; int out_pix[4];   // graph outputs the heads write: image 0, floats per image / per pixel
+  int nbuf;                     // shared-memory activation buffers
+  int buf_off[kTailMaxBufs];    // float offset of each inside the activation area
+  int buf_ks[kTailMaxBufs];     // pixel stride (floats): an odd number of 16-byte quads
+  int act_floats;               // size of the activation area
+  int in_bytes;                 // bytes the TMA of one image delivers into buffer 0
+  int last_a_layer;             // last layer that touches buffer 0 (the next image's input is fetched after it)
+  int wbuf_bytes, wdepth;       // pointwise-weight ring: wdepth (1 or 2) buffers of wbuf_bytes
+  int tbuf_bytes;               // depthwise-record ring (always two deep)
+  int generic;                  // 1: the program needs the GEN = true kernel (see kernels_tail.cu)
+  float* outs[4]; long long out_istride[4]; int out_pix[4];   // HBM tensors the layers write: image 0, floats per image / per pixel
   size_t smem_bytes;
 };
+size_t tail_smem_bytes(int act_floats, int wbuf_bytes, int wdepth, int tbuf_bytes);
 bool launch_tail_ws(const TailP& p, int B, int cap, cudaStream_t s);
+
+// ---- k_fc_tc (kernels_fc.cu): whole-map convolution = one dense contraction per image, tcgen05 GEMM over the chunk ----
+struct FcP {
+  const float* in; long long in_istride;     // [B][K] (the NHWC map, Cs == C, read as one row)
+  float* out; long long out_istride;         // [B][N]
+  const float* w;                            // per 128-channel tile: [w_parts][128][K16] fp16, UMMA K-major core matrices
+  const float* bias;                         // [N]
+  int K, K16, N, w_parts, tile_bytes;
+  float wscale;
+};
+bool launch_fc_tc(const FcP& p, int B, cudaStream_t s);
 
 // ---- detector post-processing: one block per image ----
 struct DecodeP {

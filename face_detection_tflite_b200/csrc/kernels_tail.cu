@@ -105,34 +105,42 @@ __device__ __forceinline__ void mma_ts_f16(uint32_t tmem_d, uint32_t tmem_a, uin
 }
 
 // Shared-memory carve-up (must match tail_smem_bytes below):
-//   [layers 16 x 128 B] [bias 16 x 128 floats] [barriers 16 x 8 B] | 128-byte aligned: [buffer A PA x KSA] [buffer B PB x KSB]
-//   [zero slot 128 floats] | 128-byte aligned: [weight ring 2 x wbuf_bytes]
-__global__ void __launch_bounds__(kTThreads, 1) k_tail_ws(const __grid_constant__ CUtensorMap tmap, TailP p, int B) {
+//   [layers 16 x 128 B] [bias 16 x 128 floats] [slopes 16 x 128 floats] [barriers 16 x 8 B] [scratch 16 floats]
+//   | 128-byte aligned: [activation buffers: act_floats] [zero slot 128 floats]
+//   | 128-byte aligned: [depthwise-record ring 2 x tbuf_bytes] [pointwise-weight ring wdepth x wbuf_bytes]
+// GEN = false: the detector tails (blocks with ReLU + head pairs, exact fp16 weights, residual = the block's own input);
+// GEN = true adds what the face-landmark chain needs (PReLU, W = hi + lo, weight scale, pointwise-only and dot layers, residual
+// from another buffer, results mirrored to HBM).
+template <bool GEN>
+__global__ void __launch_bounds__(kTThreads, 1) k_tail_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TailP p, int B) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   TailLayerD* sL = reinterpret_cast<TailLayerD*>(smem_raw);
   float* sBias = reinterpret_cast<float*>(smem_raw + kTailMaxLayers * sizeof(TailLayerD));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + kTailMaxLayers * 128);
-  float* bufA = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(bars + 16) + 127) & ~(uintptr_t)127);
-  float* bufB = bufA + (size_t)p.PA * p.KSA;
-  float* zslot = bufB + (size_t)p.PB * p.KSB;
-  unsigned char* wring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(zslot + 128) + 127) & ~(uintptr_t)127);
+  float* sAlpha = sBias + kTailMaxLayers * 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sAlpha + kTailMaxLayers * 128);
+  float* scratch = reinterpret_cast<float*>(bars + 16);
+  float* act0 = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(scratch + 16) + 127) & ~(uintptr_t)127);
+  float* zslot = act0 + p.act_floats;
+  unsigned char* tring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(zslot + 128) + 127) & ~(uintptr_t)127);
+  unsigned char* wring = tring + 2 * (size_t)p.tbuf_bytes;
   const uint32_t bar0 = smem_u32(bars);
-  const uint32_t in_full = bar0, a_free = bar0 + 8u, w_full = bar0 + 16u, a_full = bar0 + 32u, d_full = bar0 + 48u;
+  const uint32_t in_full = bar0, a_free = bar0 + 8u, w_full = bar0 + 16u, a_full = bar0 + 32u, d_full = bar0 + 48u, t_full = bar0 + 56u;
   const int nl = p.nlayers;
-  const uint32_t in_bytes = (uint32_t)p.PA * (uint32_t)p.KSA * 4u;
   const int my_images = blockIdx.x < B ? (B - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   // ---- prologue ---------------------------------------------------------------------------------------------------
   for (int i = tid; i < nl * (int)(sizeof(TailLayerD) / 16); i += kTThreads)
     reinterpret_cast<uint4*>(sL)[i] = reinterpret_cast<const uint4*>(p.layers)[i];
-  for (int i = tid; i < p.PB * p.KSB + 128; i += kTThreads) bufB[i] = 0.f;           // buffer B's channel pad and the zero slot stay zero
+  // every buffer but the first (the TMA fills that one, zero channel pad included) starts as zeros: channel pads stay zero
+  for (int i = (p.in_bytes >> 2) + tid; i < p.act_floats + 128; i += kTThreads) act0[i] = 0.f;
   if (warp == kTC) {
     if (lane == 0) {
       mbar_init(in_full, 1);
       mbar_init(a_free, kTC);
-      for (int i = 0; i < 2; ++i) { mbar_init(w_full + 8u * i, 1); mbar_init(a_full + 8u * i, kTC); mbar_init(d_full + 8u * i, 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(w_full + 8u * i, 1); mbar_init(a_full + 8u * i, kTC); mbar_init(t_full + 8u * i, 1); }
+      mbar_init(d_full, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     }
@@ -142,50 +150,82 @@ __global__ void __launch_bounds__(kTThreads, 1) k_tail_ws(const __grid_constant_
   }
   __syncthreads();
   for (int l = 0; l < nl; ++l)
-    for (int i = tid; i < sL[l].Npad; i += kTThreads) sBias[l * 128 + i] = p.blob[(size_t)sL[l].bias_off + i];
+    for (int i = tid; i < sL[l].Npad; i += kTThreads) {
+      sBias[l * 128 + i] = p.blob[(size_t)sL[l].bias_off + i];
+      if (GEN && sL[l].act == 2) sAlpha[l * 128 + i] = p.blob[(size_t)sL[l].alpha_off + i];
+    }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
-  const uint32_t bufA_a = smem_u32(bufA), bufB_a = smem_u32(bufB), zero_a = smem_u32(zslot), wring_a = smem_u32(wring);
-  const uint32_t ksa_b = (uint32_t)p.KSA * 4u, ksb_b = (uint32_t)p.KSB * 4u;
+  const uint32_t act_a = smem_u32(act0), zero_a = smem_u32(zslot), wring_a = smem_u32(wring), tring_a = smem_u32(tring);
 
   if (warp < kTC) {
     // =============================== compute warps ==============================================================
     const int lq = warp & 3, g = warp >> 2;                // TMEM lane quarter (hardware: warp % 4), channel-quad / column group
     const int r = lq * 32 + lane;                           // row of the 128-pixel M-tile = TMEM lane
     const uint32_t tm_lane = tmem_base + ((uint32_t)(lq * 32) << 16);
-    uint32_t ph_d = 0u;
+    uint32_t ph_d = 0u, ph_t0 = 0u, ph_t1 = 0u;
     int gl = 0, it = 0;
     for (int img = blockIdx.x; img < B; img += gridDim.x, ++it) {
       mbar_wait(in_full, (uint32_t)(it & 1));
       for (int l = 0; l < nl; ++l, ++gl) {
         const TailLayerD L = sL[l];                           // registers: the loops below must not re-read it from shared memory
-        const uint32_t src_a = L.src ? bufB_a : bufA_a, dst_a = L.dst ? bufB_a : bufA_a;
-        const uint32_t kss_b = L.src ? ksb_b : ksa_b, ksd_b = L.dst ? ksb_b : ksa_b;
+        const uint32_t src_a = act_a + 4u * (uint32_t)p.buf_off[L.src], kss_b = 4u * (uint32_t)p.buf_ks[L.src];
+        const uint32_t dst_a = L.dst >= 0 ? act_a + 4u * (uint32_t)p.buf_off[L.dst] : 0u, ksd_b = L.dst >= 0 ? 4u * (uint32_t)p.buf_ks[L.dst] : 0u;
         const int src_q = (int)(kss_b >> 4), dst_q = (int)(ksd_b >> 4);       // quads per pixel record
         const int npix = L.OH * L.OW;
-        // 256-pixel maps are split into the M-tiles "even rows" / "odd rows": a thread then owns the vertically adjacent
-        // pixels (2yy, x) and (2yy + 1, x) and feeds both depthwise outputs from ONE 4 x 3 window (6 instead of 9 LDS.128
-        // per output quad); smaller maps are one M-tile in row-major order
-        const bool paired = npix == 256 && L.OW == 16;
+        const uint32_t tb_a = tring_a + (uint32_t)(gl & 1) * (uint32_t)p.tbuf_bytes;
+        if (L.tap_bytes) {                                    // this layer's depthwise record (kind 3: its filter) has landed
+          if (gl & 1) { mbar_wait(t_full + 8u, ph_t1); ph_t1 ^= 1u; } else { mbar_wait(t_full, ph_t0); ph_t0 ^= 1u; }
+        }
+        if (GEN && L.kind == 3) {
+          // ---- whole-map dot product (a k x k VALID convolution over a k x k map with one filter) ------------------------
+          const int n = npix * L.Cin;
+          float sacc = 0.f;
+          for (int i = tid; i < n; i += kTComputeThreads) {
+            const int px = i / L.Cin, c = i - px * L.Cin;
+            float a, w;
+            asm("ld.shared.f32 %0, [%1];" : "=f"(a) : "r"(src_a + (uint32_t)px * kss_b + 4u * (uint32_t)c) : "memory");
+            asm("ld.shared.f32 %0, [%1];" : "=f"(w) : "r"(tb_a + 4u * (uint32_t)i) : "memory");
+            sacc = fmaf(a, w, sacc);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+          if (lane == 0) { scratch[warp] = sacc; mbar_arrive(a_full); mbar_arrive(a_full + 8u); }    // the filter and the map are read
+          asm volatile("bar.sync 1, %0;" ::"n"(kTComputeThreads) : "memory");
+          if (tid == 0) {
+            float tot = sBias[l * 128];
+            for (int w2 = 0; w2 < kTC; ++w2) tot += scratch[w2];
+            p.outs[L.o1][(size_t)img * p.out_istride[L.o1]] = tot;
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(kTComputeThreads) : "memory");
+          if (l == p.last_a_layer && lane == 0) mbar_arrive(a_free);
+          continue;
+        }
+        // Maps of more than 128 pixels (even height, at most 256 pixels) are split into the M-tiles "even rows" / "odd rows":
+        // a thread then owns the vertically adjacent pixels (2yy, x) and (2yy + 1, x) and feeds both depthwise outputs from
+        // ONE 4 x 3 window (6 instead of 9 LDS.128 per output quad); smaller maps are one M-tile in row-major order
+        const bool paired = npix > 128;
         const int ntiles = paired ? 2 : 1;
+        const int rows = paired ? (npix >> 1) : npix;           // rows of an M-tile that hold pixels
         const int nq = L.K16 >> 2, nq_real = (L.Cin + 3) >> 2, nq_half = (L.K16 >> 5) << 2;   // quads of the first K half (whole 16-wide K steps)
-        const uint32_t wb_a = wring_a + (uint32_t)(gl & 1) * (uint32_t)p.wbuf_bytes;
-        const uint32_t dww_a = wb_a + (uint32_t)(L.Npad * L.K16) * 2u, dwb_a = dww_a + 9u * (uint32_t)L.K16 * 4u;
+        const uint32_t dww_a = tb_a, dwb_a = dww_a + 9u * (uint32_t)L.K16 * 4u;
         const uint32_t k16_b = (uint32_t)L.K16 * 4u;
         const uint32_t acol0 = tm_lane + col_a(0), acol1 = tm_lane + col_a(1);
         // this thread's output pixel(s): (oy, ox) of tile 0; tile 1 is (oy + 1, ox) when paired
-        int oy, ox;
-        if (paired) { oy = 2 * (r >> 4); ox = r & 15; }
-        else { oy = r / L.OW; ox = r - oy * L.OW; }
-        const bool act = paired || r < npix;
+        int oy = r / L.OW;
+        const int ox = r - oy * L.OW;
+        if (paired) oy *= 2;
+        const bool act = r < rows;
+        const bool warp_on = lq * 32 < rows;                  // lane quarters without pixels only keep the hand-offs going
         const int pix0 = oy * L.OW + ox;
-        mbar_wait(w_full + 8u * (uint32_t)(gl & 1), (uint32_t)((gl >> 1) & 1));
-        // ---- operand tiles: depthwise 3x3 (blocks) or the activation itself (heads) -> fp16 hi / lo -> TMEM ------------
+        // ---- operand tiles: depthwise 3x3 (blocks) or the activation itself (pointwise layers) -> fp16 hi / lo -> TMEM ----
         // The K range is produced in two halves with an mbarrier each, so that the MMAs of the first half run while the
         // second half is still being computed.
-        if (L.kind == 0) {
+        bool half_done = false;
+        if (!warp_on) {
+        } else if (L.kind == 0) {
           // window offsets: rows oy*s - pad .. (+2, +3 when paired), cols ox*s - pad .. +2; SAME padding reads the zero slot
           uint32_t off[12];
           const int iy0 = oy * L.stride - L.pad, ix0 = ox * L.stride - L.pad;
@@ -195,7 +235,6 @@ __global__ void __launch_bounds__(kTThreads, 1) k_tail_ws(const __grid_constant_
             const bool ok = act && (unsigned)iy < (unsigned)L.IH && (unsigned)ix < (unsigned)L.IW;
             off[k] = ok ? src_a + (uint32_t)(iy * L.IW + ix) * kss_b : zero_a;
           }
-          bool half_done = false;
           for (int q = g; q < nq; q += 3) {
             if (!half_done && q >= nq_half) {
               half_done = true;
@@ -237,14 +276,9 @@ __global__ void __launch_bounds__(kTThreads, 1) k_tail_ws(const __grid_constant_
             split_store_tmem(acol0 + 2u * (uint32_t)q, a0);
             if (paired) split_store_tmem(acol1 + 2u * (uint32_t)q, a1);
           }
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) { if (!half_done) mbar_arrive(a_full); mbar_arrive(a_full + 8u); }
         } else {
           const uint32_t px0 = act ? src_a + (uint32_t)pix0 * kss_b : zero_a;
           const uint32_t px1 = px0 + (uint32_t)L.OW * kss_b;
-          bool half_done = false;
           for (int q = g; q < nq; q += 3) {
             if (!half_done && q >= nq_half) {
               half_done = true;
@@ -257,136 +291,172 @@ __global__ void __launch_bounds__(kTThreads, 1) k_tail_ws(const __grid_constant_
             split_store_tmem(acol0 + 2u * (uint32_t)q, in ? lds4(px0 + 16u * (uint32_t)q) : make_float4(0.f, 0.f, 0.f, 0.f));
             if (paired) split_store_tmem(acol1 + 2u * (uint32_t)q, in ? lds4(px1 + 16u * (uint32_t)q) : make_float4(0.f, 0.f, 0.f, 0.f));
           }
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) { if (!half_done) mbar_arrive(a_full); mbar_arrive(a_full + 8u); }
         }
+        if (warp_on) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) { if (!half_done) mbar_arrive(a_full); mbar_arrive(a_full + 8u); }
         // ---- epilogue ---------------------------------------------------------------------------------------------------
         // In-place layers: every depthwise read of the layer (all threads) must precede the first write; d_full implies it
         // (the MMAs were issued after both operand barriers completed).
-        const uint32_t bias_a = smem_u32(sBias + l * 128);
-        mbar_wait(d_full, ph_d);
-        ph_d ^= 1u;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t row_b = (uint32_t)L.IW * kss_b;
+        if (warp_on) {
+          const uint32_t bias_a = smem_u32(sBias + l * 128), alpha_a = smem_u32(sAlpha + l * 128);
+          const uint32_t rsrc_a = GEN ? act_a + 4u * (uint32_t)p.buf_off[L.rbuf] : src_a, ksr_b = GEN ? 4u * (uint32_t)p.buf_ks[L.rbuf] : kss_b;
+          const int res_q = (int)(ksr_b >> 4);
+          mbar_wait(d_full, ph_d);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t row_b = (uint32_t)L.IW * ksr_b;
 #pragma unroll 1
-        for (int t = 0; t < ntiles; ++t) {
-          const int pix = pix0 + t * L.OW;                     // tile 1 = the row below
-          const uint32_t dcol = tm_lane + col_d(t);
-          // residual source pixel(s)
-          uint32_t res_a = zero_a;
-          if (act && L.res == 1) res_a = src_a + (uint32_t)pix * kss_b;
-          if (act && L.res == 2) res_a = src_a + (uint32_t)((2 * oy) * L.IW + 2 * ox) * kss_b;
-          const uint32_t out_a = dst_a + (uint32_t)(act ? pix : 0) * ksd_b;
-          float* o1 = nullptr; float* o2 = nullptr;
-          if (L.kind == 1) {
-            o1 = p.outs[L.o1] + (size_t)img * p.out_istride[L.o1] + (size_t)(act ? pix : 0) * p.out_pix[L.o1];
-            if (L.o2 >= 0) o2 = p.outs[L.o2] + (size_t)img * p.out_istride[L.o2] + (size_t)(act ? pix : 0) * p.out_pix[L.o2];
-          }
-          for (int c16 = g; c16 < (L.Npad >> 4); c16 += 3) {
-            uint32_t u[16];
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
-                  "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
-                : "r"(dcol + 16u * (uint32_t)c16));
-            float4 bv[4], rv[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int cq = 4 * c16 + j;
-              const uint32_t qo = 16u * (uint32_t)cq;
-              bv[j] = lds4(bias_a + qo);
-              rv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (L.res == 1) {
-                if (cq < src_q) rv[j] = lds4(res_a + qo);
-              } else if (L.res == 2) {
-                if (cq < src_q) rv[j] = max4(max4(lds4(res_a + qo), lds4(res_a + kss_b + qo)), max4(lds4(res_a + row_b + qo), lds4(res_a + row_b + kss_b + qo)));
-              }
+          for (int t = 0; t < ntiles; ++t) {
+            const int pix = pix0 + t * L.OW;                     // tile 1 = the row below
+            const uint32_t dcol = tm_lane + col_d(t);
+            // residual source pixel(s)
+            uint32_t res_a = zero_a;
+            if (act && L.res == 1) res_a = rsrc_a + (uint32_t)pix * ksr_b;
+            if (act && L.res == 2) res_a = rsrc_a + (uint32_t)((2 * oy) * L.IW + 2 * ox) * ksr_b;
+            const uint32_t out_a = dst_a + (uint32_t)(act ? pix : 0) * ksd_b;
+            float* o1 = nullptr; float* o2 = nullptr;
+            int o1_q = 0;
+            if (GEN ? L.o1 >= 0 : L.kind == 1) {
+              o1 = p.outs[L.o1] + (size_t)img * p.out_istride[L.o1] + (size_t)(act ? pix : 0) * p.out_pix[L.o1];
+              o1_q = p.out_pix[L.o1] >> 2;
+              if (L.o2 >= 0) o2 = p.outs[L.o2] + (size_t)img * p.out_istride[L.o2] + (size_t)(act ? pix : 0) * p.out_pix[L.o2];
             }
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int c16 = g; c16 < (L.Npad >> 4); c16 += 3) {
+              uint32_t u[16];
+              asm volatile(
+                  "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                  : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                    "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+                  : "r"(dcol + 16u * (uint32_t)c16));
+              float4 bv[4], rv[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int cq = 4 * c16 + j;
-              float4 v = make_float4(__uint_as_float(u[4 * j]) + bv[j].x, __uint_as_float(u[4 * j + 1]) + bv[j].y,
+              for (int j = 0; j < 4; ++j) {
+                const int cq = 4 * c16 + j;
+                const uint32_t qo = 16u * (uint32_t)cq;
+                bv[j] = lds4(bias_a + qo);
+                rv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (L.res == 1) {
+                  if (cq < res_q) rv[j] = lds4(res_a + qo);
+                } else if (L.res == 2) {
+                  if (cq < res_q) rv[j] = max4(max4(lds4(res_a + qo), lds4(res_a + ksr_b + qo)), max4(lds4(res_a + row_b + qo), lds4(res_a + row_b + ksr_b + qo)));
+                }
+              }
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int cq = 4 * c16 + j;
+                float4 v;
+                if (GEN) v = make_float4(fmaf(__uint_as_float(u[4 * j]), L.wscale, bv[j].x), fmaf(__uint_as_float(u[4 * j + 1]), L.wscale, bv[j].y),
+                                         fmaf(__uint_as_float(u[4 * j + 2]), L.wscale, bv[j].z), fmaf(__uint_as_float(u[4 * j + 3]), L.wscale, bv[j].w));
+                else v = make_float4(__uint_as_float(u[4 * j]) + bv[j].x, __uint_as_float(u[4 * j + 1]) + bv[j].y,
                                      __uint_as_float(u[4 * j + 2]) + bv[j].z, __uint_as_float(u[4 * j + 3]) + bv[j].w);
-              if (L.kind == 0) {
-                v.x += rv[j].x; v.y += rv[j].y; v.z += rv[j].z; v.w += rv[j].w;
-                if (L.relu) v = max4(v, make_float4(0.f, 0.f, 0.f, 0.f));
-                if (act && cq < dst_q) sts4(out_a + 16u * (uint32_t)cq, v);       // columns >= Cout come out as exact zeros
-              } else if (act) {
-                const int c = 4 * cq;
-                if (c + 4 <= L.c1) {
-                  *reinterpret_cast<float4*>(o1 + c) = v;
-                } else {
-                  const float vv[4] = {v.x, v.y, v.z, v.w};
+                if (L.kind != 1) {
+                  v.x += rv[j].x; v.y += rv[j].y; v.z += rv[j].z; v.w += rv[j].w;
+                  if (L.act == 1) {
+                    v = max4(v, make_float4(0.f, 0.f, 0.f, 0.f));
+                  } else if (GEN && L.act == 2) {
+                    const float4 al = lds4(alpha_a + 16u * (uint32_t)cq);
+                    v = make_float4(fmaf(al.x, fminf(v.x, 0.f), fmaxf(v.x, 0.f)), fmaf(al.y, fminf(v.y, 0.f), fmaxf(v.y, 0.f)),
+                                    fmaf(al.z, fminf(v.z, 0.f), fmaxf(v.z, 0.f)), fmaf(al.w, fminf(v.w, 0.f), fmaxf(v.w, 0.f)));
+                  }
+                  if (act && cq < dst_q) sts4(out_a + 16u * (uint32_t)cq, v);       // columns >= Cout come out as exact zeros
+                  if (GEN && act && cq < o1_q) *reinterpret_cast<float4*>(o1 + 4 * cq) = v;   // the tensor is also read outside the chain
+                } else if (act) {
+                  const int c = 4 * cq;
+                  if (c + 4 <= L.c1) {
+                    *reinterpret_cast<float4*>(o1 + c) = v;
+                  } else {
+                    const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                  for (int e = 0; e < 4; ++e)
-                    if (c + e >= L.c1 && c + e - L.c1 < L.c2) o2[c + e - L.c1] = vv[e];
+                    for (int e = 0; e < 4; ++e)
+                      if (c + e >= L.c1 && c + e - L.c1 < L.c2) o2[c + e - L.c1] = vv[e];
+                  }
                 }
               }
             }
           }
         }
+        ph_d ^= 1u;
         // the layer's writes (shared memory: generic proxy; TMEM reads done) before anybody starts the next layer
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("bar.sync 1, %0;" ::"n"(kTComputeThreads) : "memory");
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (l == p.last_a_layer && lane == 0) mbar_arrive(a_free);              // buffer A may take the next image
+        if (l == p.last_a_layer && lane == 0) mbar_arrive(a_free);              // buffer 0 may take the next image
       }
     }
   } else if (lane == 0) {
-    // =============================== control lane: TMA + weight ring + MMA issue ======================================
+    // =============================== control lane: TMA + weight rings + MMA issue =====================================
     const int total = my_images * nl;
-    auto load_weights = [&](int glayer) {
+    const int D = p.wdepth;
+    auto load_weights = [&](int glayer) {                      // pointwise record of (global) layer glayer -> ring slot glayer % D
       const TailLayerD& L = sL[glayer % nl];
-      const uint32_t bar = w_full + 8u * (uint32_t)(glayer & 1);
+      if (!L.rec_bytes) return;
+      const uint32_t slot = (uint32_t)(glayer % D), bar = w_full + 8u * slot;
       mbar_expect_tx(bar, (uint32_t)L.rec_bytes);
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(wring_a + (uint32_t)(glayer & 1) * (uint32_t)p.wbuf_bytes), "l"(p.blob + (size_t)L.rec_off), "r"((uint32_t)L.rec_bytes), "r"(bar) : "memory");
+                   ::"r"(wring_a + slot * (uint32_t)p.wbuf_bytes), "l"(p.blob + (size_t)L.rec_off), "r"((uint32_t)L.rec_bytes), "r"(bar) : "memory");
+    };
+    auto load_taps = [&](int glayer) {                         // depthwise record -> ring slot glayer & 1
+      const TailLayerD& L = sL[glayer % nl];
+      if (!L.tap_bytes) return;
+      const uint32_t slot = (uint32_t)(glayer & 1), bar = t_full + 8u * slot;
+      mbar_expect_tx(bar, (uint32_t)L.tap_bytes);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(tring_a + slot * (uint32_t)p.tbuf_bytes), "l"(p.blob + (size_t)L.tap_off), "r"((uint32_t)L.tap_bytes), "r"(bar) : "memory");
     };
     auto load_image = [&](int img) {
-      mbar_expect_tx(in_full, in_bytes);
+      mbar_expect_tx(in_full, (uint32_t)p.in_bytes);
       asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-                   ::"r"(bufA_a), "l"(&tmap), "r"(0), "r"(0), "r"(0), "r"(img), "r"(in_full) : "memory");
+                   ::"r"(act_a), "l"(&tmap), "r"(0), "r"(0), "r"(0), "r"(img), "r"(in_full) : "memory");
     };
     if (my_images > 0) {
       load_image(blockIdx.x);
-      load_weights(0);
-      if (total > 1) load_weights(1);
+      for (int i = 0; i < D && i < total; ++i) load_weights(i);
+      for (int i = 0; i < 2 && i < total; ++i) load_taps(i);
     }
-    uint32_t ph_a = 0u, ph_d = 0u;
+    uint32_t ph_a = 0u, ph_d = 0u, ph_w0 = 0u, ph_w1 = 0u;
     int gl = 0, it = 0;
     for (int img = blockIdx.x; img < B; img += gridDim.x, ++it) {
       for (int l = 0; l < nl; ++l, ++gl) {
         const TailLayerD& L = sL[l];
-        const int ntiles = (L.OH * L.OW == 256 && L.OW == 16) ? 2 : 1;
-        const uint32_t idesc = (1u << 4) | ((uint32_t)(L.Npad >> 3) << 17) | ((128u >> 4) << 24);     // D f32, A / B f16, K-major
-        const uint32_t sbo = (uint32_t)(L.K16 >> 3) * 128u;
-        const uint32_t b_hi = ((sbo >> 4) & 0x3FFFu) | (1u << 14);
-        const uint32_t wb_a = wring_a + (uint32_t)(gl & 1) * (uint32_t)p.wbuf_bytes;
-        const uint32_t b_lo0 = ((wb_a & 0x3FFFFu) >> 4) | ((kLBO >> 4) << 16);
-        const int ksteps = L.K16 >> 4, khalf = L.K16 >> 5;          // K steps of the first operand half
-        mbar_wait(w_full + 8u * (uint32_t)(gl & 1), (uint32_t)((gl >> 1) & 1));
-        for (int half = 0; half < 2; ++half) {
-          mbar_wait(a_full + 8u * (uint32_t)half, ph_a);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const int k0 = half ? khalf : 0, k1 = half ? ksteps : khalf;
-          for (int t = 0; t < ntiles; ++t) {
-            const uint32_t dcol = tmem_base + col_d(t), acol = tmem_base + col_a(t);
+        if (!GEN || L.kind != 3) {
+          const int ntiles = L.OH * L.OW > 128 ? 2 : 1;
+          const uint32_t idesc = (1u << 4) | ((uint32_t)(L.Npad >> 3) << 17) | ((128u >> 4) << 24);     // D f32, A / B f16, K-major
+          const uint32_t sbo = (uint32_t)(L.K16 >> 3) * 128u;
+          const uint32_t b_hi = ((sbo >> 4) & 0x3FFFu) | (1u << 14);
+          const int slot = gl % D;
+          const uint32_t wb_a = wring_a + (uint32_t)slot * (uint32_t)p.wbuf_bytes;
+          const uint32_t b_lo0 = ((wb_a & 0x3FFFFu) >> 4) | ((kLBO >> 4) << 16);
+          const uint32_t b_lo1 = (((wb_a + (uint32_t)(L.Npad * L.K16) * 2u) & 0x3FFFFu) >> 4) | ((kLBO >> 4) << 16);   // W_lo (w_parts == 2)
+          const int ksteps = L.K16 >> 4, khalf = L.K16 >> 5;          // K steps of the first operand half
+          if (slot) { mbar_wait(w_full + 8u, ph_w1); ph_w1 ^= 1u; } else { mbar_wait(w_full, ph_w0); ph_w0 ^= 1u; }
+          for (int half = 0; half < 2; ++half) {
+            mbar_wait(a_full + 8u * (uint32_t)half, ph_a);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int k0 = half ? khalf : 0, k1 = half ? ksteps : khalf;
+            for (int t = 0; t < ntiles; ++t) {
+              const uint32_t dcol = tmem_base + col_d(t), acol = tmem_base + col_a(t);
 #pragma unroll 1
-            for (int ks = k0; ks < k1; ++ks) {
-              mma_ts_f16(dcol, acol + 8u * (uint32_t)ks, b_lo0 + 16u * (uint32_t)ks, b_hi, idesc, ks ? 1u : 0u);
-              mma_ts_f16(dcol, acol + 64u + 8u * (uint32_t)ks, b_lo0 + 16u * (uint32_t)ks, b_hi, idesc, 1u);
+              for (int ks = k0; ks < k1; ++ks) {
+                mma_ts_f16(dcol, acol + 8u * (uint32_t)ks, b_lo0 + 16u * (uint32_t)ks, b_hi, idesc, ks ? 1u : 0u);
+                mma_ts_f16(dcol, acol + 64u + 8u * (uint32_t)ks, b_lo0 + 16u * (uint32_t)ks, b_hi, idesc, 1u);
+                if (GEN && L.w_parts == 2) mma_ts_f16(dcol, acol + 8u * (uint32_t)ks, b_lo1 + 16u * (uint32_t)ks, b_hi, idesc, 1u);
+              }
             }
           }
+          ph_a ^= 1u;
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(d_full) : "memory");
+          // this layer's MMAs have read the weight buffer and every thread has read its taps: their ring slots are free
+          mbar_wait(d_full, ph_d);
+          ph_d ^= 1u;
+        } else {
+          mbar_wait(a_full, ph_a);
+          mbar_wait(a_full + 8u, ph_a);
+          ph_a ^= 1u;
         }
-        ph_a ^= 1u;
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(d_full) : "memory");
-        // this layer's MMAs have read the weight buffer and every thread has read its taps: stream in the layer after next
-        mbar_wait(d_full, ph_d);
-        ph_d ^= 1u;
-        if (gl + 2 < total) load_weights(gl + 2);
+        if (gl + D < total) load_weights(gl + D);
+        if (gl + 2 < total) load_taps(gl + 2);
         if (l == p.last_a_layer && img + (int)gridDim.x < B) {
           mbar_wait(a_free, (uint32_t)(it & 1));
           load_image(img + (int)gridDim.x);
@@ -417,12 +487,12 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// f32 [cap][H][W][CinS], box {KSA, W, H, 1}: channels >= CinS are zero-filled (the residual's zero channel pad)
+// f32 [cap][H][W][CinS], box {buf_ks[0], W, H, 1}: channels >= CinS are zero-filled (the residual's zero channel pad)
 bool tail_tensor_map(const TailP& p, int cap, CUtensorMap* out) {
   typedef std::tuple<const void*, int, int, int, int, int, long long> Key;
   static std::mutex mu;
   static std::map<Key, CUtensorMap> cache;
-  Key key(p.in, cap, p.H, p.W, p.CinS, p.KSA, p.in_istride);
+  Key key(p.in, cap, p.H, p.W, p.CinS, p.buf_ks[0], p.in_istride);
   std::lock_guard<std::mutex> g(mu);
   auto it = cache.find(key);
   if (it != cache.end()) { *out = it->second; return true; }
@@ -430,7 +500,7 @@ bool tail_tensor_map(const TailP& p, int cap, CUtensorMap* out) {
   if (!enc) return false;
   cuuint64_t gdim[4] = {(cuuint64_t)p.CinS, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)cap};
   cuuint64_t gstr[3] = {(cuuint64_t)p.CinS * 4, (cuuint64_t)p.W * p.CinS * 4, (cuuint64_t)p.in_istride * 4};
-  cuuint32_t box[4] = {(cuuint32_t)p.KSA, (cuuint32_t)p.W, (cuuint32_t)p.H, 1u};
+  cuuint32_t box[4] = {(cuuint32_t)p.buf_ks[0], (cuuint32_t)p.W, (cuuint32_t)p.H, 1u};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUtensorMap tm;
   CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.in), gdim, gstr, box, estr,
@@ -445,10 +515,10 @@ bool tail_tensor_map(const TailP& p, int cap, CUtensorMap* out) {
 
 }  // namespace
 
-size_t tail_smem_bytes(int PA, int KSA, int PB, int KSB, int wbuf_bytes) {
-  size_t head = (size_t)kTailMaxLayers * sizeof(TailLayerD) + (size_t)kTailMaxLayers * 128 * 4 + 16 * 8 + 128;
-  size_t bufs = ((size_t)PA * KSA + (size_t)PB * KSB + 128) * 4 + 128;
-  return head + bufs + 2 * (size_t)wbuf_bytes;
+size_t tail_smem_bytes(int act_floats, int wbuf_bytes, int wdepth, int tbuf_bytes) {
+  size_t head = (size_t)kTailMaxLayers * sizeof(TailLayerD) + 2 * (size_t)kTailMaxLayers * 128 * 4 + 16 * 8 + 16 * 4 + 128;
+  size_t bufs = ((size_t)act_floats + 128) * 4 + 128;
+  return head + bufs + 2 * (size_t)tbuf_bytes + (size_t)wdepth * wbuf_bytes;
 }
 
 bool launch_tail_ws(const TailP& p, int B, int cap, cudaStream_t s) {
@@ -464,12 +534,14 @@ bool launch_tail_ws(const TailP& p, int B, int cap, cudaStream_t s) {
     std::lock_guard<std::mutex> g(mu);
     size_t& c = cur[dev];
     if (p.smem_bytes > c) {
-      if (cudaFuncSetAttribute(k_tail_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes) != cudaSuccess) return false;
+      if (cudaFuncSetAttribute(k_tail_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes) != cudaSuccess ||
+          cudaFuncSetAttribute(k_tail_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes) != cudaSuccess) return false;
       c = p.smem_bytes;
     }
   }
   const int grid = std::min(B, sms);
-  k_tail_ws<<<grid, kTThreads, p.smem_bytes, s>>>(tm, p, B);
+  if (p.generic) k_tail_ws<true><<<grid, kTThreads, p.smem_bytes, s>>>(tm, p, B);
+  else k_tail_ws<false><<<grid, kTThreads, p.smem_bytes, s>>>(tm, p, B);
   return true;
 }
 

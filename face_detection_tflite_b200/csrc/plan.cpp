@@ -196,17 +196,22 @@ struct Builder {
     s->NPG = 128 / s->TM;
   }
 
-  // ---- analysis of one pointwise conv: DW3x3 -> PW -> (+res) -> act ---------------------------
-  bool analyse_pointwise(int ci, Fused* F) {
+  // ---- graph pattern of one pointwise conv: [DW3x3 ->] PW [-> ADD(residual | PAD / MAXPOOL2x2 of it)] [-> RELU | PRELU] --------
+  struct PwMatch {
+    bool has_dw = false;
+    int dws = 1, dpt = 0, dpl = 0;
+    int src = -1, cur = -1, res = -1, pool = 0, act = kActNone, alpha_tf = -1;
+    std::vector<int> absorbed;     // ops folded into the step besides the CONV_2D itself (the depthwise first when has_dw)
+  };
+  // graph_only: the residual source need not be produced by an earlier STEP (the caller checks where it lives)
+  bool match_pointwise(int ci, PwMatch* M, bool graph_only) {
     const TfOp& conv = m.ops[ci];
+    if (conv.code != kOpConv2D || conv.in.size() < 2) return false;
     const TfTensor& wt = m.tensors[conv.in[1]];
     if (wt.shape.size() != 4 || wt.shape[1] != 1 || wt.shape[2] != 1) return false;
     if (conv.stride_h != 1 || conv.stride_w != 1 || (conv.act != 0 && conv.act != 1)) return false;
-    PStep st;
-    st.kind = kStepDwPw;
-    std::vector<int> absorbed;
     int X = conv.in[0];
-    int src = X;
+    M->src = X;
     int dwi = m.producer(X);
     if (dwi >= 0 && !done[dwi] && m.ops[dwi].code == kOpDwConv2D && ncons[X] == 1 && !is_view(X)) {
       const TfOp& dw = m.ops[dwi];
@@ -215,30 +220,19 @@ struct Builder {
                 dw.dil_h == 1 && dw.dil_w == 1 && dw.padding == 0 && dw.stride_h == dw.stride_w &&
                 (dw.stride_h == 1 || dw.stride_h == 2) && dw.act == 0 && dw.in.size() >= 3;
       if (ok) {
-        st.has_dw = true;
-        st.dws = dw.stride_h;
-        src = dw.in[0];
-        const TfTensor& it = m.tensors[src];
-        same_pad(it.dim(1), 3, st.dws, &st.dpt);
-        same_pad(it.dim(2), 3, st.dws, &st.dpl);
-        absorbed.push_back(dwi);
+        M->has_dw = true;
+        M->dws = dw.stride_h;
+        M->src = dw.in[0];
+        const TfTensor& it = m.tensors[M->src];
+        same_pad(it.dim(1), 3, M->dws, &M->dpt);
+        same_pad(it.dim(2), 3, M->dws, &M->dpl);
+        M->absorbed.push_back(dwi);
       }
     }
-    const TfTensor& st_in = m.tensors[src];
-    if (st_in.shape.size() != 4) return false;
-    if (is_view(src) && (st_in.dim(3) % 4 != 0 || views[src].off % 4 != 0 || P.out_elems[views[src].root] % 4 != 0))
-      return false;
-    int Cin = st_in.dim(3);
-    st.Cout = wt.shape[0];
-    st.K = Cin;
-    st.KP = ru(Cin, 4);
-    st.KS = smem_stride(st.KP);
-    plan_columns(&st);
-    // epilogue chain
+    const int Cout = wt.shape[0];
     int cur = conv.out[0];
-    int res = -1, alpha_tf = -1;
-    st.act = conv.act == 1 ? kActRelu : kActNone;
-    if (st.act == kActNone && !is_view(cur)) {
+    M->act = conv.act == 1 ? kActRelu : kActNone;
+    if (M->act == kActNone && !is_view(cur)) {
       int c = sole_consumer(cur);
       if (c >= 0 && !done[c] && m.ops[c].code == kOpAdd && (m.ops[c].act == 0 || m.ops[c].act == 1) &&
           m.ops[c].in.size() == 2) {
@@ -272,25 +266,58 @@ struct Builder {
         int rp = m.producer(r);
         // the residual source must be materialised by an earlier step: either a stand-alone op or
         // the final tensor of an already fused chain (never an absorbed intermediate)
-        bool produced_before = rp >= 0 && rp < ci && (!done[rp] || is_output_of_fused(r));
-        good = good && rt.shape.size() == 4 && rt.dim(3) <= st.Cout && produced_before;
+        bool produced_before = graph_only || (rp >= 0 && rp < ci && (!done[rp] || is_output_of_fused(r)));
+        good = good && rt.shape.size() == 4 && rt.dim(3) <= Cout && produced_before;
         if (good) {
           if (pool) good = (rt.dim(1) + 1) / 2 == ot.dim(1) && (rt.dim(2) + 1) / 2 == ot.dim(2);
           else good = rt.dim(1) == ot.dim(1) && rt.dim(2) == ot.dim(2);
         }
         if (good) {
-          res = r;
-          st.res_pool = pool;
-          // the residual is the block input itself: take it from the staged tile when it is there
-          bool even = rt.dim(1) % 2 == 0 && rt.dim(2) % 2 == 0;
-          st.res_mode = (st.has_dw && r == src && (!pool || (even && st.dws == 2))) ? 1 : 2;
-          absorbed.push_back(c);
-          for (int a : abs2) absorbed.push_back(a);
+          M->res = r;
+          M->pool = pool;
+          M->absorbed.push_back(c);
+          for (int a : abs2) M->absorbed.push_back(a);
           cur = add.out[0];
-          if (add.act == 1) st.act = kActRelu;
+          if (add.act == 1) M->act = kActRelu;
         }
       }
-      if (st.act == kActNone) fuse_activation(&cur, &st.act, &alpha_tf, &absorbed);
+      if (M->act == kActNone) fuse_activation(&cur, &M->act, &M->alpha_tf, &M->absorbed);
+    }
+    M->cur = cur;
+    return true;
+  }
+
+  // ---- analysis of one pointwise conv: DW3x3 -> PW -> (+res) -> act ---------------------------
+  bool analyse_pointwise(int ci, Fused* F) {
+    const TfOp& conv = m.ops[ci];
+    PwMatch M;
+    if (!match_pointwise(ci, &M, false)) return false;
+    const TfTensor& wt = m.tensors[conv.in[1]];
+    PStep st;
+    st.kind = kStepDwPw;
+    std::vector<int> absorbed = M.absorbed;
+    const int src = M.src;
+    st.has_dw = M.has_dw; st.dws = M.dws; st.dpt = M.dpt; st.dpl = M.dpl;
+    const TfTensor& st_in = m.tensors[src];
+    if (st_in.shape.size() != 4) return false;
+    if (is_view(src) && (st_in.dim(3) % 4 != 0 || views[src].off % 4 != 0 || P.out_elems[views[src].root] % 4 != 0))
+      return false;
+    int Cin = st_in.dim(3);
+    st.Cout = wt.shape[0];
+    st.K = Cin;
+    st.KP = ru(Cin, 4);
+    st.KS = smem_stride(st.KP);
+    plan_columns(&st);
+    // epilogue chain
+    int cur = M.cur;
+    int res = M.res, alpha_tf = M.alpha_tf;
+    st.act = M.act;
+    if (res >= 0) {
+      const TfTensor& rt = m.tensors[res];
+      st.res_pool = M.pool;
+      // the residual is the block input itself: take it from the staged tile when it is there
+      bool even = rt.dim(1) % 2 == 0 && rt.dim(2) % 2 == 0;
+      st.res_mode = (st.has_dw && res == src && (!M.pool || (even && st.dws == 2))) ? 1 : 2;
     }
     // spatial tiling
     const TfTensor& ot = m.tensors[conv.out[0]];
@@ -694,6 +721,45 @@ struct Builder {
     st.sh = conv.stride_h; st.sw = conv.stride_w;
     int Cin = wt.shape[3];
     st.Cout = wt.shape[0];
+    // the window is the whole map (VALID, 1x1 output): one dense contraction per image -> k_fc_tc (tcgen05 GEMM over the chunk)
+    if (use_tc && conv.padding == 1 && st.kh == it.dim(1) && st.kw == it.dim(2) && ot.numel() == st.Cout && conv.act == 0 &&
+        !is_view(conv.in[0]) && Cin % 4 == 0 && Cin == it.dim(3) && (st.kh * st.kw * Cin) % 16 == 0 && st.kh * st.kw * Cin <= 384) {
+      std::vector<float> w, b;
+      if (!m.const_f32(conv.in[1], &w)) return fail("conv weights are not constant");
+      if (conv.in.size() > 2 && conv.in[2] >= 0) { if (!m.const_f32(conv.in[2], &b)) return fail("conv bias is not constant"); }
+      b.resize(st.Cout, 0.f);
+      st.kind = kStepFcTc;
+      st.K = st.kh * st.kw * Cin;
+      st.K8 = st.K;                                  // K16
+      st.w_parts = f16_exact(w) ? 1 : 2;
+      float scale = 1.f, wsc = 1.f;
+      if (st.w_parts == 2) {
+        float mx = 0.f;
+        for (float v : w) mx = std::max(mx, std::fabs(v));
+        if (mx > 0.f) { int e; std::frexp(mx, &e); scale = std::ldexp(1.f, 14 - e); }
+      }
+      const int ntile = (st.Cout + 127) / 128;
+      std::vector<float> rec;
+      for (int tI = 0; tI < ntile; ++tI) {
+        std::vector<float> r1 = pack_w_f16(w, std::min(128, st.Cout - tI * 128), st.K, 128, st.K, st.w_parts, &wsc, scale, tI * 128);
+        rec.insert(rec.end(), r1.begin(), r1.end());
+      }
+      st.ts_rec_bytes = st.w_parts * 128 * st.K * 2;
+      st.out_scale = 1.0 / (double)scale;
+      st.w = push(rec, rec.size());
+      st.bias = push(b, b.size() + 8);
+      st.smem = (size_t)st.ts_rec_bytes + 256;
+      st.act = kActNone;
+      done[ci] = 1;
+      st.macs = (double)st.K * st.Cout;
+      st.name = m.tensors[conv.out[0]].name;
+      F->ok = true;
+      F->st = st;
+      F->src_tf = conv.in[0];
+      F->out_tf = conv.out[0];
+      fused_outputs.push_back(conv.out[0]);
+      return true;
+    }
     if (conv.padding == 0) { same_pad(it.dim(1), st.kh, st.sh, &st.pt); same_pad(it.dim(2), st.kw, st.sw, &st.pl); }
     st.K = st.kh * st.kw * Cin;
     st.KP = ru(st.K, 4);
@@ -820,6 +886,86 @@ struct Builder {
   // kTailMaxLayers layers) leaves the plan as it is.
   static int odd_quads(int c) { int q = ru(c, 4) / 4; if (q % 2 == 0) ++q; return q * 4; }
 
+  // fp16 K-major core-matrix image of W [N][K] (8 rows x 16 bytes per core matrix, row groups SBO = (K16 / 8) * 128 bytes apart), as
+  // floats; parts == 2: W * 2^s = hi + lo, both fp16 (the second image follows the first), s chosen so that the largest weight sits
+  // near 2^13 (no fp16 subnormals among the significant ones); *wscale = 2^-s.  parts == 1 requires exact fp16 weights (s = 0).
+  std::vector<float> pack_w_f16(const std::vector<float>& w, int N, int K, int Npad, int K16, int parts, float* wscale, float force_scale = 0.f, int n_first = 0) {
+    const size_t SBO16 = (size_t)(K16 / 8) * 128;
+    std::vector<uint16_t> img((size_t)parts * Npad * K16, 0);
+    float scale = 1.f;
+    if (parts == 2) {
+      float mx = 0.f;
+      for (float v : w) mx = std::max(mx, std::fabs(v));
+      if (mx > 0.f) { int e; std::frexp(mx, &e); scale = std::ldexp(1.f, 14 - e); }
+      if (force_scale > 0.f) scale = force_scale;
+    }
+    for (int n = 0; n < N; ++n)
+      for (int k = 0; k < K; ++k) {
+        const float v = w[(size_t)(n_first + n) * K + k] * scale;
+        const size_t o = ((size_t)(n >> 3) * SBO16 + (size_t)(k >> 3) * 128 + (size_t)(n & 7) * 16 + (size_t)(k & 7) * 2) / 2;
+        const uint16_t hb = f32_to_f16(v);
+        img[o] = hb;
+        if (parts == 2) img[(size_t)Npad * K16 + o] = f32_to_f16(v - f16_to_f32(hb));
+      }
+    *wscale = 1.f / scale;
+    std::vector<float> rec((img.size() + 1) / 2, 0.f);
+    std::memcpy(rec.data(), img.data(), img.size() * 2);
+    return rec;
+  }
+  static bool f16_exact(const std::vector<float>& w) {
+    for (float v : w) if (f16_to_f32(f32_to_f16(v)) != v) return false;
+    return true;
+  }
+
+  // Shared-memory geometry of a k_tail_ws step from its layers and buffers (pixels, widest tenant); false: does not fit.
+  bool finish_tail(PStep* t, const std::vector<int>& buf_px, const std::vector<int>& buf_c) {
+    if (buf_px.empty() || buf_px.size() > (size_t)kTailMaxBufs || t->tail.empty() || (int)t->tail.size() > kTailMaxLayers) return false;
+    int off = 0;
+    t->tail_nbuf = (int)buf_px.size();
+    for (size_t b = 0; b < buf_px.size(); ++b) {
+      const int ks = odd_quads(buf_c[b]);
+      t->tail_buf_off[b] = off; t->tail_buf_ks[b] = ks; t->tail_buf_px[b] = buf_px[b];
+      off += buf_px[b] * ks;
+    }
+    if (t->tail_buf_ks[0] > 256) return false;                // TMA box limit
+    t->tail_act_floats = off;
+    t->tail_in_bytes = buf_px[0] * t->tail_buf_ks[0] * 4;
+    size_t wbuf = 0, tbuf = 0;
+    int last0 = 0;
+    for (size_t li = 0; li < t->tail.size(); ++li) {
+      const TailLayerD& L = t->tail[li];
+      wbuf = std::max(wbuf, (size_t)L.rec_bytes);
+      tbuf = std::max(tbuf, (size_t)L.tap_bytes);
+      if (L.rec_bytes % 16 || L.tap_bytes % 16) return false;
+      if (L.src == 0 || L.dst == 0 || (L.res && L.rbuf == 0)) last0 = (int)li;
+    }
+    t->tail_last_a = last0;
+    t->tail_wbuf = (int)((wbuf + 127) / 128 * 128);
+    t->tail_tbuf = (int)((tbuf + 127) / 128 * 128);
+    auto bytes = [&](int depth) {       // = tail_smem_bytes() in kernels_tail.cu
+      return (size_t)kTailMaxLayers * sizeof(TailLayerD) + 2 * (size_t)kTailMaxLayers * 512 + 16 * 8 + 16 * 4 + 128 +
+             ((size_t)off + 128) * 4 + 128 + 2 * (size_t)t->tail_tbuf + (size_t)depth * t->tail_wbuf;
+    };
+    t->tail_wdepth = bytes(2) <= (size_t)225 * 1024 ? 2 : 1;
+    t->smem = bytes(t->tail_wdepth);
+    return t->smem <= (size_t)225 * 1024;
+  }
+
+  // Replaces steps [f, end) by the tail step and redoes the liveness bookkeeping.
+  void redo_liveness() {
+    for (PTensor& x : P.tensors) { x.materialized = false; x.def_step = -1; x.last_use = -1; }
+    for (size_t i = 0; i < P.steps.size(); ++i) {
+      const PStep& s = P.steps[i];
+      P.tensors[s.out].materialized = true;
+      if (s.out2 >= 0) P.tensors[s.out2].materialized = true;
+      for (int e : s.extra_out) { P.tensors[e].materialized = true; use((int)i, e); }
+      if (!s.in_u8) use((int)i, s.in);
+      use((int)i, s.in2);
+      use((int)i, s.out);
+      use((int)i, s.out2);
+    }
+  }
+
   void fuse_tail() {
     const int S = (int)P.steps.size();
     auto block_ok = [&](const PStep& s) {
@@ -869,13 +1015,12 @@ struct Builder {
         if (!P.steps[j].has_dw && P.steps[j].in == P.steps[i].out) order.push_back(j);
     }
     if ((int)order.size() != S - f || (int)order.size() > kTailMaxLayers) return;
-    // buffers: A until the stride-2 block, B after it
+    // buffers: 0 until the stride-2 block, 1 after it
     std::map<int, int> buf_of;
     buf_of[X] = 0;
-    int maxA = P.tensors[X].Cs, maxB = 4, PA = P.tensors[X].H * P.tensors[X].W, PB = 1, n_s2 = 0, last_a = 0;
+    int maxA = P.tensors[X].Cs, maxB = 4, PA = P.tensors[X].H * P.tensors[X].W, PB = 1, n_s2 = 0;
     PStep t;
     t.kind = kStepTailWs;
-    size_t wbuf = 0;
     for (size_t li = 0; li < order.size(); ++li) {
       const PStep& s = P.steps[order[li]];
       const PTensor& in = P.tensors[s.in];
@@ -885,14 +1030,15 @@ struct Builder {
       TailLayerD L = {};
       L.kind = s.has_dw ? 0 : 1;
       L.src = bi->second;
+      L.rbuf = L.src;
       L.IH = in.H; L.IW = in.W; L.OH = out.H; L.OW = out.W;
       L.Cin = in.C; L.Cout = s.Cout; L.K16 = ru(in.C, 16); L.Npad = ru(s.Cout, 16);
       L.o1 = L.o2 = -1;
-      if (L.src == 0) last_a = (int)li;
+      L.w_parts = 1; L.wscale = 1.f; L.alpha_off = 0;
       if (s.has_dw) {
         L.stride = s.dws; L.pad = s.dpt;
         L.res = s.in2 >= 0 ? (s.res_pool ? 2 : 1) : 0;
-        L.relu = s.act == kActRelu ? 1 : 0;
+        L.act = s.act == kActRelu ? 1 : 0;
         if (s.dws == 2) {
           if (L.src != 0 || ++n_s2 > 1) return;
           L.dst = 1;
@@ -904,38 +1050,33 @@ struct Builder {
         buf_of[s.out] = L.dst;
         (L.dst ? maxB : maxA) = std::max(L.dst ? maxB : maxA, ru(s.Cout, 4));
       } else {
-        L.dst = L.src;
+        L.dst = -1;
         L.c1 = s.c2 > 0 ? s.c1 : s.Cout; L.c2 = s.c2;
         L.o1 = (int)t.tail_outs.size(); t.tail_outs.push_back(s.out);
         if (s.c2 > 0) { L.o2 = (int)t.tail_outs.size(); t.tail_outs.push_back(s.out2); }
         if (t.tail_outs.size() > 4) return;
       }
-      // the kernel's M-tile maps: a 16-wide 256-pixel map (two tiles: even / odd rows) or at most 128 pixels (one tile)
-      if (!((L.OH * L.OW == 256 && L.OW == 16) || L.OH * L.OW <= 128)) return;
+      // the kernel's M-tile maps: at most 128 pixels (one tile) or an even-height map of at most 256 (two tiles: even / odd rows)
+      if (!(L.OH * L.OW <= 128 || (L.OH * L.OW <= 256 && L.OH % 2 == 0 && (!s.has_dw || s.dws == 1)))) return;
       // the step's tensor-core operands back to plain arrays: W [Cout][Cin] (exact values), taps [9][K8], biases
       const size_t SBO8 = (size_t)(s.K8 / 4) * 128;
       const int K16 = L.K16;
-      std::vector<uint16_t> wh((size_t)L.Npad * K16, 0);
-      const size_t SBO16 = (size_t)(K16 / 8) * 128;
+      std::vector<float> wplain((size_t)s.Cout * in.C);
       for (int n = 0; n < s.Cout; ++n)
-        for (int k = 0; k < in.C; ++k) {
-          const float v = P.blob[(size_t)s.w + ((size_t)(n >> 3) * SBO8 + (size_t)(k >> 2) * 128 + (size_t)(n & 7) * 16 + (size_t)(k & 3) * 4) / 4];
-          const uint16_t hbits = f32_to_f16(v);
-          if (f16_to_f32(hbits) != v) return;                 // not an fp16-origin model: keep the TF32 hi/lo kernels
-          wh[((size_t)(n >> 3) * SBO16 + (size_t)(k >> 3) * 128 + (size_t)(n & 7) * 16 + (size_t)(k & 7) * 2) / 2] = hbits;
-        }
-      std::vector<float> rec((wh.size() + 1) / 2 + (s.has_dw ? (size_t)10 * K16 : 0), 0.f);
-      std::memcpy(rec.data(), wh.data(), wh.size() * 2);
+        for (int k = 0; k < in.C; ++k)
+          wplain[(size_t)n * in.C + k] = P.blob[(size_t)s.w + ((size_t)(n >> 3) * SBO8 + (size_t)(k >> 2) * 128 + (size_t)(n & 7) * 16 + (size_t)(k & 3) * 4) / 4];
+      if (!f16_exact(wplain)) return;                           // not an fp16-origin model: keep the TF32 hi/lo kernels
+      std::vector<float> rec = pack_w_f16(wplain, s.Cout, in.C, L.Npad, K16, 1, &L.wscale);
+      L.rec_bytes = (int)(rec.size() * 4);
+      L.rec_off = (int)push(rec, rec.size());
       if (s.has_dw) {
-        float* dw = rec.data() + wh.size() / 2;
+        std::vector<float> dw((size_t)10 * K16, 0.f);
         for (int k = 0; k < 9; ++k)
           for (int c = 0; c < in.C; ++c) dw[(size_t)k * K16 + c] = P.blob[(size_t)s.dww + (size_t)k * s.K8 + c];
         for (int c = 0; c < in.C; ++c) dw[(size_t)9 * K16 + c] = P.blob[(size_t)s.dwb + c];
+        L.tap_bytes = (int)(dw.size() * 4);
+        L.tap_off = (int)push(dw, dw.size());
       }
-      L.rec_bytes = (int)(rec.size() * 4);
-      if (L.rec_bytes % 16) return;
-      wbuf = std::max(wbuf, (size_t)L.rec_bytes);
-      L.rec_off = (int)push(rec, rec.size());
       // pointwise bias [Npad]: the step's own array is zero-padded past Cout already (Npad16 >= Npad here)
       std::vector<float> bias((size_t)L.Npad, 0.f);
       for (int n = 0; n < s.Cout; ++n) bias[n] = P.blob[(size_t)s.bias + n];
@@ -943,12 +1084,7 @@ struct Builder {
       t.macs += s.macs;
       t.tail.push_back(L);
     }
-    t.tail_ksa = odd_quads(maxA); t.tail_ksb = odd_quads(maxB); t.tail_pa = PA; t.tail_pb = PB; t.tail_last_a = last_a;
-    t.tail_wbuf = (int)((wbuf + 127) / 128 * 128);
-    if (t.tail_ksa > 256 || t.tail_outs.empty()) return;
-    t.smem = (size_t)kTailMaxLayers * sizeof(TailLayerD) + (size_t)kTailMaxLayers * 512 + 256 +
-             ((size_t)PA * t.tail_ksa + (size_t)PB * t.tail_ksb + 128) * 4 + 128 + 2 * (size_t)t.tail_wbuf;     // = tail_smem_bytes()
-    if (t.smem > (size_t)225 * 1024) return;
+    if (t.tail_outs.empty() || !finish_tail(&t, {PA, PB}, {maxA, maxB})) return;
     t.in = X;
     t.out = t.tail_outs[0];
     for (size_t k = 1; k < t.tail_outs.size(); ++k) t.extra_out.push_back(t.tail_outs[k]);
@@ -956,17 +1092,203 @@ struct Builder {
     // replace the suffix and redo the liveness bookkeeping
     P.steps.resize(f);
     P.steps.push_back(t);
-    for (PTensor& x : P.tensors) { x.materialized = false; x.def_step = -1; x.last_use = -1; }
-    for (size_t i = 0; i < P.steps.size(); ++i) {
-      const PStep& s = P.steps[i];
-      P.tensors[s.out].materialized = true;
-      if (s.out2 >= 0) P.tensors[s.out2].materialized = true;
-      for (int e : s.extra_out) { P.tensors[e].materialized = true; use((int)i, e); }
-      if (!s.in_u8) use((int)i, s.in);
-      use((int)i, s.in2);
-      use((int)i, s.out);
-      use((int)i, s.out2);
+    redo_liveness();
+  }
+
+  // ---- image-resident chain found on the GRAPH (before the per-conv planning) --------------------------------------
+  // The face-landmark net below 12x12: seventeen small layers (two branches, PReLU, fp32 weights) that the per-layer
+  // kernels run at 1-10 % of any roofline.  From the first block whose input map fits one CTA (<= 256 pixels, <= 128
+  // channels) the matcher follows every [DW3x3 ->] PW1x1 [-> + residual] [-> ReLU / PReLU] pattern whose inputs live
+  // inside the chain, plus whole-map convolutions with one filter (a dot product), assigns shared-memory buffers by
+  // liveness (in place where the source dies) and emits ONE k_tail_ws step.  Tensors that are read outside the chain are
+  // also written to HBM by the layer that produces them.  A chain that would end in 1x1 heads is left to fuse_tail().
+  int chain_emit_at = -1;
+  PStep chain_step;
+  void fuse_chain() {
+    static const int want = [] { const char* e = std::getenv("FDT_CHAIN"); return e ? std::atoi(e) : 1; }();   // FDT_CHAIN=0: A/B, one launch per layer
+    if (!want) return;
+    for (size_t s0 = 0; s0 < m.ops.size() && chain_emit_at < 0; ++s0)
+      if (m.ops[s0].code == kOpConv2D && !done[s0]) try_chain((int)s0);
+  }
+
+  struct ChainLayer { int conv; PwMatch M; int kind; int out_tf; };
+
+  void try_chain(int s0) {
+    PwMatch M0;
+    if (!match_pointwise(s0, &M0, true) || !M0.has_dw) return;
+    const int T0 = M0.src;
+    {
+      const TfTensor& t0 = m.tensors[T0];
+      if (is_view(T0) || t0.shape.size() != 4 || t0.dim(1) * t0.dim(2) > 256 || t0.dim(3) > 128 || m.producer(T0) < 0) return;
     }
+    std::vector<char> absorbed(m.ops.size(), 0);
+    std::vector<int> chainT{T0};
+    auto in_chain = [&](int t) { return std::find(chainT.begin(), chainT.end(), t) != chainT.end(); };
+    std::vector<ChainLayer> layers;
+    // pass A1: the convolutions, in graph order
+    for (size_t j = s0; j < m.ops.size(); ++j) {
+      const TfOp& op = m.ops[j];
+      if (op.code != kOpConv2D || done[j]) continue;
+      PwMatch M;
+      if (match_pointwise((int)j, &M, true) && in_chain(M.src) && (M.res < 0 || in_chain(M.res))) {
+        const TfTensor& it = m.tensors[M.src];
+        const TfTensor& ot = m.tensors[M.cur];
+        const int Cout = m.tensors[op.in[1]].shape[0];
+        bool ok = it.shape.size() == 4 && ot.shape.size() == 4 && !is_view(M.cur) && it.dim(3) <= 128 && Cout <= 128;
+        const int npix = ok ? ot.dim(1) * ot.dim(2) : 0;
+        ok = ok && (npix <= 128 || (npix <= 256 && ot.dim(1) % 2 == 0 && (!M.has_dw || M.dws == 1)));
+        if (ok && M.has_dw) {
+          if (M.dws == 1) ok = M.dpt == 1 && M.dpl == 1;
+          else ok = it.dim(1) % 2 == 0 && it.dim(2) % 2 == 0 && M.dpt == 0 && M.dpl == 0;
+        }
+        if (ok && M.res >= 0) {
+          const TfTensor& rt = m.tensors[M.res];
+          if (M.pool) ok = rt.dim(1) == 2 * ot.dim(1) && rt.dim(2) == 2 * ot.dim(2);
+        }
+        if (ok) {
+          layers.push_back({(int)j, M, M.has_dw ? 0 : 2, M.cur});
+          absorbed[j] = 1;
+          for (int a : M.absorbed) absorbed[a] = 1;
+          chainT.push_back(M.cur);
+          continue;
+        }
+      }
+      // whole-map convolution with one filter: a dot product over the resident map
+      if (in_chain(op.in[0]) && op.in.size() >= 2) {
+        const TfTensor& wt = m.tensors[op.in[1]];
+        const TfTensor& it = m.tensors[op.in[0]];
+        if (wt.shape.size() == 4 && wt.shape[0] == 1 && wt.shape[1] == it.dim(1) && wt.shape[2] == it.dim(2) && op.padding == 1 &&
+            op.act == 0 && op.dil_h == 1 && op.dil_w == 1 && numel(op.out[0]) == 1) {
+          PwMatch M;
+          M.src = op.in[0]; M.cur = op.out[0];
+          layers.push_back({(int)j, M, 3, op.out[0]});
+          absorbed[j] = 1;
+        }
+      }
+    }
+    if (layers.size() < 3 || layers.size() > (size_t)kTailMaxLayers) return;
+    // pass A2: chain tensors read outside the chain (or graph outputs) are exits
+    std::vector<int> exits;
+    for (size_t j = 0; j < m.ops.size(); ++j) {
+      if (absorbed[j]) continue;
+      for (int i : m.ops[j].in) {
+        if (i < 0 || i == T0 || !in_chain(i)) continue;
+        const TfOp& op = m.ops[j];
+        if (op.code == kOpConv2D) {               // a 1x1 head on a chain tensor: that tail belongs to fuse_tail()
+          const TfTensor& wt = m.tensors[op.in[1]];
+          if (wt.shape.size() == 4 && wt.shape[1] == 1 && wt.shape[2] == 1) return;
+        }
+        if (std::find(exits.begin(), exits.end(), i) == exits.end()) exits.push_back(i);
+      }
+    }
+    for (int o : m.outputs) if (in_chain(o) && o != T0) return;
+    // pass B: buffers by liveness
+    const int NL = (int)layers.size();
+    std::map<int, int> last_read;                     // tensor -> last layer that reads it
+    for (int i = 0; i < NL; ++i) {
+      last_read[layers[i].M.src] = i;
+      if (layers[i].M.res >= 0) last_read[layers[i].M.res] = i;
+    }
+    std::map<int, int> buf_of;
+    std::vector<int> buf_px, buf_c, buf_free_after;   // a buffer is free after layer buf_free_after (its tenant's last read)
+    buf_of[T0] = 0;
+    buf_px.push_back(m.tensors[T0].dim(1) * m.tensors[T0].dim(2));
+    buf_c.push_back(ru(m.tensors[T0].dim(3), 4));
+    buf_free_after.push_back(last_read[T0]);
+    PStep t;
+    t.kind = kStepTailWs;
+    for (int i = 0; i < NL; ++i) {
+      const ChainLayer& cl = layers[i];
+      const TfOp& conv = m.ops[cl.conv];
+      const TfTensor& it = m.tensors[cl.M.src];
+      const TfTensor& ot = m.tensors[cl.out_tf];
+      TailLayerD L = {};
+      L.kind = cl.kind;
+      L.src = buf_of[cl.M.src];
+      L.rbuf = cl.M.res >= 0 ? buf_of[cl.M.res] : L.src;
+      L.o1 = L.o2 = -1;
+      L.wscale = 1.f; L.w_parts = 1; L.dst = -1;
+      L.IH = it.dim(1); L.IW = it.dim(2);
+      L.Cin = it.dim(3);
+      std::vector<float> w, b;
+      if (!m.const_f32(conv.in[1], &w)) return;
+      if (conv.in.size() > 2 && conv.in[2] >= 0 && !m.const_f32(conv.in[2], &b)) return;
+      if (cl.kind == 3) {
+        L.OH = L.IH; L.OW = L.IW; L.Cout = 1; L.K16 = 16; L.Npad = 4;
+        b.resize(4, 0.f);
+        L.bias_off = (int)push(b, 4);
+        const size_t n = ru((int)w.size(), 4);
+        L.tap_bytes = (int)(n * 4);
+        L.tap_off = (int)push(w, n);
+        L.o1 = (int)t.tail_outs.size(); t.tail_outs.push_back(pt(cl.out_tf));
+        t.macs += (double)w.size();
+        t.tail.push_back(L);
+        continue;
+      }
+      L.OH = ot.dim(1); L.OW = ot.dim(2);
+      L.Cout = m.tensors[conv.in[1]].shape[0];
+      L.K16 = ru(L.Cin, 16); L.Npad = ru(L.Cout, 16);
+      L.stride = cl.M.dws; L.pad = cl.M.dpt;
+      L.res = cl.M.res >= 0 ? (cl.M.pool ? 2 : 1) : 0;
+      L.act = cl.M.act;
+      // destination: in place when the source dies here and keeps its pixel count, else a free buffer of that size, else a new one
+      const int npix = L.OH * L.OW;
+      const int sb = L.src;
+      if (buf_px[sb] == npix && last_read[cl.M.src] == i && (sb != 0 || true)) {
+        L.dst = sb;
+      } else {
+        for (size_t k = 1; k < buf_px.size() && L.dst < 0; ++k)
+          if (buf_px[k] == npix && buf_free_after[k] < i && (int)k != L.rbuf) L.dst = (int)k;
+        if (L.dst < 0) { L.dst = (int)buf_px.size(); buf_px.push_back(npix); buf_c.push_back(4); buf_free_after.push_back(-1); }
+      }
+      if (L.dst >= kTailMaxBufs) return;
+      buf_of[cl.out_tf] = L.dst;
+      buf_c[L.dst] = std::max(buf_c[L.dst], ru(L.Cout, 4));
+      buf_free_after[L.dst] = last_read.count(cl.out_tf) ? last_read[cl.out_tf] : i;
+      if (std::find(exits.begin(), exits.end(), cl.out_tf) != exits.end()) {
+        L.o1 = (int)t.tail_outs.size(); t.tail_outs.push_back(pt(cl.out_tf));
+      }
+      if (t.tail_outs.size() > 4) return;
+      // weights
+      b.resize(L.Cout, 0.f);
+      L.w_parts = f16_exact(w) ? 1 : 2;
+      std::vector<float> rec = pack_w_f16(w, L.Cout, L.Cin, L.Npad, L.K16, L.w_parts, &L.wscale);
+      L.rec_bytes = (int)(rec.size() * 4);
+      L.rec_off = (int)push(rec, rec.size());
+      std::vector<float> bias((size_t)L.Npad, 0.f);
+      for (int n = 0; n < L.Cout; ++n) bias[n] = b[n];
+      L.bias_off = (int)push(bias, bias.size());
+      if (cl.M.alpha_tf >= 0) {
+        std::vector<float> al;
+        if (!m.const_f32(cl.M.alpha_tf, &al) || (int)al.size() != L.Cout) return;
+        L.alpha_off = (int)push(al, (size_t)L.Npad);
+      }
+      if (cl.kind == 0) {
+        const TfOp& dw = m.ops[cl.M.absorbed[0]];
+        std::vector<float> dwv, dbv;
+        if (!m.const_f32(dw.in[1], &dwv) || !m.const_f32(dw.in[2], &dbv)) return;
+        std::vector<float> rec2((size_t)10 * L.K16, 0.f);
+        for (int k = 0; k < 9; ++k)
+          for (int c = 0; c < L.Cin; ++c) rec2[(size_t)k * L.K16 + c] = dwv[(size_t)k * L.Cin + c];
+        for (int c = 0; c < L.Cin; ++c) rec2[(size_t)9 * L.K16 + c] = dbv[c];
+        L.tap_bytes = (int)(rec2.size() * 4);
+        L.tap_off = (int)push(rec2, rec2.size());
+      }
+      t.macs += (double)npix * ((double)L.Cin * L.Cout + (cl.kind == 0 ? 9.0 * L.Cin : 0.0));
+      t.tail.push_back(L);
+    }
+    if (t.tail_outs.empty() || !finish_tail(&t, buf_px, buf_c)) return;
+    t.in = pt(T0);
+    t.out = t.tail_outs[0];
+    for (size_t k = 1; k < t.tail_outs.size(); ++k) t.extra_out.push_back(t.tail_outs[k]);
+    t.name = "chain:" + m.tensors[layers.front().out_tf].name + ".." + m.tensors[layers.back().out_tf].name;
+    // commit
+    int first = (int)m.ops.size();
+    for (size_t j = 0; j < m.ops.size(); ++j)
+      if (absorbed[j]) { done[j] = 1; first = std::min(first, (int)j); }
+    for (int e : exits) fused_outputs.push_back(e);
+    chain_emit_at = first;
+    chain_step = t;
   }
 
   // ---- emission ---------------------------------------------------------------------------------
@@ -1012,6 +1334,7 @@ struct Builder {
     P.in_w = in.shape[2];
 
     // pass 1: fusion analysis
+    if (fuse == 1 && use_tc) fuse_chain();
     if (fuse >= 1) {
       for (size_t i = 0; i < no; ++i) {
         if (done[i] || m.ops[i].code != kOpConv2D) continue;
@@ -1040,6 +1363,13 @@ struct Builder {
     // pass 2: emission in graph order
     for (size_t i = 0; i < no; ++i) {
       const TfOp& op = m.ops[i];
+      if ((int)i == chain_emit_at) {
+        PStep s = chain_step;
+        if (!P.tensors[s.in].materialized) return fail("internal: the chain's input is not materialised");
+        int idx = (int)P.steps.size();
+        for (int e : s.extra_out) { P.tensors[e].materialized = true; use(idx, e); }
+        if (!emit(s)) return false;
+      }
       auto fit = fused.find((int)i);
       if (fit != fused.end()) {
         Fused& F = fit->second;
@@ -1211,8 +1541,9 @@ std::string Plan::describe() const {
     s += buf;
     for (size_t l = 0; l < st.tail.size(); ++l) {
       const TailLayerD& L = st.tail[l];
-      snprintf(buf, sizeof buf, "      tail %2zu %s buf %d->%d %dx%d->%dx%d s%d C %d->%d K16=%d Npad=%d res=%d relu=%d rec=%dB\n", l, L.kind ? "heads" : "block",
-               L.src, L.dst, L.IH, L.IW, L.OH, L.OW, L.stride, L.Cin, L.Cout, L.K16, L.Npad, L.res, L.relu, L.rec_bytes);
+      static const char* lk[] = {"block", "heads", "pw", "dot"};
+      snprintf(buf, sizeof buf, "      tail %2zu %s buf %d->%d %dx%d->%dx%d s%d C %d->%d K16=%d Npad=%d res=%d(buf %d) act=%d wparts=%d out=%d rec=%dB taps=%dB\n", l, lk[L.kind & 3],
+               L.src, L.dst, L.IH, L.IW, L.OH, L.OW, L.stride, L.Cin, L.Cout, L.K16, L.Npad, L.res, L.rbuf, L.act, L.w_parts, L.o1, L.rec_bytes, L.tap_bytes);
       s += buf;
     }
   }

@@ -53,7 +53,8 @@ struct PStep {
   // k_tail_ws: the layer program and its shared-memory geometry (see kernels_tail.cu)
   std::vector<TailLayerD> tail;
   std::vector<int> tail_outs;   // PTensor ids the heads write, indexed by TailLayerD::o1 / o2
-  int tail_ksa = 0, tail_ksb = 0, tail_pa = 0, tail_pb = 0, tail_last_a = 0, tail_wbuf = 0;
+  int tail_nbuf = 0, tail_buf_off[kTailMaxBufs] = {0}, tail_buf_ks[kTailMaxBufs] = {0}, tail_buf_px[kTailMaxBufs] = {0};   // shared-memory activation buffers
+  int tail_act_floats = 0, tail_in_bytes = 0, tail_last_a = 0, tail_wbuf = 0, tail_wdepth = 2, tail_tbuf = 0;
   double macs = 0;  // per image
 };
 

@@ -1,27 +1,36 @@
-// Layer program of k_tail_ws (kernels_tail.cu): the small-resolution BlazeBlocks and head pairs of a detector,
-// executed by ONE launch with the activations of an image resident in shared memory.  Built by plan.cpp, uploaded
-// by engine.cu, interpreted by the kernel.
+// Layer program of k_tail_ws (kernels_tail.cu): a chain of small-resolution layers executed by ONE launch with the
+// activations of an image resident in shared memory - the 16x16 / 8x8 BlazeBlocks and head pairs of a detector, or the
+// 12x12 ... 3x3 trunk and both branches of the face-landmark net.  Built by plan.cpp, uploaded by engine.cu,
+// interpreted by the kernel.
 #pragma once
 
 namespace fdt {
 
 struct TailLayerD {
-  int kind;            // 0: BlazeBlock (depthwise 3x3 -> pointwise -> + residual -> ReLU), 1: head pair (pointwise only -> graph outputs)
-  int src, dst;        // activation buffer read / written: 0 = A (first resolution), 1 = B (after the stride-2 block)
+  int kind;            // 0: block (depthwise 3x3 -> pointwise -> + residual -> activation), 1: head pair (pointwise only -> graph outputs),
+                       // 2: pointwise only -> activation -> buffer, 3: dot product of the whole map with one filter -> one scalar per image
+  int src, dst;        // shared-memory activation buffer read / written (dst -1: none)
   int stride, pad;     // depthwise stride, SAME pad-before
   int IH, IW, OH, OW;  // input / output spatial size
   int Cin, Cout, K16, Npad;
-  int res;             // 0 none, 1 the same pixel of src, 2 2x2 max-pool of src (zero channel pad in both)
-  int rec_off;         // float offset in the weight blob of the record [W fp16 Npad x K16 | dww 9 x K16 | dwb K16]
+  int res;             // 0 none, 1 the same pixel of buffer rbuf, 2 2x2 max-pool of buffer rbuf (zero channel pad in both)
+  int rec_off;         // float offset in the weight blob of the pointwise record [W fp16 w_parts x Npad x K16]
   int rec_bytes;       // its size (multiple of 16): one bulk copy per layer
   int bias_off;        // float offset of the pointwise bias [Npad]
   int c1, c2;          // heads: columns [0, c1) -> output o1, [c1, c1 + c2) -> output o2
-  int o1, o2;          // heads: indices into TailP::outs (-1: none)
-  int relu;            // 1: ReLU epilogue
-  int pad_[10];
+  int o1, o2;          // indices into TailP::outs (-1: none); kinds 0 / 2: the layer's result is ALSO written to HBM tensor o1
+  int act;             // 0 none, 1 ReLU, 2 PReLU (slopes at alpha_off)
+  int rbuf;            // residual buffer
+  int w_parts;         // 1: weights exact in fp16; 2: W = hi + lo (fp32-origin weights, a third MMA pass A_hi x W_lo)
+  int tap_off;         // float offset of the depthwise record [taps 9 x K16 | bias K16] (kind 3: the filter [OH*OW*Cin] | bias)
+  int tap_bytes;
+  int alpha_off;       // float offset of the PReLU slopes [Npad]
+  float wscale;        // the stored weights are W * 2^s; the epilogue multiplies the accumulator by wscale = 2^-s
+  int pad_[4];
 };
 static_assert(sizeof(TailLayerD) == 128, "TailLayerD is copied as 16-byte words");
 
 constexpr int kTailMaxLayers = 16;
+constexpr int kTailMaxBufs = 8;
 
 }  // namespace fdt
