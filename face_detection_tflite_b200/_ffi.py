@@ -9,7 +9,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 LIB_PATH = PKG / "libfdt_cuda.so"
 
-FDT_OK, FDT_ERR_NOT_READY, FDT_ERR_BAD_ARG, FDT_ERR_SIZE_MISMATCH, FDT_ERR_MODEL, FDT_ERR_CUDA, FDT_ERR_UNSUPPORTED = range(7)
+FDT_OK, FDT_ERR_NOT_READY, FDT_ERR_BAD_ARG, FDT_ERR_SIZE_MISMATCH, FDT_ERR_MODEL, FDT_ERR_CUDA, FDT_ERR_UNSUPPORTED, FDT_ERR_FORMAT = range(8)
 FDT_MAT_8UC1, FDT_MAT_8UC3, FDT_MAT_8UC4 = 0, 16, 24
 FDT_MEM_HOST, FDT_MEM_DEVICE = 0, 1
 FDT_MAX_FACES = 100
@@ -70,6 +70,11 @@ SIGNATURES = {
     "fdt_profile_net": (C.c_int32, [P, C.c_int32, C.c_int32, C.c_int32, f32p, C.c_int32, i32p]),
     "fdt_get_net_step_info": (C.c_int32, [P, C.c_int32, C.c_int32, C.c_char_p, C.c_char_p, C.c_int32, f64p, f64p]),
     "fdt_num_devices": (C.c_int32, [P]),
+    "fdt_detect_jpeg": (C.c_int32, [P, P, C.c_size_t, C.c_int32, C.POINTER(FdtFace), i32p, f32p, f32p, i32p]),
+    "fdt_decode_jpeg": (C.c_int32, [P, P, C.c_size_t, P, C.c_size_t, i32p]),
+    "fdt_get_decoded_frame": (C.c_int32, [P, P, C.c_size_t]),
+    "fdt_host_jpeg_info": (C.c_int32, [P, C.c_size_t, i32p]),
+    "fdt_host_jpeg_coefficients": (C.c_int32, [P, C.c_size_t, C.c_int32, P, C.c_size_t, i32p, P]),
     "fdt_host_eye_rois": (C.c_int32, [P, P]),
     "fdt_host_embedding_roi": (C.c_int32, [P, P, P]),
     "fdt_last_launch_count": (C.c_int64, [P]),

@@ -21,6 +21,7 @@ COMMON += os.environ.get("FDT_NVCC_FLAGS", "").split()   # tuning experiments, e
 SOURCES = {
     "tflite_model.cpp": [],
     "plan.cpp": [],
+    "jpeg_host.cpp": [],
     "engine.cu": [],
     "fdt_api.cu": [],
     "kernels_naive.cu": [],
@@ -29,6 +30,7 @@ SOURCES = {
     "kernels_tail.cu": [],
     "kernels_ts.cu": [],
     "kernels_fc.cu": [],
+    "kernels_jpeg.cu": [],
     "kernels_pre.cu": [],
     # f64 geometry must be evaluated operation by operation (no fused multiply-add contraction)
     "kernels_post.cu": ["-fmad=false"],

@@ -20,6 +20,7 @@
 
 #include "../../include/fdt_api.h"
 #include "engine.h"
+#include "jpeg_host.h"
 #include "fdt_math.h"
 #include "kernels.h"
 
@@ -145,6 +146,7 @@ struct fdt_handle {
   std::string err;
   long long launches = 0;
   long long h2d_bytes = 0;
+  long long jpeg_launches = 0;
   int last_first_chunk = 0;                  // images of the last call's first chunk (debug taps)
   int last_mesh_faces = 0, last_mesh_slot = 0, last_iris_faces = 0, last_iris_slot = 0;
   bool stage_timing = false;
@@ -152,6 +154,12 @@ struct fdt_handle {
   int stage_launches[kNumStages] = {};
   cudaEvent_t ev[2] = {};
   cudaEvent_t tev[3] = {};
+  // JPEG front end: coefficient / plane / frame buffers, grown on demand
+  int16_t* d_jcoef = nullptr; size_t jcoef_cap = 0;
+  uint8_t* d_jplanes = nullptr; size_t jplanes_cap = 0;
+  uint8_t* d_jframe = nullptr; size_t jframe_cap = 0;
+  uint16_t* d_jq = nullptr;
+  int jw = 0, jh = 0;                        // size of the frame in d_jframe
   bool ready = false;
 };
 
@@ -673,6 +681,72 @@ int create_single(const fdt_config& cfg, const uint8_t* det_tflite, size_t det_l
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
+// ---- JPEG front end -----------------------------------------------------------------------------------------------
+namespace {
+template <typename T> bool grow(fdt_handle* h, T** p, size_t* cap, size_t need) {
+  if (need <= *cap) return true;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *cap = 0;
+  const size_t want = need + need / 4 + 256;
+  if (!cuda_ok(h, cudaMalloc(reinterpret_cast<void**>(p), want * sizeof(T)), "cudaMalloc(jpeg)")) return false;
+  *cap = want;
+  return true;
+}
+
+// decodes into h->d_jframe (packed BGR, EXIF orientation applied); *w / *hh = the oriented size
+int jpeg_to_device(fdt_handle* h, const uint8_t* bytes, size_t nbytes, int* w, int* hh) {
+  if (!bytes || nbytes == 0) return fail(h, FDT_ERR_FORMAT, "empty image buffer");
+  JpegImage img;
+  std::string e;
+  const JpegStatus st = jpeg_decode_coefficients(bytes, nbytes, &img, &e);
+  if (st == kJpegBad) return fail(h, FDT_ERR_FORMAT, e);
+  if (st == kJpegUnsupported) return fail(h, FDT_ERR_UNSUPPORTED, e);
+  cudaSetDevice(h->cfg.device);
+  cudaStream_t s = h->slots[0].stream;
+  size_t ncoef = 0, nplane = 0, coff[3] = {0, 0, 0}, poff[3] = {0, 0, 0};
+  for (int c = 0; c < img.ncomp; ++c) {
+    coff[c] = ncoef; poff[c] = nplane;
+    ncoef += img.comp[c].coef.size();
+    nplane += (size_t)img.comp[c].bw * 8 * img.comp[c].bh * 8;
+  }
+  const bool swap = img.orientation >= 5;
+  const int ow = swap ? img.height : img.width, oh = swap ? img.width : img.height;
+  if (!grow(h, &h->d_jcoef, &h->jcoef_cap, ncoef) || !grow(h, &h->d_jplanes, &h->jplanes_cap, nplane) ||
+      !grow(h, &h->d_jframe, &h->jframe_cap, (size_t)ow * oh * 3)) return FDT_ERR_CUDA;
+  if (!h->d_jq && !cuda_ok(h, cudaMalloc(reinterpret_cast<void**>(&h->d_jq), 3 * 64 * sizeof(uint16_t)), "cudaMalloc(jpeg q)")) return FDT_ERR_CUDA;
+  uint16_t q[3 * 64];
+  for (int c = 0; c < img.ncomp; ++c) std::memcpy(q + 64 * c, img.qt[img.comp[c].tq], 64 * sizeof(uint16_t));
+  // pageable sources: the copies are staged by the driver before the call returns, so the local buffers may go out of scope
+  if (!cuda_ok(h, cudaMemcpyAsync(h->d_jq, q, (size_t)img.ncomp * 64 * sizeof(uint16_t), cudaMemcpyHostToDevice, s), "jpeg q upload")) return FDT_ERR_CUDA;
+  for (int c = 0; c < img.ncomp; ++c)
+    if (!cuda_ok(h, cudaMemcpyAsync(h->d_jcoef + coff[c], img.comp[c].coef.data(), img.comp[c].coef.size() * sizeof(int16_t), cudaMemcpyHostToDevice, s), "jpeg coefficient upload"))
+      return FDT_ERR_CUDA;
+  h->h2d_bytes += (long long)(ncoef * sizeof(int16_t));
+  for (int c = 0; c < img.ncomp; ++c) {
+    JpegIdctP p;
+    p.coef = h->d_jcoef + coff[c]; p.q = h->d_jq + 64 * c; p.bw = img.comp[c].bw; p.bh = img.comp[c].bh;
+    p.plane = h->d_jplanes + poff[c]; p.pitch = img.comp[c].bw * 8;
+    launch_jpeg_idct(p, s);
+  }
+  JpegColorP cp;
+  cp.py = h->d_jplanes + poff[0]; cp.pitch_y = img.comp[0].bw * 8;
+  cp.pcb = cp.pcr = cp.py; cp.pitch_c = cp.pitch_y; cp.cdw = img.comp[0].dw; cp.cdh = img.comp[0].dh; cp.hs = cp.vs = 1;
+  if (img.ncomp == 3) {
+    cp.pcb = h->d_jplanes + poff[1]; cp.pcr = h->d_jplanes + poff[2]; cp.pitch_c = img.comp[1].bw * 8;
+    cp.cdw = img.comp[1].dw; cp.cdh = img.comp[1].dh; cp.hs = img.hmax / img.comp[1].h; cp.vs = img.vmax / img.comp[1].v;
+  }
+  cp.W = img.width; cp.H = img.height; cp.ncomp = img.ncomp; cp.orientation = img.orientation;
+  cp.out = h->d_jframe; cp.out_w = ow;
+  launch_jpeg_color(cp, s);
+  h->jpeg_launches = img.ncomp + 1;
+  if (!cuda_ok(h, cudaStreamSynchronize(s), "jpeg decode")) return FDT_ERR_CUDA;   // the coefficient vectors die with this frame
+  *w = ow; *hh = oh;
+  h->jw = ow; h->jh = oh;
+  return FDT_OK;
+}
+}  // namespace
+
+
 extern "C" {
 
 void fdt_default_config(fdt_config* cfg) {
@@ -866,6 +940,10 @@ int32_t fdt_destroy(fdt_handle* h) {
       if (sl.ev_det) cudaEventDestroy(sl.ev_det);
     }
     for (void* p : h->dev_allocs) cudaFree(p);
+    if (h->d_jcoef) cudaFree(h->d_jcoef);
+    if (h->d_jplanes) cudaFree(h->d_jplanes);
+    if (h->d_jframe) cudaFree(h->d_jframe);
+    if (h->d_jq) cudaFree(h->d_jq);
     for (void* p : h->pin_allocs) cudaFreeHost(p);
     void* dev[] = {h->d_faces, h->d_counts, h->d_anchors};
     for (void* p : dev) if (p) cudaFree(p);
@@ -911,6 +989,79 @@ int32_t fdt_detect_batch_device(fdt_handle* h, const uint8_t* d_frames, int32_t 
     if (d_counts) *d_counts = h->d_counts;
   }
   return rc;
+}
+
+int32_t fdt_decode_jpeg(fdt_handle* h, const uint8_t* bytes, size_t nbytes, uint8_t* out_bgr, size_t out_capacity, int32_t* out_wh) {
+  if (!h) return fail(nullptr, FDT_ERR_NOT_READY, "null handle");
+  std::lock_guard<std::mutex> g(h->mu);
+  fdt_handle* p = primary(h);
+  if (!p->ready) return fail(h, FDT_ERR_NOT_READY, "detector is not initialised");
+  int w = 0, hh = 0;
+  int rc = jpeg_to_device(p, bytes, nbytes, &w, &hh);
+  if (rc != FDT_OK) { if (p != h) h->err = p->err; return rc; }
+  if (out_wh) { out_wh[0] = w; out_wh[1] = hh; }
+  if (out_bgr) {
+    if (out_capacity < (size_t)w * hh * 3) return fail(h, FDT_ERR_SIZE_MISMATCH, "output buffer smaller than width * height * 3");
+    if (!cuda_ok(h, cudaMemcpy(out_bgr, p->d_jframe, (size_t)w * hh * 3, cudaMemcpyDeviceToHost), "jpeg frame download")) return FDT_ERR_CUDA;
+  }
+  return FDT_OK;
+}
+
+int32_t fdt_get_decoded_frame(fdt_handle* h, uint8_t* out_bgr, size_t out_capacity) {
+  if (!h) return fail(nullptr, FDT_ERR_NOT_READY, "null handle");
+  std::lock_guard<std::mutex> g(h->mu);
+  fdt_handle* p = primary(h);
+  if (!p->ready || !p->d_jframe || p->jw <= 0) return fail(h, FDT_ERR_NOT_READY, "no decoded frame");
+  if (!out_bgr || out_capacity < (size_t)p->jw * p->jh * 3) return fail(h, FDT_ERR_SIZE_MISMATCH, "output buffer smaller than width * height * 3");
+  cudaSetDevice(p->cfg.device);
+  if (!cuda_ok(h, cudaMemcpy(out_bgr, p->d_jframe, (size_t)p->jw * p->jh * 3, cudaMemcpyDeviceToHost), "jpeg frame download")) return FDT_ERR_CUDA;
+  return FDT_OK;
+}
+
+int32_t fdt_detect_jpeg(fdt_handle* h, const uint8_t* bytes, size_t nbytes, int32_t mode, fdt_face* out_faces, int32_t* out_count,
+                        float* out_mesh, float* out_iris, int32_t* out_wh) {
+  if (!h) return fail(nullptr, FDT_ERR_NOT_READY, "null handle");
+  std::lock_guard<std::mutex> g(h->mu);
+  fdt_handle* p = primary(h);
+  if (!p->ready) return fail(h, FDT_ERR_NOT_READY, "detector is not initialised");
+  int w = 0, hh = 0;
+  int rc = jpeg_to_device(p, bytes, nbytes, &w, &hh);
+  if (rc == FDT_OK) {
+    if (out_wh) { out_wh[0] = w; out_wh[1] = hh; }
+    const long long jl = p->jpeg_launches;
+    rc = detect_single(p, p->d_jframe, 1, w, hh, w * 3, FDT_MAT_8UC3, mode, FDT_MEM_DEVICE, out_faces, out_count, out_mesh, out_iris, false);
+    p->launches += jl;
+  }
+  if (p != h) { h->err = p->err; h->launches = p->launches; h->h2d_bytes = p->h2d_bytes; }
+  return rc;
+}
+
+int32_t fdt_host_jpeg_info(const uint8_t* bytes, size_t nbytes, int32_t* info8) {
+  JpegImage img;
+  std::string e;
+  const JpegStatus st = jpeg_decode_coefficients(bytes, nbytes, &img, &e);
+  if (st != kJpegOk) { std::lock_guard<std::mutex> g(g_create_mu); g_create_error = e; return st == kJpegBad ? FDT_ERR_FORMAT : FDT_ERR_UNSUPPORTED; }
+  if (info8) {
+    info8[0] = img.width; info8[1] = img.height; info8[2] = img.ncomp; info8[3] = img.progressive ? 1 : 0;
+    info8[4] = img.orientation; info8[5] = img.hmax; info8[6] = img.vmax; info8[7] = 0;
+  }
+  return FDT_OK;
+}
+
+int32_t fdt_host_jpeg_coefficients(const uint8_t* bytes, size_t nbytes, int32_t comp, int16_t* out, size_t capacity, int32_t* dims6, uint16_t* qt64) {
+  JpegImage img;
+  std::string e;
+  const JpegStatus st = jpeg_decode_coefficients(bytes, nbytes, &img, &e);
+  if (st != kJpegOk) { std::lock_guard<std::mutex> g(g_create_mu); g_create_error = e; return st == kJpegBad ? FDT_ERR_FORMAT : FDT_ERR_UNSUPPORTED; }
+  if (comp < 0 || comp >= img.ncomp) return FDT_ERR_BAD_ARG;
+  const JpegComp& c = img.comp[comp];
+  if (dims6) { dims6[0] = c.bw; dims6[1] = c.bh; dims6[2] = c.dw; dims6[3] = c.dh; dims6[4] = c.h; dims6[5] = c.v; }
+  if (qt64) std::memcpy(qt64, img.qt[c.tq], 64 * sizeof(uint16_t));
+  if (out) {
+    if (capacity < c.coef.size()) return FDT_ERR_SIZE_MISMATCH;
+    std::memcpy(out, c.coef.data(), c.coef.size() * sizeof(int16_t));
+  }
+  return FDT_OK;
 }
 
 int32_t fdt_synchronize(fdt_handle* h) {

@@ -3,6 +3,7 @@
 // always written as 0) except for views into graph outputs, which are dense (Cs == C).
 #pragma once
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstdint>
 
 #include "../../include/fdt_api.h"
@@ -213,6 +214,24 @@ struct FcP {
   float wscale;
 };
 bool launch_fc_tc(const FcP& p, int B, cudaStream_t s);
+
+// ---- JPEG front end (kernels_jpeg.cu): coefficients -> component planes -> BGR frame ----
+struct JpegIdctP {
+  const int16_t* coef;      // [bh][bw][64] quantised coefficients, natural order
+  const uint16_t* q;        // [64] quantisation table, natural order
+  int bw, bh;
+  uint8_t* plane; int pitch;   // [bh * 8][pitch = bw * 8]
+};
+struct JpegColorP {
+  const uint8_t* py; const uint8_t* pcb; const uint8_t* pcr;
+  int pitch_y, pitch_c;
+  int W, H, ncomp;
+  int cdw, cdh, hs, vs;     // chroma plane size in samples, subsampling factors (1 or 2)
+  int orientation;          // EXIF 1..8
+  uint8_t* out; int out_w;  // packed BGR, out_w = W (orientations 1-4) or H (5-8)
+};
+void launch_jpeg_idct(const JpegIdctP& p, cudaStream_t s);
+void launch_jpeg_color(const JpegColorP& p, cudaStream_t s);
 
 // ---- detector post-processing: one block per image ----
 struct DecodeP {

@@ -616,7 +616,7 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
       __syncwarp();
       if (lane == 0) {
         mbar_arrive_relaxed(d_empty + 8u * di);
-        if (epi_reads_stage) mbar_arrive_relaxed(empty_in + 8u * si);
+        if (epi_reads_stage) mbar_arrive(empty_in + 8u * si);     // release: the warp's residual loads from the stage precede the producer's refill
       }
       WS_TRACE(0, it, 2);
       if (++si == NS) { si = 0; sph ^= 1; }

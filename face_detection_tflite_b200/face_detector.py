@@ -23,6 +23,10 @@ class StateError(RuntimeError):
     """Dart StateError (not initialised / disposed / double initialise)."""
 
 
+class FormatException(ValueError):
+    """Dart FormatException: the image bytes cannot be decoded (face_detector.dart:476)."""
+
+
 def _raise(lib, handle, code: int):
     msg = lib.fdt_last_error(handle)
     msg = msg.decode() if msg else "error %d" % code
@@ -30,6 +34,8 @@ def _raise(lib, handle, code: int):
         raise StateError(msg)
     if code in (_ffi.FDT_ERR_BAD_ARG, _ffi.FDT_ERR_SIZE_MISMATCH):
         raise ValueError(msg)          # Dart ArgumentError
+    if code == _ffi.FDT_ERR_FORMAT:
+        raise FormatException(msg)
     if code == _ffi.FDT_ERR_UNSUPPORTED:
         raise NotImplementedError(msg)
     raise RuntimeError(msg)
@@ -138,6 +144,42 @@ class FaceDetector:
             _raise(self._lib, self._h, rc)
         return [self._to_face(faces[i], mesh[i] if want_mesh else None, width, height, iris[i] if want_iris else None)
                 for i in range(count.value)]
+
+    def detectFacesFromBytes(self, imageBytes, *, mode: FaceDetectionMode = FaceDetectionMode.full) -> List[Face]:
+        """detectFacesFromBytes (face_detector.dart:477-485): encoded image bytes (JPEG) -> faces.  The reference decodes with
+        cv.imdecode; here the host runs the Huffman decoder and the device does the rest (bit-exact with cv.imdecode, EXIF
+        orientation included).  Raises FormatException when the bytes cannot be decoded, like the reference."""
+        self._check()
+        buf = np.frombuffer(bytes(imageBytes), np.uint8)
+        faces = (_ffi.FdtFace * self._max_faces)()
+        count = C.c_int32(0)
+        mode = FaceDetectionMode(mode)
+        want_mesh = mode != FaceDetectionMode.fast
+        want_iris = mode == FaceDetectionMode.full
+        mesh = np.empty((self._max_faces, 468, 3), np.float32) if want_mesh else None
+        iris = np.empty((self._max_faces, 152, 3), np.float32) if want_iris else None
+        wh = (C.c_int32 * 2)()
+        rc = self._lib.fdt_detect_jpeg(self._h, buf.ctypes.data, buf.size, int(mode), faces, C.byref(count),
+                                       mesh.ctypes.data_as(_ffi.f32p) if want_mesh else None,
+                                       iris.ctypes.data_as(_ffi.f32p) if want_iris else None, wh)
+        if rc != _ffi.FDT_OK:
+            _raise(self._lib, self._h, rc)
+        return [self._to_face(faces[i], mesh[i] if want_mesh else None, wh[0], wh[1], iris[i] if want_iris else None)
+                for i in range(count.value)]
+
+    def decodeImage(self, imageBytes) -> np.ndarray:
+        """The decoder alone (cv.imdecode(bytes, IMREAD_COLOR)): HxWx3 BGR uint8."""
+        self._check()
+        buf = np.frombuffer(bytes(imageBytes), np.uint8)
+        wh = (C.c_int32 * 2)()
+        rc = self._lib.fdt_decode_jpeg(self._h, buf.ctypes.data, buf.size, None, 0, wh)
+        if rc != _ffi.FDT_OK:
+            _raise(self._lib, self._h, rc)
+        out = np.empty((wh[1], wh[0], 3), np.uint8)
+        rc = self._lib.fdt_get_decoded_frame(self._h, out.ctypes.data, out.size)
+        if rc != _ffi.FDT_OK:
+            _raise(self._lib, self._h, rc)
+        return out
 
     def detectFacesFromMat(self, mat: np.ndarray, *, mode: FaceDetectionMode = FaceDetectionMode.full) -> List[Face]:
         """detectFacesFromMat (face_detector.dart:559-572): `mat` is an HxW[xC] uint8 array (cv.Mat)."""

@@ -37,7 +37,8 @@ typedef struct fdt_handle fdt_handle;
  *   FDT_ERR_BAD_ARG       <- ArgumentError (gates outside [0,1], lib/src/shared/face_gates.dart:31-59)
  *   FDT_ERR_SIZE_MISMATCH <- ArgumentError (byte length mismatch, lib/src/util/helpers.dart:440-447)
  *   FDT_ERR_MODEL         <- model buffer rejected (Interpreter.fromBuffer failure)
- *   FDT_ERR_CUDA          <- device / driver failure (no reference equivalent)                    */
+ *   FDT_ERR_CUDA          <- device / driver failure (no reference equivalent)
+ *   FDT_ERR_FORMAT        <- FormatException (undecodable image bytes, lib/src/face_detector.dart:476)     */
 typedef enum fdt_status {
   FDT_OK = 0,
   FDT_ERR_NOT_READY = 1,
@@ -45,7 +46,8 @@ typedef enum fdt_status {
   FDT_ERR_SIZE_MISMATCH = 3,
   FDT_ERR_MODEL = 4,
   FDT_ERR_CUDA = 5,
-  FDT_ERR_UNSUPPORTED = 6
+  FDT_ERR_UNSUPPORTED = 6,
+  FDT_ERR_FORMAT = 7
 } fdt_status;
 
 /* FaceDetectionModel (lib/src/shared/face_types.dart:100-115) -> SSD anchor option set
@@ -263,6 +265,23 @@ FDT_EXPORT int32_t fdt_get_net_step_info(fdt_handle* h, int32_t which, int32_t s
 FDT_EXPORT int32_t fdt_extract_aligned_squares(fdt_handle* h, const uint8_t* frame, int32_t width, int32_t height,
                                                int32_t row_stride, int32_t mat_type, const double* rois, int32_t n,
                                                int32_t out_size, uint8_t* out_crops, int32_t* out_ok);
+/* ---- JPEG front end: detectFacesFromBytes (lib/src/face_detector.dart:477-485; the reference decodes with cv.imdecode
+ * and throws FormatException when the bytes cannot be decoded, :472-476) ------------------------------------------
+ * The host parses the markers and runs the Huffman decoder (baseline and progressive, 8-bit, grey or YCbCr with 1x / 2x
+ * chroma subsampling, restart intervals); dequantisation, the integer IDCT, fancy chroma upsampling, colour conversion
+ * and the EXIF orientation run on the device and equal cv2.imdecode (libjpeg-turbo) byte for byte.
+ * FDT_ERR_FORMAT: the bytes are not a decodable JPEG (FormatException); FDT_ERR_UNSUPPORTED: arithmetic coding, 12-bit,
+ * CMYK, lossless.
+ * fdt_detect_jpeg : decode + detect in `mode`; out_wh[2] (optional) receives the decoded width, height.
+ * fdt_decode_jpeg : decode only; out_bgr (optional, host, packed BGR, capacity in bytes) receives the frame.
+ * fdt_get_decoded_frame : copies the frame the last fdt_decode_jpeg / fdt_detect_jpeg left on the device (so a caller can
+ *                   size its buffer from out_wh first without decoding twice). */
+FDT_EXPORT int32_t fdt_detect_jpeg(fdt_handle* h, const uint8_t* bytes, size_t nbytes, int32_t mode, fdt_face* out_faces,
+                                   int32_t* out_count, float* out_mesh, float* out_iris, int32_t* out_wh);
+FDT_EXPORT int32_t fdt_decode_jpeg(fdt_handle* h, const uint8_t* bytes, size_t nbytes, uint8_t* out_bgr, size_t out_capacity,
+                                   int32_t* out_wh);
+FDT_EXPORT int32_t fdt_get_decoded_frame(fdt_handle* h, uint8_t* out_bgr, size_t out_capacity);
+
 /* Number of CUDA devices the handle spans (1 unless created with a device list). */
 FDT_EXPORT int32_t fdt_num_devices(fdt_handle* h);
 
@@ -293,6 +312,13 @@ FDT_EXPORT int32_t fdt_host_face_roi(const double* kp12, double img_w, double im
                                      double* out10);
 FDT_EXPORT int32_t fdt_host_eye_rois(const double* corners8, double* out8);
 FDT_EXPORT int32_t fdt_host_embedding_roi(const double* left_eye_xy, const double* right_eye_xy, double* out4);
+/* Host half of the JPEG front end, for tests and bindings: info8 = width, height, components, progressive, EXIF
+ * orientation, hmax, vmax, 0.  fdt_host_jpeg_coefficients copies component `comp`'s quantised coefficients
+ * ([blocks_h][blocks_w][64] int16, natural order, MCU-padded) and its quantisation table (natural order); dims6 =
+ * blocks_w, blocks_h, samples_w, samples_h, h sampling factor, v sampling factor.  `out` may be NULL to query the sizes. */
+FDT_EXPORT int32_t fdt_host_jpeg_info(const uint8_t* bytes, size_t nbytes, int32_t* info8);
+FDT_EXPORT int32_t fdt_host_jpeg_coefficients(const uint8_t* bytes, size_t nbytes, int32_t comp, int16_t* out,
+                                              size_t capacity, int32_t* dims6, uint16_t* qt64);
 
 FDT_EXPORT const char* fdt_last_error(fdt_handle* h); /* NULL handle -> last create error */
 FDT_EXPORT const char* fdt_version(void);
