@@ -145,6 +145,36 @@ class FdtFaceDetector {
     }
   }
 
+  /// detectFacesFromBytes (face_detector.dart:477-485): encoded image bytes (JPEG) -> faces; same default mode (full).
+  /// The reference decodes with cv.imdecode on the host; here the host only runs the Huffman decoder, the IDCT, chroma
+  /// upsampling, colour conversion and EXIF orientation run on the GPU (byte-equal to cv.imdecode).  Throws
+  /// [FormatException] when the bytes cannot be decoded, like the reference.
+  Future<List<Face>> detectFacesFromBytes(
+    Uint8List imageBytes, {
+    FaceDetectionMode mode = FaceDetectionMode.full,
+  }) async {
+    _check();
+    final arena = Arena();
+    try {
+      final Pointer<Uint8> src = arena<Uint8>(imageBytes.length);
+      src.asTypedList(imageBytes.length).setAll(0, imageBytes);
+      final Pointer<FdtFace> faces = arena<FdtFace>(_maxFaces);
+      final Pointer<Int32> count = arena<Int32>();
+      final Pointer<Int32> wh = arena<Int32>(2);
+      final bool wantMesh = mode != FaceDetectionMode.fast;
+      final bool wantIris = mode == FaceDetectionMode.full;
+      final Pointer<Float> mesh = wantMesh ? arena<Float>(_maxFaces * kFdtMeshFloats) : nullptr;
+      final Pointer<Float> iris = wantIris ? arena<Float>(_maxFaces * kFdtIrisFloats) : nullptr;
+      final int rc = _lib.detectJpeg(_h, src, imageBytes.length, mode.index, faces, count, mesh, iris, wh);
+      if (rc != FdtStatus.ok) {
+        _lib.throwFor(rc, _h); // FormatException for undecodable bytes
+      }
+      return <Face>[for (int i = 0; i < count.value; i++) _toFace(faces[i], mesh, iris, i, wh[0], wh[1])];
+    } finally {
+      arena.releaseAll();
+    }
+  }
+
   /// New batched entry point: [frames] holds [count] packed frames (count * height * width * channels bytes).
   /// One `fdt_detect_batch` call; results come back in frame order.  For sustained throughput keep the frames in a
   /// buffer from `fdt_alloc_pinned` (see [FdtPinnedFrames]) so the upload runs at PCIe speed.

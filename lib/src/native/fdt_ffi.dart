@@ -21,6 +21,7 @@ abstract final class FdtStatus {
   static const int model = 4;
   static const int cuda = 5;
   static const int unsupported = 6;
+  static const int format = 7; // FormatException (undecodable image bytes, face_detector.dart:476)
 }
 
 const int kFdtMaxFaces = 100; // weightedNms maxDet (helpers.dart:187)
@@ -106,6 +107,10 @@ typedef _ExtractSquaresD = int Function(Pointer<Void>, Pointer<Uint8>, int, int,
     Pointer<Uint8>, Pointer<Int32>);
 typedef _EmbeddingRoiC = Int32 Function(Pointer<Double>, Pointer<Double>, Pointer<Double>);
 typedef _EmbeddingRoiD = int Function(Pointer<Double>, Pointer<Double>, Pointer<Double>);
+typedef _DetectJpegC = Int32 Function(Pointer<Void>, Pointer<Uint8>, Size, Int32, Pointer<FdtFace>, Pointer<Int32>,
+    Pointer<Float>, Pointer<Float>, Pointer<Int32>);
+typedef _DetectJpegD = int Function(Pointer<Void>, Pointer<Uint8>, int, int, Pointer<FdtFace>, Pointer<Int32>,
+    Pointer<Float>, Pointer<Float>, Pointer<Int32>);
 typedef _NumDevicesC = Int32 Function(Pointer<Void>);
 typedef _NumDevicesD = int Function(Pointer<Void>);
 
@@ -123,6 +128,7 @@ class FdtLibrary {
         getInfo = _lib.lookupFunction<_GetInfoC, _GetInfoD>('fdt_get_info'),
         extractAlignedSquares = _lib.lookupFunction<_ExtractSquaresC, _ExtractSquaresD>('fdt_extract_aligned_squares'),
         hostEmbeddingRoi = _lib.lookupFunction<_EmbeddingRoiC, _EmbeddingRoiD>('fdt_host_embedding_roi'),
+        detectJpeg = _lib.lookupFunction<_DetectJpegC, _DetectJpegD>('fdt_detect_jpeg'),
         numDevices = _lib.lookupFunction<_NumDevicesC, _NumDevicesD>('fdt_num_devices');
 
   final DynamicLibrary _lib;
@@ -137,6 +143,7 @@ class FdtLibrary {
   final _GetInfoD getInfo;
   final _ExtractSquaresD extractAlignedSquares;
   final _EmbeddingRoiD hostEmbeddingRoi;
+  final _DetectJpegD detectJpeg;
   final _NumDevicesD numDevices;
 
   static FdtLibrary? _instance;
@@ -159,6 +166,8 @@ class FdtLibrary {
       case FdtStatus.badArg:
       case FdtStatus.sizeMismatch:
         throw ArgumentError(msg); // face_gates.dart:31-59, helpers.dart:440-447
+      case FdtStatus.format:
+        throw FormatException(msg); // undecodable image bytes, face_detector.dart:476
       case FdtStatus.unsupported:
         throw UnsupportedError(msg);
       default:
