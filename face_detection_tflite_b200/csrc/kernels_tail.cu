@@ -38,7 +38,11 @@
 namespace fdt {
 namespace {
 
-constexpr int kTC = 12;                       // compute warps
+#ifndef FDT_TAIL_WARPS
+#define FDT_TAIL_WARPS 12                      // measured: 16 warps (96 registers, spills) run the detector tail 9 % slower
+#endif
+constexpr int kTC = FDT_TAIL_WARPS;           // compute warps (a multiple of 4: one group of kTG warps per TMEM lane quarter)
+constexpr int kTG = kTC / 4;
 constexpr int kTComputeThreads = kTC * 32;
 constexpr int kTThreads = (kTC + 1) * 32;
 // TMEM columns: accumulators of tile 0 / 1 at 0 / 128 (Npad <= 128); operand of tile 0 / 1 at 256 / 384: hi halves at +0,
@@ -235,7 +239,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_tail_ws(const __grid_constant_
             const bool ok = act && (unsigned)iy < (unsigned)L.IH && (unsigned)ix < (unsigned)L.IW;
             off[k] = ok ? src_a + (uint32_t)(iy * L.IW + ix) * kss_b : zero_a;
           }
-          for (int q = g; q < nq; q += 3) {
+          for (int q = g; q < nq; q += kTG) {
             if (!half_done && q >= nq_half) {
               half_done = true;
               asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -279,7 +283,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_tail_ws(const __grid_constant_
         } else {
           const uint32_t px0 = act ? src_a + (uint32_t)pix0 * kss_b : zero_a;
           const uint32_t px1 = px0 + (uint32_t)L.OW * kss_b;
-          for (int q = g; q < nq; q += 3) {
+          for (int q = g; q < nq; q += kTG) {
             if (!half_done && q >= nq_half) {
               half_done = true;
               asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -322,7 +326,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_tail_ws(const __grid_constant_
               o1_q = p.out_pix[L.o1] >> 2;
               if (L.o2 >= 0) o2 = p.outs[L.o2] + (size_t)img * p.out_istride[L.o2] + (size_t)(act ? pix : 0) * p.out_pix[L.o2];
             }
-            for (int c16 = g; c16 < (L.Npad >> 4); c16 += 3) {
+            for (int c16 = g; c16 < (L.Npad >> 4); c16 += kTG) {
               uint32_t u[16];
               asm volatile(
                   "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
