@@ -9,6 +9,7 @@ namespace fdt {
 Engine::~Engine() {
   if (d_blob_) cudaFree(d_blob_);
   for (TailLayerD* p : d_tail_) if (p) cudaFree(p);
+  for (TailBlk* p : d_blks_) if (p) cudaFree(p);
 }
 
 bool Engine::init(const uint8_t* tflite, size_t len, int fuse_level, std::string* err, bool use_tc) {
@@ -22,12 +23,19 @@ bool Engine::init(const uint8_t* tflite, size_t len, int fuse_level, std::string
     return false;
   }
   d_tail_.assign(plan_.steps.size(), nullptr);
+  d_blks_.assign(plan_.steps.size(), nullptr);
   for (size_t i = 0; i < plan_.steps.size(); ++i) {
     const PStep& st = plan_.steps[i];
     if (st.kind != kStepTailWs) continue;
     if (cudaMalloc(&d_tail_[i], st.tail.size() * sizeof(TailLayerD)) != cudaSuccess ||
         cudaMemcpy(d_tail_[i], st.tail.data(), st.tail.size() * sizeof(TailLayerD), cudaMemcpyHostToDevice) != cudaSuccess) {
       *err = "tail program upload failed";
+      return false;
+    }
+    if (st.tail_blks.empty()) continue;
+    if (cudaMalloc(&d_blks_[i], st.tail_blks.size() * sizeof(TailBlk)) != cudaSuccess ||
+        cudaMemcpy(d_blks_[i], st.tail_blks.data(), st.tail_blks.size() * sizeof(TailBlk), cudaMemcpyHostToDevice) != cudaSuccess) {
+      *err = "chain block table upload failed";
       return false;
     }
   }
@@ -228,6 +236,16 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         p.generic = 0;
         for (const TailLayerD& L : st.tail)
           if (L.kind >= 2 || L.act == 2 || L.w_parts != 1 || L.wscale != 1.f || L.rbuf != L.src || (L.kind != 1 && L.o1 >= 0)) p.generic = 1;
+        p.blks = nullptr; p.nblks = 0; p.bias_floats = 0; p.in_px = iv.H * iv.W;
+        for (int k = 0; k < 2; ++k) { p.rsrc[k] = nullptr; p.rs_istride[k] = 0; p.rs_cs[k] = p.rs_w[k] = p.rs_c[k] = 0; }
+        if (st.tail_wide) {
+          p.generic = 2;
+          p.blks = d_blks_[&st - plan_.steps.data()]; p.nblks = (int)st.tail_blks.size(); p.bias_floats = st.tail_bias_floats;
+          for (size_t k = 0; k < st.tail_rsrc.size() && k < 2; ++k) {
+            TV rv = view(ctx, st.tail_rsrc[k]);
+            p.rsrc[k] = rv.p; p.rs_istride[k] = rv.istride; p.rs_cs[k] = rv.Cs; p.rs_w[k] = rv.W; p.rs_c[k] = rv.C;
+          }
+        }
         p.last_a_layer = st.tail_last_a; p.wbuf_bytes = st.tail_wbuf; p.wdepth = st.tail_wdepth; p.tbuf_bytes = st.tail_tbuf; p.smem_bytes = st.smem;
         for (int k = 0; k < 4; ++k) { p.outs[k] = nullptr; p.out_istride[k] = 0; p.out_pix[k] = 0; }
         for (size_t k = 0; k < st.tail_outs.size(); ++k) {

@@ -42,6 +42,7 @@ class Engine {
   Plan plan_;
   float* d_blob_ = nullptr;
   std::vector<TailLayerD*> d_tail_;     // per plan step: device copy of a k_tail_ws layer program (or null)
+  std::vector<TailBlk*> d_blks_;        // per plan step: device copy of a k_chain_wide W block table (or null)
   int max_ctas_ = 148 * 4;
   mutable bool failed_ = false;
 };

@@ -197,11 +197,15 @@ struct TailP {
   int last_a_layer;             // last layer that touches buffer 0 (the next image's input is fetched after it)
   int wbuf_bytes, wdepth;       // pointwise-weight ring: wdepth (1 or 2) buffers of wbuf_bytes
   int tbuf_bytes;               // depthwise-record ring (always two deep)
-  int generic;                  // 1: the program needs the GEN = true kernel (see kernels_tail.cu)
+  int generic;                  // 1: the program needs the GEN = true kernel (see kernels_tail.cu); 2: k_chain_wide
+  // k_chain_wide only: W block table (device), shared-memory bias area, residual tensors read from HBM
+  const TailBlk* blks; int nblks; int bias_floats; int in_px;
+  const float* rsrc[2]; long long rs_istride[2]; int rs_cs[2], rs_w[2], rs_c[2];
   float* outs[4]; long long out_istride[4]; int out_pix[4];   // HBM tensors the layers write: image 0, floats per image / per pixel
   size_t smem_bytes;
 };
 size_t tail_smem_bytes(int act_floats, int wbuf_bytes, int wdepth, int tbuf_bytes);
+size_t wide_smem_bytes(int act_floats, int wbuf_bytes, int wdepth, int tbuf_bytes, int bias_floats);
 bool launch_tail_ws(const TailP& p, int B, int cap, cudaStream_t s);
 
 // ---- k_fc_tc (kernels_fc.cu): whole-map convolution = one dense contraction per image, tcgen05 GEMM over the chunk ----

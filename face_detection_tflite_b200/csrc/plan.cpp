@@ -927,7 +927,7 @@ struct Builder {
       t->tail_buf_off[b] = off; t->tail_buf_ks[b] = ks; t->tail_buf_px[b] = buf_px[b];
       off += buf_px[b] * ks;
     }
-    if (t->tail_buf_ks[0] > 256) return false;                // TMA box limit
+    if (t->tail_buf_ks[0] > 256 && !t->tail_wide) return false;                // TMA box limit (k_chain_wide copies pixel by pixel)
     t->tail_act_floats = off;
     t->tail_in_bytes = buf_px[0] * t->tail_buf_ks[0] * 4;
     size_t wbuf = 0, tbuf = 0;
@@ -940,8 +940,25 @@ struct Builder {
       if (L.src == 0 || L.dst == 0 || (L.res && L.rbuf == 0)) last0 = (int)li;
     }
     t->tail_last_a = last0;
-    t->tail_wbuf = (int)((wbuf + 127) / 128 * 128);
     t->tail_tbuf = (int)((tbuf + 127) / 128 * 128);
+    if (t->tail_wide) {
+      // k_chain_wide: ring of W blocks (as deep as fits, at least the blocks one K chunk needs at once), bias area by offset
+      int need = 2;
+      for (const TailLayerD& L : t->tail) need = std::max(need, L.ng >> 8);
+      for (const TailBlk& b : t->tail_blks) wbuf = std::max(wbuf, (size_t)b.bytes);
+      t->tail_wbuf = (int)((wbuf + 127) / 128 * 128);
+      if (t->tail_blks.size() > (size_t)kTailMaxBlks) return false;
+      auto wbytes = [&](int depth) {      // = wide_smem_bytes() in kernels_tail.cu
+        return (size_t)kTailMaxLayers * sizeof(TailLayerD) + (size_t)kTailMaxBlks * sizeof(TailBlk) + 2 * (size_t)t->tail_bias_floats * 4 + 32 * 8 + 16 * 4 + 128 +
+               ((size_t)off + 512) * 4 + 128 + 2 * (size_t)t->tail_tbuf + (size_t)depth * t->tail_wbuf;
+      };
+      int depth = 4;
+      while (depth > need && wbytes(depth) > (size_t)225 * 1024) --depth;
+      t->tail_wdepth = depth;
+      t->smem = wbytes(depth);
+      return t->smem <= (size_t)225 * 1024;
+    }
+    t->tail_wbuf = (int)((wbuf + 127) / 128 * 128);
     auto bytes = [&](int depth) {       // = tail_smem_bytes() in kernels_tail.cu
       return (size_t)kTailMaxLayers * sizeof(TailLayerD) + 2 * (size_t)kTailMaxLayers * 512 + 16 * 8 + 16 * 4 + 128 +
              ((size_t)off + 128) * 4 + 128 + 2 * (size_t)t->tail_tbuf + (size_t)depth * t->tail_wbuf;
@@ -959,6 +976,7 @@ struct Builder {
       P.tensors[s.out].materialized = true;
       if (s.out2 >= 0) P.tensors[s.out2].materialized = true;
       for (int e : s.extra_out) { P.tensors[e].materialized = true; use((int)i, e); }
+      for (int e : s.tail_rsrc) use((int)i, e);
       if (!s.in_u8) use((int)i, s.in);
       use((int)i, s.in2);
       use((int)i, s.out);
@@ -1102,39 +1120,68 @@ struct Builder {
   // inside the chain, plus whole-map convolutions with one filter (a dot product), assigns shared-memory buffers by
   // liveness (in place where the source dies) and emits ONE k_tail_ws step.  Tensors that are read outside the chain are
   // also written to HBM by the layer that produces them.  A chain that would end in 1x1 heads is left to fuse_tail().
-  int chain_emit_at = -1;
-  PStep chain_step;
+  struct ChainOut { int emit_at; PStep step; };
+  std::vector<ChainOut> chains;
   void fuse_chain() {
     static const int want = [] { const char* e = std::getenv("FDT_CHAIN"); return e ? std::atoi(e) : 1; }();   // FDT_CHAIN=0: A/B, one launch per layer
     if (!want) return;
-    for (size_t s0 = 0; s0 < m.ops.size() && chain_emit_at < 0; ++s0)
-      if (m.ops[s0].code == kOpConv2D && !done[s0]) try_chain((int)s0);
+    bool narrow_done = false;                // one narrow chain per graph (the face-landmark trunk), any number of wide ones
+    for (size_t s0 = 0; s0 < m.ops.size(); ++s0)
+      if (m.ops[s0].code == kOpConv2D && !done[s0]) try_chain((int)s0, &narrow_done);
   }
 
   struct ChainLayer { int conv; PwMatch M; int kind; int out_tf; };
 
-  void try_chain(int s0) {
+  // one W block of k_chain_wide: rows [n0, n0 + ncols) x K range [k0, k0 + kw) of W [N][K] (zero outside), fp16 K-major core matrices,
+  // parts == 2: the lo image follows the hi image; `scale` as in pack_w_f16
+  std::vector<float> pack_w_block(const std::vector<float>& w, int N, int K, int n0, int ncols, int k0, int kw, int parts, float scale) {
+    const size_t SBO16 = (size_t)(kw / 8) * 128;
+    std::vector<uint16_t> img((size_t)parts * ncols * kw, 0);
+    for (int n = 0; n < ncols && n0 + n < N; ++n)
+      for (int k = 0; k < kw && k0 + k < K; ++k) {
+        const float v = w[(size_t)(n0 + n) * K + k0 + k] * scale;
+        const size_t o = ((size_t)(n >> 3) * SBO16 + (size_t)(k >> 3) * 128 + (size_t)(n & 7) * 16 + (size_t)(k & 7) * 2) / 2;
+        const uint16_t hb = f32_to_f16(v);
+        img[o] = hb;
+        if (parts == 2) img[(size_t)ncols * kw + o] = f32_to_f16(v - f16_to_f32(hb));
+      }
+    std::vector<float> rec((img.size() + 1) / 2, 0.f);
+    std::memcpy(rec.data(), img.data(), img.size() * 2);
+    return rec;
+  }
+
+  void try_chain(int s0, bool* narrow_done) {
     PwMatch M0;
-    if (!match_pointwise(s0, &M0, true) || !M0.has_dw) return;
+    if (!match_pointwise(s0, &M0, true)) return;
     const int T0 = M0.src;
+    // a layer no per-layer tensor-core kernel takes (more than 128 channels on either side) opens a WIDE chain (k_chain_wide):
+    // up to 384 channels, residuals from HBM tensors, any number of layers down to one
+    const bool wide = m.tensors[T0].shape.size() == 4 && (m.tensors[T0].dim(3) > 128 || m.tensors[m.ops[s0].in[1]].shape[0] > 128);
+    if (!wide && (!M0.has_dw || *narrow_done)) return;
+    const int cmax = wide ? 384 : 128;
     {
       const TfTensor& t0 = m.tensors[T0];
-      if (is_view(T0) || t0.shape.size() != 4 || t0.dim(1) * t0.dim(2) > 256 || t0.dim(3) > 128 || m.producer(T0) < 0) return;
+      if (is_view(T0) || t0.shape.size() != 4 || t0.dim(1) * t0.dim(2) > 256 || t0.dim(3) > cmax || m.producer(T0) < 0) return;
     }
-    std::vector<char> absorbed(m.ops.size(), 0);
+    const int first_op = M0.has_dw ? M0.absorbed[0] : s0;
     std::vector<int> chainT{T0};
     auto in_chain = [&](int t) { return std::find(chainT.begin(), chainT.end(), t) != chainT.end(); };
+    // a residual read from HBM: a plain NHWC tensor produced before the chain starts
+    auto hbm_res_ok = [&](int t) {
+      const int pr = m.producer(t);
+      return wide && !is_view(t) && m.tensors[t].shape.size() == 4 && pr >= 0 && pr < first_op && m.tensors[t].dim(3) <= cmax;
+    };
     std::vector<ChainLayer> layers;
     // pass A1: the convolutions, in graph order
     for (size_t j = s0; j < m.ops.size(); ++j) {
       const TfOp& op = m.ops[j];
       if (op.code != kOpConv2D || done[j]) continue;
       PwMatch M;
-      if (match_pointwise((int)j, &M, true) && in_chain(M.src) && (M.res < 0 || in_chain(M.res))) {
+      if (match_pointwise((int)j, &M, true) && in_chain(M.src) && (M.res < 0 || in_chain(M.res) || hbm_res_ok(M.res))) {
         const TfTensor& it = m.tensors[M.src];
         const TfTensor& ot = m.tensors[M.cur];
         const int Cout = m.tensors[op.in[1]].shape[0];
-        bool ok = it.shape.size() == 4 && ot.shape.size() == 4 && !is_view(M.cur) && it.dim(3) <= 128 && Cout <= 128;
+        bool ok = it.shape.size() == 4 && ot.shape.size() == 4 && !is_view(M.cur) && it.dim(3) <= cmax && Cout <= cmax;
         const int npix = ok ? ot.dim(1) * ot.dim(2) : 0;
         ok = ok && (npix <= 128 || (npix <= 256 && ot.dim(1) % 2 == 0 && (!M.has_dw || M.dws == 1)));
         if (ok && M.has_dw) {
@@ -1147,8 +1194,6 @@ struct Builder {
         }
         if (ok) {
           layers.push_back({(int)j, M, M.has_dw ? 0 : 2, M.cur});
-          absorbed[j] = 1;
-          for (int a : M.absorbed) absorbed[a] = 1;
           chainT.push_back(M.cur);
           continue;
         }
@@ -1162,11 +1207,48 @@ struct Builder {
           PwMatch M;
           M.src = op.in[0]; M.cur = op.out[0];
           layers.push_back({(int)j, M, 3, op.out[0]});
-          absorbed[j] = 1;
         }
       }
     }
-    if (layers.size() < 3 || layers.size() > (size_t)kTailMaxLayers) return;
+    if (layers.size() > (size_t)kTailMaxLayers) {
+      if (!wide) return;
+      layers.resize(kTailMaxLayers);
+    }
+    if (!wide) {
+      if (layers.size() >= 3 && build_chain(T0, layers, false)) *narrow_done = true;
+      return;
+    }
+    // wide: the longest prefix (in graph order) whose buffers and weight ring fit one CTA
+    for (size_t n = layers.size(); n >= 1; --n) {
+      std::vector<ChainLayer> pre(layers.begin(), layers.begin() + n);
+      // every layer of the prefix must read tensors of the prefix
+      std::vector<int> have{T0};
+      bool closed = true;
+      for (const ChainLayer& cl : pre) {
+        closed = closed && std::find(have.begin(), have.end(), cl.M.src) != have.end();
+        if (cl.M.res >= 0 && std::find(have.begin(), have.end(), cl.M.res) == have.end()) closed = closed && hbm_res_ok(cl.M.res) && !in_chain(cl.M.res);
+        have.push_back(cl.out_tf);
+      }
+      if (closed && build_chain(T0, pre, true)) return;
+    }
+  }
+
+  bool build_chain(int T0, const std::vector<ChainLayer>& layers, bool wide) {
+    const size_t blob_mark = P.blob.size();
+    if (build_chain_inner(T0, layers, wide)) return true;
+    P.blob.resize(blob_mark);                         // a failed attempt leaves no records behind
+    return false;
+  }
+
+  bool build_chain_inner(int T0, const std::vector<ChainLayer>& layers, bool wide) {
+    std::vector<char> absorbed(m.ops.size(), 0);
+    std::vector<int> chainT{T0};
+    for (const ChainLayer& cl : layers) {
+      absorbed[cl.conv] = 1;
+      for (int a : cl.M.absorbed) absorbed[a] = 1;
+      if (cl.kind != 3) chainT.push_back(cl.out_tf);
+    }
+    auto in_chain = [&](int t) { return std::find(chainT.begin(), chainT.end(), t) != chainT.end(); };
     // pass A2: chain tensors read outside the chain (or graph outputs) are exits
     std::vector<int> exits;
     for (size_t j = 0; j < m.ops.size(); ++j) {
@@ -1174,14 +1256,14 @@ struct Builder {
       for (int i : m.ops[j].in) {
         if (i < 0 || i == T0 || !in_chain(i)) continue;
         const TfOp& op = m.ops[j];
-        if (op.code == kOpConv2D) {               // a 1x1 head on a chain tensor: that tail belongs to fuse_tail()
+        if (op.code == kOpConv2D && !wide) {               // a 1x1 head on a chain tensor: that tail belongs to fuse_tail()
           const TfTensor& wt = m.tensors[op.in[1]];
-          if (wt.shape.size() == 4 && wt.shape[1] == 1 && wt.shape[2] == 1) return;
+          if (wt.shape.size() == 4 && wt.shape[1] == 1 && wt.shape[2] == 1) return false;
         }
         if (std::find(exits.begin(), exits.end(), i) == exits.end()) exits.push_back(i);
       }
     }
-    for (int o : m.outputs) if (in_chain(o) && o != T0) return;
+    for (int o : m.outputs) if (in_chain(o) && o != T0) return false;
     // pass B: buffers by liveness
     const int NL = (int)layers.size();
     std::map<int, int> last_read;                     // tensor -> last layer that reads it
@@ -1197,6 +1279,8 @@ struct Builder {
     buf_free_after.push_back(last_read[T0]);
     PStep t;
     t.kind = kStepTailWs;
+    t.tail_wide = wide ? 1 : 0;
+    int bias_s = 0;
     for (int i = 0; i < NL; ++i) {
       const ChainLayer& cl = layers[i];
       const TfOp& conv = m.ops[cl.conv];
@@ -1205,18 +1289,22 @@ struct Builder {
       TailLayerD L = {};
       L.kind = cl.kind;
       L.src = buf_of[cl.M.src];
-      L.rbuf = cl.M.res >= 0 ? buf_of[cl.M.res] : L.src;
+      const bool res_hbm = cl.M.res >= 0 && !in_chain(cl.M.res);
+      L.rbuf = cl.M.res >= 0 && !res_hbm ? buf_of[cl.M.res] : L.src;
       L.o1 = L.o2 = -1;
       L.wscale = 1.f; L.w_parts = 1; L.dst = -1;
+      L.nk = 1; L.ng = 1 | (1 << 8);
       L.IH = it.dim(1); L.IW = it.dim(2);
       L.Cin = it.dim(3);
       std::vector<float> w, b;
-      if (!m.const_f32(conv.in[1], &w)) return;
-      if (conv.in.size() > 2 && conv.in[2] >= 0 && !m.const_f32(conv.in[2], &b)) return;
+      if (!m.const_f32(conv.in[1], &w)) return false;
+      if (conv.in.size() > 2 && conv.in[2] >= 0 && !m.const_f32(conv.in[2], &b)) return false;
       if (cl.kind == 3) {
         L.OH = L.IH; L.OW = L.IW; L.Cout = 1; L.K16 = 16; L.Npad = 4;
         b.resize(4, 0.f);
         L.bias_off = (int)push(b, 4);
+        L.bias_s = wide ? bias_s : i * 128;
+        bias_s += 4;
         const size_t n = ru((int)w.size(), 4);
         L.tap_bytes = (int)(n * 4);
         L.tap_off = (int)push(w, n);
@@ -1230,43 +1318,101 @@ struct Builder {
       L.K16 = ru(L.Cin, 16); L.Npad = ru(L.Cout, 16);
       L.stride = cl.M.dws; L.pad = cl.M.dpt;
       L.res = cl.M.res >= 0 ? (cl.M.pool ? 2 : 1) : 0;
-      L.act = cl.M.act;
-      // destination: in place when the source dies here and keeps its pixel count, else a free buffer of that size, else a new one
-      const int npix = L.OH * L.OW;
-      const int sb = L.src;
-      if (buf_px[sb] == npix && last_read[cl.M.src] == i && (sb != 0 || true)) {
-        L.dst = sb;
-      } else {
-        for (size_t k = 1; k < buf_px.size() && L.dst < 0; ++k)
-          if (buf_px[k] == npix && buf_free_after[k] < i && (int)k != L.rbuf) L.dst = (int)k;
-        if (L.dst < 0) { L.dst = (int)buf_px.size(); buf_px.push_back(npix); buf_c.push_back(4); buf_free_after.push_back(-1); }
+      if (cl.M.res >= 0) L.c1 = ru(m.tensors[cl.M.res].dim(3), 4);          // kinds 0 / 2: channels of the residual tensor (k_chain_wide)
+      if (res_hbm) {
+        const int rp = pt(cl.M.res);
+        if (P.tensors[rp].Cs % 4 != 0 || P.tensors[rp].root >= 0) return false;
+        size_t k = std::find(t.tail_rsrc.begin(), t.tail_rsrc.end(), rp) - t.tail_rsrc.begin();
+        if (k == t.tail_rsrc.size()) t.tail_rsrc.push_back(rp);
+        if (t.tail_rsrc.size() > 2) return false;
+        L.res += 2;                                   // 3: same pixel, 4: 2x2 max-pool, of the HBM tensor rsrc[rbuf]
+        L.rbuf = (int)k;
       }
-      if (L.dst >= kTailMaxBufs) return;
-      buf_of[cl.out_tf] = L.dst;
-      buf_c[L.dst] = std::max(buf_c[L.dst], ru(L.Cout, 4));
-      buf_free_after[L.dst] = last_read.count(cl.out_tf) ? last_read[cl.out_tf] : i;
-      if (std::find(exits.begin(), exits.end(), cl.out_tf) != exits.end()) {
+      L.act = cl.M.act;
+      const int npix = L.OH * L.OW;
+      const bool paired = npix > 128;
+      const int ngroups = paired ? (L.Npad + 127) / 128 : 1;
+      if (!wide && (L.K16 > 128 || L.Npad > 128)) return false;
+      // destination: none when nothing in the chain reads the result (it only leaves to HBM); in place on the residual or the
+      // source when that dies here and keeps its pixel count (never the source when the layer runs as several column groups:
+      // the later groups still read it; never buffer 0 of a wide chain: its loader rewrites only the input's channels), else a
+      // free buffer of that size, else a new one
+      const int sb = L.src;
+      const bool is_exit = std::find(exits.begin(), exits.end(), cl.out_tf) != exits.end();
+      const bool read_inside = last_read.count(cl.out_tf) > 0;
+      if (!read_inside && !is_exit) return false;
+      if (read_inside || !wide) {
+        const int rb = (cl.M.res >= 0 && !res_hbm && L.res == 1) ? L.rbuf : -1;
+        if (wide && rb > 0 && buf_px[rb] == npix && last_read[cl.M.res] == i) {
+          L.dst = rb;
+        } else if (buf_px[sb] == npix && last_read[cl.M.src] == i && !(wide && sb == 0) && ngroups == 1) {
+          L.dst = sb;
+        } else {
+          for (size_t k = 1; k < buf_px.size() && L.dst < 0; ++k)
+            if (buf_px[k] == npix && buf_free_after[k] < i && (int)k != L.rbuf && (int)k != sb) L.dst = (int)k;
+          if (L.dst < 0) { L.dst = (int)buf_px.size(); buf_px.push_back(npix); buf_c.push_back(4); buf_free_after.push_back(-1); }
+        }
+        if (L.dst >= kTailMaxBufs) return false;
+        buf_of[cl.out_tf] = L.dst;
+        buf_c[L.dst] = std::max(buf_c[L.dst], ru(L.Cout, 4));
+        buf_free_after[L.dst] = last_read.count(cl.out_tf) ? last_read[cl.out_tf] : i;
+      }
+      if (is_exit) {
         L.o1 = (int)t.tail_outs.size(); t.tail_outs.push_back(pt(cl.out_tf));
       }
-      if (t.tail_outs.size() > 4) return;
+      if (t.tail_outs.size() > 4) return false;
       // weights
       b.resize(L.Cout, 0.f);
       L.w_parts = f16_exact(w) ? 1 : 2;
-      std::vector<float> rec = pack_w_f16(w, L.Cout, L.Cin, L.Npad, L.K16, L.w_parts, &L.wscale);
-      L.rec_bytes = (int)(rec.size() * 4);
-      L.rec_off = (int)push(rec, rec.size());
+      if (!wide) {
+        std::vector<float> rec = pack_w_f16(w, L.Cout, L.Cin, L.Npad, L.K16, L.w_parts, &L.wscale);
+        L.rec_bytes = (int)(rec.size() * 4);
+        L.rec_off = (int)push(rec, rec.size());
+        L.bias_s = i * 128;
+      } else {
+        float scale = 1.f;
+        if (L.w_parts == 2) {
+          float mx = 0.f;
+          for (float v : w) mx = std::max(mx, std::fabs(v));
+          if (mx > 0.f) { int e; std::frexp(mx, &e); scale = std::ldexp(1.f, 14 - e); }
+        }
+        L.wscale = 1.f / scale;
+        L.nk = (L.K16 + 127) / 128;
+        const int nblocks_n = (L.Npad + 127) / 128;               // column blocks of <= 128, balanced, multiples of 16
+        const int bw = ru((L.Npad / 16 + nblocks_n - 1) / nblocks_n * 16, 16);
+        const int nbg = paired ? 1 : nblocks_n;
+        if (!paired && L.Npad > 384) return false;
+        L.ng = (paired ? nblocks_n : 1) | (nbg << 8);
+        L.blk0 = (int)t.tail_blks.size();
+        for (int grp = 0; grp < (paired ? nblocks_n : 1); ++grp)
+          for (int kc = 0; kc < L.nk; ++kc)
+            for (int nb = 0; nb < nbg; ++nb) {
+              const int bi = paired ? grp : nb;
+              const int n0 = bi * bw, ncols = std::min(bw, L.Npad - n0);
+              const int k0 = kc * 128, kw = std::min(128, L.K16 - k0);
+              std::vector<float> rec = pack_w_block(w, L.Cout, L.Cin, n0, ncols, k0, kw, L.w_parts, scale);
+              TailBlk bk;
+              bk.bytes = (int)(rec.size() * 4);
+              bk.off = (int)push(rec, rec.size());
+              bk.n0 = n0; bk.ncols = ncols;
+              if (bk.bytes % 16 || ncols < 16 || ncols % 16) return false;
+              t.tail_blks.push_back(bk);
+            }
+        L.bias_s = bias_s;
+        bias_s += L.Npad;
+      }
       std::vector<float> bias((size_t)L.Npad, 0.f);
       for (int n = 0; n < L.Cout; ++n) bias[n] = b[n];
       L.bias_off = (int)push(bias, bias.size());
       if (cl.M.alpha_tf >= 0) {
         std::vector<float> al;
-        if (!m.const_f32(cl.M.alpha_tf, &al) || (int)al.size() != L.Cout) return;
+        if (!m.const_f32(cl.M.alpha_tf, &al) || (int)al.size() != L.Cout) return false;
         L.alpha_off = (int)push(al, (size_t)L.Npad);
       }
       if (cl.kind == 0) {
         const TfOp& dw = m.ops[cl.M.absorbed[0]];
         std::vector<float> dwv, dbv;
-        if (!m.const_f32(dw.in[1], &dwv) || !m.const_f32(dw.in[2], &dbv)) return;
+        if (!m.const_f32(dw.in[1], &dwv) || !m.const_f32(dw.in[2], &dbv)) return false;
         std::vector<float> rec2((size_t)10 * L.K16, 0.f);
         for (int k = 0; k < 9; ++k)
           for (int c = 0; c < L.Cin; ++c) rec2[(size_t)k * L.K16 + c] = dwv[(size_t)k * L.Cin + c];
@@ -1277,7 +1423,8 @@ struct Builder {
       t.macs += (double)npix * ((double)L.Cin * L.Cout + (cl.kind == 0 ? 9.0 * L.Cin : 0.0));
       t.tail.push_back(L);
     }
-    if (t.tail_outs.empty() || !finish_tail(&t, buf_px, buf_c)) return;
+    t.tail_bias_floats = wide ? ru(bias_s, 4) + 4 : kTailMaxLayers * 128;
+    if (t.tail_outs.empty() || !finish_tail(&t, buf_px, buf_c)) return false;
     t.in = pt(T0);
     t.out = t.tail_outs[0];
     for (size_t k = 1; k < t.tail_outs.size(); ++k) t.extra_out.push_back(t.tail_outs[k]);
@@ -1287,8 +1434,8 @@ struct Builder {
     for (size_t j = 0; j < m.ops.size(); ++j)
       if (absorbed[j]) { done[j] = 1; first = std::min(first, (int)j); }
     for (int e : exits) fused_outputs.push_back(e);
-    chain_emit_at = first;
-    chain_step = t;
+    chains.push_back({first, t});
+    return true;
   }
 
   // ---- emission ---------------------------------------------------------------------------------
@@ -1363,11 +1510,16 @@ struct Builder {
     // pass 2: emission in graph order
     for (size_t i = 0; i < no; ++i) {
       const TfOp& op = m.ops[i];
-      if ((int)i == chain_emit_at) {
-        PStep s = chain_step;
+      for (const ChainOut& co : chains) {
+        if ((int)i != co.emit_at) continue;
+        PStep s = co.step;
         if (!P.tensors[s.in].materialized) return fail("internal: the chain's input is not materialised");
         int idx = (int)P.steps.size();
         for (int e : s.extra_out) { P.tensors[e].materialized = true; use(idx, e); }
+        for (int e : s.tail_rsrc) {
+          if (!P.tensors[e].materialized) return fail("internal: a chain residual is not materialised");
+          use(idx, e);
+        }
         if (!emit(s)) return false;
       }
       auto fit = fused.find((int)i);
@@ -1539,12 +1691,22 @@ std::string Plan::describe() const {
              st.res_pool ? "(pool)" : "", st.res_mode, o.tf, o.H, o.W, o.C, o.Cs, o.root >= 0 ? "view" : "arena", st.act,
              (int)st.has_dw, st.dws, st.K, st.NC, st.nchunks, st.TM, st.NPG, st.TH, st.TW, st.G, st.RS, st.nd, st.ns, st.na, st.no, st.smem, st.name.c_str());
     s += buf;
+    if (st.tail_wide) {
+      snprintf(buf, sizeof buf, "      k_chain_wide: %zu W blocks (ring %d x %d B), act %d floats, %zu HBM residual tensor(s)\n", st.tail_blks.size(), st.tail_wdepth, st.tail_wbuf,
+               st.tail_act_floats, st.tail_rsrc.size());
+      s += buf;
+    }
     for (size_t l = 0; l < st.tail.size(); ++l) {
       const TailLayerD& L = st.tail[l];
       static const char* lk[] = {"block", "heads", "pw", "dot"};
       snprintf(buf, sizeof buf, "      tail %2zu %s buf %d->%d %dx%d->%dx%d s%d C %d->%d K16=%d Npad=%d res=%d(buf %d) act=%d wparts=%d out=%d rec=%dB taps=%dB\n", l, lk[L.kind & 3],
                L.src, L.dst, L.IH, L.IW, L.OH, L.OW, L.stride, L.Cin, L.Cout, L.K16, L.Npad, L.res, L.rbuf, L.act, L.w_parts, L.o1, L.rec_bytes, L.tap_bytes);
       s += buf;
+      if (st.tail_wide && L.kind != 3) {
+        s.pop_back();
+        snprintf(buf, sizeof buf, " wide: groups=%d blocks/group=%d Kchunks=%d blk0=%d\n", L.ng & 0xff, L.ng >> 8, L.nk, L.blk0);
+        s += buf;
+      }
     }
   }
   snprintf(buf, sizeof buf, "steps=%zu  MACs/image=%.3fM  arena/image=%.1f KB  weights=%.1f KB\n", steps.size(),

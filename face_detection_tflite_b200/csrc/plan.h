@@ -54,6 +54,10 @@ struct PStep {
   std::vector<TailLayerD> tail;
   std::vector<int> tail_outs;   // PTensor ids the heads write, indexed by TailLayerD::o1 / o2
   int tail_nbuf = 0, tail_buf_off[kTailMaxBufs] = {0}, tail_buf_ks[kTailMaxBufs] = {0}, tail_buf_px[kTailMaxBufs] = {0};   // shared-memory activation buffers
+  // k_chain_wide (layers wider than 128 channels): W block table, HBM residual tensors, shared-memory bias area
+  std::vector<TailBlk> tail_blks;
+  std::vector<int> tail_rsrc;
+  int tail_wide = 0, tail_bias_floats = 0;
   int tail_act_floats = 0, tail_in_bytes = 0, tail_last_a = 0, tail_wbuf = 0, tail_wdepth = 2, tail_tbuf = 0;
   double macs = 0;  // per image
 };

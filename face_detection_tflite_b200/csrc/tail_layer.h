@@ -13,7 +13,8 @@ struct TailLayerD {
   int stride, pad;     // depthwise stride, SAME pad-before
   int IH, IW, OH, OW;  // input / output spatial size
   int Cin, Cout, K16, Npad;
-  int res;             // 0 none, 1 the same pixel of buffer rbuf, 2 2x2 max-pool of buffer rbuf (zero channel pad in both)
+  int res;             // 0 none, 1 the same pixel of buffer rbuf, 2 2x2 max-pool of buffer rbuf (zero channel pad in both);
+                       // k_chain_wide only: 3 the same pixel / 4 2x2 max-pool of the HBM tensor TailP::rsrc[rbuf]
   int rec_off;         // float offset in the weight blob of the pointwise record [W fp16 w_parts x Npad x K16]
   int rec_bytes;       // its size (multiple of 16): one bulk copy per layer
   int bias_off;        // float offset of the pointwise bias [Npad]
@@ -26,11 +27,25 @@ struct TailLayerD {
   int tap_bytes;
   int alpha_off;       // float offset of the PReLU slopes [Npad]
   float wscale;        // the stored weights are W * 2^s; the epilogue multiplies the accumulator by wscale = 2^-s
-  int pad_[4];
+  // k_chain_wide (layers wider than 128 channels): the pointwise product runs as ng column groups x nk K chunks (<= 128 each);
+  // W arrives as blocks [<= 128 columns][<= 128 K] in consumption order (group, K chunk, block of the group)
+  int blk0;            // index of the layer's first block in the chain's block table
+  int nk;              // K chunks
+  int ng;              // column groups | blocks per group << 8  (two-tile maps: groups of one block; one-tile maps: one group of <= 3 blocks)
+  int bias_s;          // float offset of the layer's bias / slopes inside the kernel's shared-memory copies
 };
 static_assert(sizeof(TailLayerD) == 128, "TailLayerD is copied as 16-byte words");
 
+// one W block of k_chain_wide: [w_parts][ncols][kw] fp16 in UMMA K-major core matrices, kw = min(128, K16 - 128 * chunk)
+struct TailBlk {
+  int off;             // float offset in the weight blob
+  int bytes;           // multiple of 16: one bulk copy
+  int n0, ncols;       // accumulator columns [n0, n0 + ncols) of the layer
+};
+static_assert(sizeof(TailBlk) == 16, "TailBlk is copied as 16-byte words");
+
 constexpr int kTailMaxLayers = 16;
+constexpr int kTailMaxBlks = 128;
 constexpr int kTailMaxBufs = 8;
 
 }  // namespace fdt
