@@ -320,6 +320,31 @@ def main():
                         "results leave compacted (counts + the first 4 slots per frame, more on demand)" if not standard else
                         "; whole frames are uploaded (the crop-warp gathers from the full-resolution frame)")}
         lib.fdt_free_pinned(pin)
+        # PCIe ceiling next to it: plain cudaMemcpyAsync of one contiguous pinned buffer, all ranks at the same time (what the
+        # host can feed N GPUs at once).  The e2e step uploads h2d bytes per step; achieved / ceiling says how close it runs to the link.
+        try:
+            nb = 512 << 20
+            hp = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+            dp = torch.empty(nb, dtype=torch.uint8, device="cuda")
+            dp.copy_(hp, non_blocking=True)
+            barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(4):
+                dp.copy_(hp, non_blocking=True)
+            ev1.record()
+            torch.cuda.synchronize()
+            ceil_gbs = 4 * nb / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+            tot = torch.tensor([ceil_gbs], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tot)
+            ach = h2d * e_steps / (e_ms / 1e3) / 1e9 * world          # every rank uploads its own shard
+            e2e["pcie"] = {"h2d_ceiling_gbs_this_gpu": ceil_gbs, "h2d_ceiling_gbs_all_ranks": float(tot.item()),
+                           "h2d_achieved_gbs_all_ranks": ach, "frac_of_ceiling": ach / float(tot.item()),
+                           "how": "cudaMemcpyAsync of one contiguous 512 MiB pinned buffer x 4, CUDA events, every rank at the same time"}
+            del hp, dp
+        except Exception as ex:                      # the measurement is informative only
+            e2e["pcie"] = {"error": str(ex)[:200]}
 
     clocks = sampler.stop()
     clocks["window"] = "warm-up + timed steps + e2e steps"

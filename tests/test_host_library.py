@@ -166,6 +166,31 @@ def test_warp_specialised_plans_respect_the_hardware_limits(lib, model_bytes, mo
     assert n_ws >= 8, "the conv stack should run on the warp-specialised kernels"
 
 
+def test_detectors_and_mesh_run_on_tensor_core_kernels_only(lib, model_bytes):
+    """no CUDA-core convolution step (dwpw / gemm_conv / naive_conv) is left in the production plans of the
+    detectors and the face-landmark net; the full-range layers wider than 128 channels (12x12x144..256, 6x6x384) run as
+    k_chain_wide programs whose W blocks respect the kernel's limits."""
+    buf = C.create_string_buffer(1 << 17)
+    for model in ("shortRange", "full", "backCamera", "mesh"):
+        d = model_bytes[model]
+        assert lib.fdt_host_plan_describe(d, len(d), 1, buf, len(buf)) == 0, buf.value
+        text = buf.value.decode()
+        kinds = re.findall(r"^\s*\d+ (\w+)\s+in=", text, re.M)
+        assert kinds and not set(kinds) & {"dwpw", "gemm_conv", "naive_conv", "maxpool", "add", "act", "padc", "stem"}, (model, sorted(set(kinds)))
+    d = model_bytes["full"]
+    assert lib.fdt_host_plan_describe(d, len(d), 1, buf, len(buf)) == 0
+    text = buf.value.decode()
+    wide = re.findall(r"k_chain_wide: (\d+) W blocks \(ring (\d+) x (\d+) B\), act (\d+) floats, (\d+) HBM", text)
+    assert len(wide) == 5                                                   # [18..21] [22] [23] [24..31] [32]
+    for nblk, depth, wbuf, act, nres in wide:
+        assert int(nblk) <= 128 and 2 <= int(depth) <= 4 and int(wbuf) <= 32768 and int(nres) <= 2
+    layers = re.findall(r"C (\d+)->(\d+) K16=(\d+) Npad=(\d+) .* wide: groups=(\d+) blocks/group=(\d+) Kchunks=(\d+)", text)
+    assert len(layers) == 15
+    for cin, cout, k16, npad, ng, nbg, nk in (tuple(int(x) for x in l) for l in layers):
+        assert nk == (k16 + 127) // 128 and ng * nbg == (npad + 127) // 128 and nbg <= 3
+        assert max(cin, cout) > 128                                           # only layers no per-layer tensor-core kernel takes
+
+
 def test_malformed_models_are_rejected_not_crashed(model_bytes):
     """The model bytes reach the flatbuffer reader through the public API (fdt_create / FaceDetector.create
     detectorBytes): truncated and bit-flipped buffers must come back as FDT_ERR_MODEL (or parse), never crash.
