@@ -11,6 +11,11 @@ __device__ __forceinline__ void load_bgr(const uint8_t* px, int channels, int* v
   else { v[0] = px[0]; v[1] = px[1]; v[2] = px[2]; }
 }
 
+// One thread per output pixel: four 3-byte taps (byte loads; neighbouring threads share the sectors through L1) and one uchar4
+// store.  Measured alternative (round 2): a row-staged kernel - one warp per output row, the two source rows fetched with
+// coalesced 16-byte streaming loads into shared memory, taps read from there - ran 17-33 % SLOWER on B200 (148 vs 126 us per
+// 1024 1280x720 frames, 97 vs 73 us per 256 1920x1080 frames): the DRAM traffic is the same (every sector of the 2-in-10 source
+// rows either way) and the staging adds a shared-memory round trip to a kernel that already sits at 65 % of peak DRAM throughput.
 __global__ void k_letterbox(LetterboxP p, int B) {
   const int npx = p.dst_w * p.dst_h;
   const long long total = (long long)B * npx;
