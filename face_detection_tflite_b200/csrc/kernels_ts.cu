@@ -94,14 +94,17 @@ __device__ __forceinline__ uint32_t col_a(int slot, int t) { return 256u + (uint
 // Shared-memory carve-up (must match ts_smem_bytes): [W fp16 Npad x K16 | dww 9 x K16 | dwb K16] [bias Npad] [barriers 32 x 8 B]
 //   | 128-byte aligned: [input ring ns x stage_bytes]
 // S = depthwise stride.  S == 1: output tile 16 x 16 (M-tiles = even / odd rows), staged 18 x 18.  S == 2: output tile 8 x 16
-// (one M-tile), staged 17 x 33.
+// (one M-tile), staged 17 rows x 33 columns as TWO planes of 17 x 17 pixels - the even and the odd input columns, each fetched by
+// its own TMA with an element stride of 2 along x.  Neighbouring lanes (output columns x, x + 1) then read pixels that are ONE
+// record apart (KS = an odd number of 16-byte quads: conflict-free LDS.128) instead of two records apart (every load 2-way
+// bank-conflicted: ncu counted 12.7 M conflict cycles per 1024 frames on short-range block 3).
 template <int S>
 __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant__ CUtensorMap tmap, BlockTsP p, int B) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint32_t tmem_base_s;
   constexpr int NT = S == 1 ? 2 : 1;                         // M-tiles per output tile
   constexpr int TH = S == 1 ? 16 : 8, TW = 16;
-  constexpr int IW = S == 1 ? 18 : 33;                       // staged row length (pixels)
+  constexpr int IW = S == 1 ? 18 : 17;                       // staged row length (pixels; S == 2: of one column-parity plane)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float* sRec = reinterpret_cast<float*>(smem_raw);
   float* sBias = sRec + (p.rec_bytes >> 2);
@@ -134,6 +137,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
   const uint32_t tmem_base = tmem_base_s;
   const uint32_t ring_a = smem_u32(ring), ks_b = (uint32_t)p.KS * 4u, row_b = (uint32_t)IW * ks_b;
   const uint32_t stage_b = (uint32_t)p.stage_bytes;
+  const uint32_t plane_b = (17u * 17u * ks_b + 127u) & ~127u;   // S == 2: the odd-column plane follows the even-column plane (TMA destinations are 128-byte aligned)
+  // S == 2: byte offset of window column kx = 0, 1, 2 (input columns 2x, 2x + 1, 2x + 2)
+  const uint32_t col2_b[3] = {0u, plane_b, ks_b};
 
   if (warp < kC) {
     // =============================== compute warps ==============================================================
@@ -142,8 +148,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
     const int yy = L >> 4, x = L & 15;                       // S == 1: row pair / column of the 16 x 16 tile; S == 2: row / column of the 8 x 16 tile
     const uint32_t tm_lane = tmem_base + ((uint32_t)(lq * 32) << 16);
     // top-left of this thread's input window inside a stage: S == 1 rows 2yy .. 2yy + 3, cols x .. x + 2 (halo included);
-    // S == 2 rows 2yy .. 2yy + 2, cols 2x .. 2x + 2
-    const uint32_t win = (uint32_t)((2 * yy) * IW + (S == 1 ? x : 2 * x)) * ks_b;
+    // S == 2 rows 2yy .. 2yy + 2, cols 2x .. 2x + 2 = entries x (even plane), x (odd plane), x + 1 (even plane)
+    const uint32_t win = (uint32_t)((2 * yy) * IW + x) * ks_b;
     const int nq = p.K16 >> 2, nq_real = (p.Cin + 3) >> 2, ks_q = p.KS >> 2;
     const uint32_t rec_a = smem_u32(sRec), dww_a = rec_a + (uint32_t)(p.Npad * p.K16) * 2u, dwb_a = dww_a + 9u * (uint32_t)p.K16 * 4u;
     const uint32_t k16_b = (uint32_t)p.K16 * 4u, bias_a = smem_u32(sBias);
@@ -178,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
             if (p.res == 1) {
               if (cq < ks_q) rv[j] = lds4(res_a + qo);
             } else if (p.res == 2) {
-              if (cq < ks_q) rv[j] = max4(max4(lds4(res_a + qo), lds4(res_a + ks_b + qo)), max4(lds4(res_a + row_b + qo), lds4(res_a + row_b + ks_b + qo)));
+              if (cq < ks_q) rv[j] = max4(max4(lds4(res_a + qo), lds4(res_a + plane_b + qo)), max4(lds4(res_a + row_b + qo), lds4(res_a + row_b + plane_b + qo)));
             }
           }
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -242,7 +248,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
           } else {
             a0 = bias;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) fma4(a0, lds4(pa + (uint32_t)(k / 3) * row_b + (uint32_t)(k % 3) * ks_b), w[k]);
+            for (int k = 0; k < 9; ++k) fma4(a0, lds4(pa + (uint32_t)(k / 3) * row_b + col2_b[k % 3]), w[k]);
           }
         }
         split_store_tmem(acol0 + 2u * (uint32_t)q, 32u, a0);
@@ -264,10 +270,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
         const int b = tile / tpi, trem = tile - b * tpi, ty = trem / tiles_x, tx = trem - ty * tiles_x;
         if (i >= NS) mbar_wait(in_empty + 8u * (uint32_t)stage, (uint32_t)(((i / NS) - 1) & 1));
         const uint32_t bar = in_full + 8u * (uint32_t)stage;
-        mbar_expect_tx(bar, (uint32_t)((S == 1 ? 18 * 18 : 17 * 33) * p.KS) * 4u);
+        mbar_expect_tx(bar, (uint32_t)((S == 1 ? 18 * 18 : 2 * 17 * 17) * p.KS) * 4u);
         const int ix0 = S == 1 ? tx * TW - 1 : tx * TW * 2, iy0 = S == 1 ? ty * TH - 1 : ty * TH * 2;
         asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
                      ::"r"(ring_a + (uint32_t)stage * stage_b), "l"(&tmap), "r"(0), "r"(ix0), "r"(iy0), "r"(b), "r"(bar) : "memory");
+        if (S == 2)        // the odd input columns (the map walks x with an element stride of 2)
+          asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                       ::"r"(ring_a + (uint32_t)stage * stage_b + plane_b), "l"(&tmap), "r"(0), "r"(ix0 + 1), "r"(iy0), "r"(b), "r"(bar) : "memory");
       }
     }
     __syncwarp();
@@ -335,7 +344,7 @@ bool ts_tensor_map(const BlockTsP& p, int cap, CUtensorMap* out) {
   cuuint64_t gdim[4] = {(cuuint64_t)p.CinS, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)cap};
   cuuint64_t gstr[3] = {(cuuint64_t)p.CinS * 4, (cuuint64_t)p.W * p.CinS * 4, (cuuint64_t)p.in_istride * 4};
   cuuint32_t box[4] = {(cuuint32_t)p.KS, p.stride == 1 ? 18u : 33u, p.stride == 1 ? 18u : 17u, 1u};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t estr[4] = {1, p.stride == 1 ? 1u : 2u, 1, 1};     // stride 2: every other column (33 traversed -> 17 delivered)
   CUtensorMap tm;
   CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.in), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

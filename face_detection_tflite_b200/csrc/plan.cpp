@@ -440,9 +440,10 @@ struct Builder {
   void plan_ts(PStep* st, const TfTensor& in, int OH, int OW, bool prelu) {
     static const int want = [] { const char* e = std::getenv("FDT_TS"); return e ? std::atoi(e) : 1; }();      // FDT_TS=0: A/B against k_block_ws
     if (!want || !st->has_dw || st->c2 > 0 || st->w_parts != 1 || prelu) return;
-    // up to 24 channels k_block_ws keeps a thread's depthwise taps in registers for the whole kernel (one work item per
-    // thread) and measures faster (0.136 vs 0.147 ms per 512 frames on the 64x64x24 block); from 28 channels on this kernel wins
-    if (in.dim(3) < 28 && want < 2) return;
+    // Below 28 input channels the choice follows the output record (measured per 1024 frames, 64x64x24 input): 24 output channels
+    // (32-byte aligned 96-byte records, 256-bit stores) 227 us here vs 257 us on k_block_ws; 28 output channels (112-byte records,
+    // float4 stores) 296 vs 273 us.  From 28 input channels on this kernel always wins.
+    if (in.dim(3) < 28 && ru(st->Cout, 4) % 8 != 0 && want < 2) return;
     if (st->act != kActRelu && st->act != kActNone) return;
     const int Cin = in.dim(3), K16 = ru(Cin, 16), Npad = ru(st->Cout, 16);
     if (K16 > 64 || Npad > 64) return;
@@ -473,8 +474,8 @@ struct Builder {
     std::vector<float> bias((size_t)Npad, 0.f);
     for (int n = 0; n < st->Cout; ++n) bias[n] = P.blob[(size_t)st->bias + n];
     const int KS = odd_quads(ru(Cin, 4));
-    const int px = st->dws == 1 ? 18 * 18 : 17 * 33;
-    const int stage_bytes = (px * KS * 4 + 127) / 128 * 128;
+    // stride 2: the even- and the odd-column plane of 17 x 17 pixels, each 128-byte aligned (one TMA each)
+    const int stage_bytes = st->dws == 1 ? (18 * 18 * KS * 4 + 127) / 128 * 128 : 2 * ((17 * 17 * KS * 4 + 127) / 128 * 128);
     const size_t head = rec.size() * 4 + (size_t)Npad * 4 + 32 * 8 + 256;
     int ns = (int)(((size_t)220 * 1024 - head) / stage_bytes);
     if (ns < 2) return;
