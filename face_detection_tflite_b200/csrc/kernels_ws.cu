@@ -151,15 +151,17 @@ __device__ __forceinline__ float4 leaky4(const float4& a, const float4& al) {
 // up to three output rows it feeds, so only the accumulators stay live (no 3-row window in registers).  Each output
 // still sums bias, then taps (ky, kx) in row-major order - the same order as the per-output form.
 template <int S, int RS>
-__device__ __forceinline__ void dw_item(uint32_t base, uint32_t row_b, uint32_t ks_b, const float4 (&w)[9], const float4& bias,
+__device__ __forceinline__ void dw_item(uint32_t base, uint32_t row_b, uint32_t c1_b, uint32_t c2_b, const float4 (&w)[9], const float4& bias,
                                         float* sAhi, float* sAlo, uint32_t sl, uint32_t aq, uint32_t SBO, uint32_t TW) {
+  // c1_b / c2_b: byte offsets of window columns 1 and 2 (one and two records, or - stride 2 with the even / odd input columns
+  // staged as two planes - the odd plane and one record)
   constexpr int NR = S == 1 ? RS + 2 : 2 * RS + 1;     // staged rows this item reads
   float4 acc[3];                                        // acc[t % 3] = output row t
 #pragma unroll
   for (int r = 0; r < NR; ++r) {
     float4 v[3];
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) v[kx] = lds4(base + (uint32_t)r * row_b + kx * ks_b);
+    for (int kx = 0; kx < 3; ++kx) v[kx] = lds4(base + (uint32_t)r * row_b + (kx == 0 ? 0u : (kx == 1 ? c1_b : c2_b)));
     if (S == 1) {
       if (r >= 2) {                                     // ky = 2 of output r-2: complete
         float4& a = acc[(r - 2) % 3];
@@ -310,8 +312,7 @@ __device__ __forceinline__ void epi_fast(uint32_t tcol0, uint32_t res_a, uint32_
 // Loads of an 8-column group (bias, slopes, residual) are issued before tcgen05.wait::ld so they overlap the TMEM read.
 template <int RES, int LEAKY>
 __device__ __forceinline__ void epi_tile(const DwPwTcP& p, uint32_t tcol0, uint32_t res_a, uint32_t bias_a, uint32_t alpha_a,
-                                         float* orow, bool valid, const float* rbase, int oy, int ox) {
-  const uint32_t ks_b = (uint32_t)p.KS * 4u, row_b = (uint32_t)p.IW * ks_b;
+                                         float* orow, bool valid, const float* rbase, int oy, int ox, uint32_t ks_b, uint32_t row_b) {
   for (int c0 = 0; c0 < p.Npad; c0 += 8) {
     uint32_t u[8];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -421,6 +422,12 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
   const uint32_t full_in = bar0, empty_in = bar0 + 8u * 6, a_full = bar0 + 8u * 12, a_empty = bar0 + 8u * 16,
                  d_full = bar0 + 8u * 20, d_empty = bar0 + 8u * 24;
   const int NT = p.nt;
+  // stride 2 with the even / odd input columns staged as two planes [G][IH][PW][KS] (plan_ws: deint): neighbouring output
+  // columns read neighbouring records (conflict-free LDS.128); one TMA per plane, the map walks x with an element stride of 2
+  const bool deint = S == 2 && p.deint != 0;
+  const uint32_t plane_b = (uint32_t)p.plane_floats * 4u;
+  const int RW = deint ? p.PW : p.IW;                 // staged row length in records
+  const uint32_t tma_bytes = deint ? 2u * (uint32_t)(p.G * p.IH * p.PW * p.KS) * 4u : (uint32_t)(p.G * p.IH * p.IW * p.KS) * 4u;
   const int thw = p.TH * p.TW;
   const int nslots = p.G * thw;
   const bool epi_reads_stage = p.res_mode == 1;
@@ -449,17 +456,21 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     if (p.no > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_out) : "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");          // (PDL) the input is the previous kernel's output
-    const uint32_t stage_bytes = (uint32_t)(p.G * p.IH * p.IW * p.KS) * 4u;
     for (int tile = blockIdx.x; tile < ntiles && early < NS; tile += gridDim.x, ++early) {
       int grp, trem, tyi, txi;
       p.fd_tpg.divmod(tile, grp, trem);
       p.fd_tilesX.divmod(trem, tyi, txi);
       const uint32_t bar = full_in + 8u * early;
-      mbar_expect_tx(bar, stage_bytes);
+      mbar_expect_tx(bar, tma_bytes);
       asm volatile(
           "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
           ::"r"(smem_u32(sIn0 + (size_t)early * in_stage_floats)), "l"(&tmap), "r"(0), "r"(txi * p.TW * p.s - p.dpl),
             "r"(tyi * p.TH * p.s - p.dpt), "r"(grp * p.G), "r"(bar) : "memory");
+      if (deint)
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+            ::"r"(smem_u32(sIn0 + (size_t)early * in_stage_floats) + plane_b), "l"(&tmap), "r"(0), "r"(txi * p.TW * p.s + 1),
+              "r"(tyi * p.TH * p.s), "r"(grp * p.G), "r"(bar) : "memory");
     }
   }
   // all threads: weights, bias, slopes, depthwise taps (cp.async), depthwise table
@@ -481,7 +492,8 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
       p.fd_nstrips.divmod(r, r2, st);
       p.fd_Q8.divmod(r2, g, qq);
       const int tyb = st * RS;
-      uint32_t in_off = (uint32_t)(((g * p.IH + tyb * S) * p.IW + tx * S) * p.KS + 4 * qq);
+      uint32_t in_off = deint ? (uint32_t)(((g * p.IH + tyb * 2) * p.PW + tx) * p.KS + 4 * qq)
+                              : (uint32_t)(((g * p.IH + tyb * S) * p.IW + tx * S) * p.KS + 4 * qq);
       uint32_t slot0 = (uint32_t)(g * thw + tyb * p.TW + tx);
       dtab[it] = (in_off >> 2) | (slot0 << 14) | ((uint32_t)qq << 22);
     }
@@ -526,10 +538,12 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
     const long long o_rel2 = slot_ok ? (long long)e_g * p.out2_istride + ((long long)e_ty * p.OW + e_tx) * p.Cs2 : 0;
     const int cout_loop = p.c2 > 0 ? p.c1 + ((p.c2 + 3) & ~3) : p.CoutS, c1 = p.c2 > 0 ? p.c1 : (1 << 30);
     const int rs = p.res_pool ? 2 : 1;
-    const uint32_t res_off = slot_ok ? (uint32_t)((((size_t)e_g * p.IH + e_ty * rs + p.dpt) * p.IW + e_tx * rs + p.dpl) * p.KS) : 0u;
+    const uint32_t res_off = !slot_ok ? 0u : deint ? (uint32_t)((((size_t)e_g * p.IH + e_ty * 2) * p.PW + e_tx) * p.KS)
+                                                   : (uint32_t)((((size_t)e_g * p.IH + e_ty * rs + p.dpt) * p.IW + e_tx * rs + p.dpl) * p.KS);
     const uint32_t sIn0_a = smem_u32(sIn0), bias_a = smem_u32(sBias), alpha_a = smem_u32(sAlpha);
     int ob = 0, oph = 0;
-    const uint32_t ks_b = (uint32_t)p.KS * 4u, row_b = (uint32_t)p.IW * ks_b;
+    // byte distance of the residual's right / lower neighbour in the stage (pooled residuals only read them)
+    const uint32_t ks_b = deint ? plane_b : (uint32_t)p.KS * 4u, row_b = (uint32_t)RW * (uint32_t)p.KS * 4u;
     int si = 0, sph = 0, di = 0, dph = 0;
     long long* tr = (p.trace && blockIdx.x == 0 && tid == 0) ? p.trace : nullptr;
     int it = 0;
@@ -607,10 +621,10 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
           }
         }
       } else {
-        if (res_kind == 1) epi_tile<1, 1>(p, tcol0, res_a, bias_a, alpha_a, orow, valid, rbase, oy, ox);
-        else if (res_kind == 2) epi_tile<2, 1>(p, tcol0, res_a, bias_a, alpha_a, orow, valid, rbase, oy, ox);
-        else if (res_kind == 3) epi_tile<3, 1>(p, tcol0, res_a, bias_a, alpha_a, orow, valid, rbase, oy, ox);
-        else epi_tile<0, 1>(p, tcol0, res_a, bias_a, alpha_a, orow, valid, rbase, oy, ox);
+        if (res_kind == 1) epi_tile<1, 1>(p, tcol0, res_a, bias_a, alpha_a, orow, valid, rbase, oy, ox, ks_b, row_b);
+        else if (res_kind == 2) epi_tile<2, 1>(p, tcol0, res_a, bias_a, alpha_a, orow, valid, rbase, oy, ox, ks_b, row_b);
+        else if (res_kind == 3) epi_tile<3, 1>(p, tcol0, res_a, bias_a, alpha_a, orow, valid, rbase, oy, ox, ks_b, row_b);
+        else epi_tile<0, 1>(p, tcol0, res_a, bias_a, alpha_a, orow, valid, rbase, oy, ox, ks_b, row_b);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -625,7 +639,8 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
   } else if (warp < kEpiWarps + ND) {
     // =============================== depthwise / A-operand warps ====================================
     const int dtid = tid - kEpiWarps * 32;
-    const uint32_t ks_b = (uint32_t)p.KS * 4u, row_b = (uint32_t)p.IW * ks_b;
+    const uint32_t ks_b = (uint32_t)p.KS * 4u, row_b = (uint32_t)RW * ks_b;
+    const uint32_t c1_b = deint ? plane_b : ks_b, c2_b = deint ? ks_b : 2u * ks_b;
     const uint32_t sIn0_a = smem_u32(sIn0), sDw_a = smem_u32(sDw);
     // one work item per thread: its taps stay in registers for the whole kernel
     const bool hoist = S != 0 && p.n_items <= kDwThreads;
@@ -654,7 +669,7 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
       WS_TRACE(1, it, 1);
       if (S != 0) {
         if (hoist) {
-          if (mine) dw_item<S ? S : 1, RS>(sIn_a + ((e0 & 0x3FFFu) << 4), row_b, ks_b, w0, bias0, sAhi, sAlo, (e0 >> 14) & 0xFFu, (e0 >> 22) * kLBO, SBO, (uint32_t)p.TW);
+          if (mine) dw_item<S ? S : 1, RS>(sIn_a + ((e0 & 0x3FFFu) << 4), row_b, c1_b, c2_b, w0, bias0, sAhi, sAlo, (e0 >> 14) & 0xFFu, (e0 >> 22) * kLBO, SBO, (uint32_t)p.TW);
         } else {
           for (int it = dtid; it < p.n_items; it += kDwThreads) {
             const uint32_t e = dtab[it];
@@ -663,7 +678,7 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
 #pragma unroll
             for (int t = 0; t < 9; ++t) w[t] = lds4(wq + (uint32_t)(t * p.K8) * 4u);
             const float4 bias = lds4(wq + (uint32_t)(9 * p.K8) * 4u);
-            dw_item<S ? S : 1, RS>(sIn_a + ((e & 0x3FFFu) << 4), row_b, ks_b, w, bias, sAhi, sAlo, (e >> 14) & 0xFFu, (e >> 22) * kLBO, SBO, (uint32_t)p.TW);
+            dw_item<S ? S : 1, RS>(sIn_a + ((e & 0x3FFFu) << 4), row_b, c1_b, c2_b, w, bias, sAhi, sAlo, (e >> 14) & 0xFFu, (e >> 22) * kLBO, SBO, (uint32_t)p.TW);
           }
         }
       } else {
@@ -688,7 +703,6 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
   } else if (warp == kEpiWarps + ND) {
     // =============================== TMA producer ===================================================
     if (lane == 0) {
-      const uint32_t stage_bytes = (uint32_t)(p.G * p.IH * p.IW * p.KS) * 4u;
       int si = early == NS ? 0 : early, sph = early == NS ? 1 : 0;     // the first `early` tiles were requested in the prologue
       long long* tr = (p.trace && blockIdx.x == 0) ? p.trace : nullptr;
       int it = early;
@@ -702,11 +716,15 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
         mbar_wait(empty_in + 8u * si, (uint32_t)(sph ^ 1));
         WS_TRACE(2, it, 1);
         const uint32_t bar = full_in + 8u * si;
-        mbar_expect_tx(bar, stage_bytes);
+        mbar_expect_tx(bar, tma_bytes);
         const uint32_t dst = smem_u32(sIn0 + (size_t)si * in_stage_floats);
         asm volatile(
             "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
             ::"r"(dst), "l"(&tmap), "r"(0), "r"(ix0), "r"(iy0), "r"(b0), "r"(bar) : "memory");
+        if (deint)
+          asm volatile(
+              "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+              ::"r"(dst + plane_b), "l"(&tmap), "r"(0), "r"(ix0 + 1), "r"(iy0), "r"(b0), "r"(bar) : "memory");
         WS_TRACE(2, it, 2);
         if (++si == NS) { si = 0; sph ^= 1; }
       }
@@ -1094,7 +1112,7 @@ bool input_tensor_map(const DwPwTcP& p, int cap, CUtensorMap* out) {
   typedef std::tuple<const void*, int, int, int, int, int, int, int, int, long long> Key;
   static std::mutex mu;
   static std::map<Key, CUtensorMap> cache;
-  Key key(p.in, cap, p.H, p.W, p.CinS, p.KS, p.IW, p.IH, p.G, p.in_istride);
+  Key key(p.in, cap, p.H, p.W, p.CinS, p.KS, p.deint ? -p.IW : p.IW, p.IH, p.G, p.in_istride);
   std::lock_guard<std::mutex> g(mu);
   auto it = cache.find(key);
   if (it != cache.end()) { *out = it->second; return true; }
@@ -1103,7 +1121,7 @@ bool input_tensor_map(const DwPwTcP& p, int cap, CUtensorMap* out) {
   cuuint64_t gdim[4] = {(cuuint64_t)p.CinS, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)cap};
   cuuint64_t gstr[3] = {(cuuint64_t)p.CinS * 4, (cuuint64_t)p.W * p.CinS * 4, (cuuint64_t)p.in_istride * 4};
   cuuint32_t box[4] = {(cuuint32_t)p.KS, (cuuint32_t)p.IW, (cuuint32_t)p.IH, (cuuint32_t)p.G};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t estr[4] = {1, p.deint ? 2u : 1u, 1, 1};          // deint: every other column (IW traversed -> PW = (IW + 1) / 2 delivered)
   CUtensorMap tm;
   CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.in), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

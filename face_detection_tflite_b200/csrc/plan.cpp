@@ -116,6 +116,12 @@ struct Builder {
     return true;
   }
 
+  // Channel stride of an arena tensor: channels rounded up to a quad (float4 loads / stores everywhere), pad channels exact zeros.
+  // Measured alternative (round 2): rounding up to 8 channels, so that every pixel record is 32-byte aligned and every epilogue uses
+  // 256-bit stores, LOSES on the only layers it changes (short-range 28 / 36 / 42 channels): block 2 273 -> 295 us per 1024 frames
+  // (14 % more bytes written), block 3 126 -> 131, blocks 4-6 -8 us in total.
+  int cs(int C) const { return ru(C, 4); }
+
   int pt(int tf) {
     auto it = P.tf2pt.find(tf);
     if (it != P.tf2pt.end()) return it->second;
@@ -133,7 +139,7 @@ struct Builder {
       x.view_off = views[tf].off;
       x.istride = P.out_elems[x.root];
     } else {
-      x.Cs = ru(x.C, 4);
+      x.Cs = cs(x.C);
       x.istride = (long long)x.H * x.W * x.Cs;
     }
     P.tensors.push_back(x);
@@ -440,10 +446,10 @@ struct Builder {
   void plan_ts(PStep* st, const TfTensor& in, int OH, int OW, bool prelu) {
     static const int want = [] { const char* e = std::getenv("FDT_TS"); return e ? std::atoi(e) : 1; }();      // FDT_TS=0: A/B against k_block_ws
     if (!want || !st->has_dw || st->c2 > 0 || st->w_parts != 1 || prelu) return;
-    // Below 28 input channels the choice follows the output record (measured per 1024 frames, 64x64x24 input): 24 output channels
-    // (32-byte aligned 96-byte records, 256-bit stores) 227 us here vs 257 us on k_block_ws; 28 output channels (112-byte records,
-    // float4 stores) 296 vs 273 us.  From 28 input channels on this kernel always wins.
-    if (in.dim(3) < 28 && ru(st->Cout, 4) % 8 != 0 && want < 2) return;
+    // Below 28 input channels the choice follows the output width (measured per 1024 frames, 64x64x24 input): up to 24 output
+    // channels (three 8-column epilogue groups, one per warp of a lane quarter) 228 us here vs 257 us on k_block_ws; 28 output
+    // channels (four groups: one warp of three does double work) 296-308 vs 273 us.  From 28 input channels on this kernel always wins.
+    if (in.dim(3) < 28 && cs(st->Cout) > 24 && want < 2) return;
     if (st->act != kActRelu && st->act != kActNone) return;
     const int Cin = in.dim(3), K16 = ru(Cin, 16), Npad = ru(st->Cout, 16);
     if (K16 > 64 || Npad > 64) return;
@@ -581,7 +587,7 @@ struct Builder {
     // channel guard: the TMA zero-fills everything past CinS), an odd number of 16-byte quads (conflict-free LDS.128)
     {
       int ks = s.K8;
-      if (s.res_mode == 1 && ru(s.Cout, 4) > ks) ks = ru(s.Cout, 4);
+      if (s.res_mode == 1 && cs(s.Cout) > ks) ks = cs(s.Cout);
       if ((ks / 4) % 2 == 0) ks += 4;
       s.KS = ks;
     }
@@ -634,11 +640,20 @@ struct Builder {
       size_t head = ((size_t)s.w_parts * s.Npad * s.K8 + 2 * (size_t)s.Npad + (s.has_dw ? 10 * (size_t)s.K8 : 0)) * 4 + (n_items + 1) / 2 * 8 + 32 * 8 + 128;
       size_t a_bytes = (size_t)2 * s.a_rows * s.K8 * 4;
       size_t in_bytes = ((size_t)s.G * s.IH * s.IW * s.KS * 4 + 127) / 128 * 128;
+      // stride 2 (even input, no padding before): even and odd columns as two planes, one TMA each (element stride 2 along x), so
+      // that neighbouring output columns read neighbouring records - conflict-free LDS.128 (see k_block_ts)
+      s.deint = (s.has_dw && s.dws == 2 && s.dpt == 0 && s.dpl == 0 && (s.IW & 1)) ? 1 : 0;
+      s.PW = (s.IW + 1) / 2;
+      if (s.deint) {
+        const size_t plane = ((size_t)s.G * s.IH * s.PW * s.KS * 4 + 127) / 128 * 128;
+        s.plane_floats = (int)(plane / 4);
+        in_bytes = 2 * plane;
+      }
       // Output tile for the TMA-store epilogue: pixel stride KSo = CoutS rounded to an odd number of quads (conflict-free
       // STS.128), one or two buffers.  Ring choice: (A buffers, input stages) with even A rings preferred (the two MMA
       // issuers alternate tiles); output buffers first, since the direct-store epilogue saturates the LSU.
       static const int want_no = [] { const char* e = std::getenv("FDT_WS_NO"); return e ? std::atoi(e) : 0; }();   // measured: direct stores are as fast; TMA store via FDT_WS_NO=2
-      const int couts = ru(s.Cout, 4);
+      const int couts = cs(s.Cout);
       s.KSo = ((couts / 4) % 2 == 0) ? couts + 4 : couts;
       const size_t out_bytes = ((size_t)s.G * s.TH * s.TW * s.KSo * 4 + 127) / 128 * 128;
       const bool can_tma_out = s.KSo <= 256;
@@ -1276,7 +1291,7 @@ struct Builder {
     std::vector<int> buf_px, buf_c, buf_free_after;   // a buffer is free after layer buf_free_after (its tenant's last read)
     buf_of[T0] = 0;
     buf_px.push_back(m.tensors[T0].dim(1) * m.tensors[T0].dim(2));
-    buf_c.push_back(ru(m.tensors[T0].dim(3), 4));
+    buf_c.push_back(wide ? P.tensors[pt(T0)].Cs : ru(m.tensors[T0].dim(3), 4));     // (the wide loader copies whole Cs-float records)
     buf_free_after.push_back(last_read[T0]);
     PStep t;
     t.kind = kStepTailWs;
