@@ -99,6 +99,12 @@ __device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint32_t a_lo, uint32_t 
         "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\tsetp.ne.b32 p, %6, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}\n" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc));
 }
+// A operand from tensor memory (kind::f16): used by k_stem_ws, whose im2col rows are written with tcgen05.st
+__device__ __forceinline__ void mma_ts_f16(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tmov.b64 db, {%2, %3};\n\tsetp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}\n" ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc));
+}
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -832,8 +838,12 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
 // 16-byte chunks that are copied verbatim (LDS.128 -> STS.128) into the UMMA K-major core-matrix layout.
 //
 //   warp 12 (1 lane) producer: TMA of the raw u8x4 patch [PH][40] (zero fill outside the image) into a 6-stage ring
-//   warps 4..11     builders : raw -> fp16 patch (PRMT + 2 HSUB2 per pixel pair, 0 outside the image), then im2col
-//   warp 13 (1 lane) MMA     : K8/16 x w_parts tcgen05.mma into one of four TMEM accumulators
+//   warps 4..11     builders : two groups of four warps that take alternate tiles; per tile: raw -> fp16 patch (PRMT + 2 HSUB2 per
+//                              pixel pair, 0 outside the image), then thread = TMEM lane = output pixel copies its im2col row
+//                              (KW x CPK 16-byte chunks, LDS.128) straight into TENSOR MEMORY (tcgen05.st): the A operand never
+//                              touches shared memory (round 1 wrote it there: 240 STS + 256 tensor-core read wavefronts per tile of
+//                              the ~1,430 that bound the kernel on the LSU pipe)
+//   warp 13 (1 lane) MMA     : K8/16 x w_parts tcgen05.mma (A from TMEM, W from shared memory) into one of four TMEM accumulators
 //   warps 0..3      epilogue : D * out_scale + bias, ReLU/PReLU, float4 stores
 // Two such CTAs share an SM (registers are allocated per four warps: 14 warps x 56 registers fit twice, 18 would not).
 // Warps: 4*kStemEG epilogue, 8 builders, 1 producer, 1 MMA.  Registers are allocated per 4 warps, so 14 warps x 56 registers
@@ -852,7 +862,11 @@ __global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUte
 #ifndef FDT_STEM_NA
 #define FDT_STEM_NA 2
 #endif
-  constexpr int NS = 6, NA = FDT_STEM_NA, NT = 4;   // NA = 2 keeps the CTA under 113 KB: two CTAs (36 warps) per SM
+  constexpr int NS = 6, NA = FDT_STEM_NA;           // (NA only sizes the plan's shared-memory estimate now: A lives in TMEM)
+  // TMEM: accumulators [0, 128) (four of <= 32 columns, or two of <= 64), operand slot of builder group g at 128 + 64 g:
+  // 256 columns per CTA, two CTAs per SM
+  const int NT = p.Npad <= 32 ? 4 : 2;
+  constexpr uint32_t kStemTmemCols = 256, kStemACol = 128;
   constexpr int RAWW = 40;                             // raw patch row: the TMA box must start 16-byte aligned in x, so it
                                                        // begins up to 3 pixels left of the patch (offset rx_off) and is 40 wide
   constexpr uint32_t RAW_STAGE = (PH * RAWW * 4 + 127) / 128 * 128;
@@ -867,9 +881,9 @@ __global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUte
   float* sBias = reinterpret_cast<float*>(sW + w_bytes);
   float* sAlpha = sBias + p.Npad;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sAlpha + p.Npad);
-  uint8_t* sA = reinterpret_cast<uint8_t*>(((uintptr_t)(bars + 32) + 127) & ~(uintptr_t)127);
-  uint8_t* sHp = sA + NA * A_BYTES;
-  uint8_t* sRaw = sHp + 2 * ((HP_BYTES + 127) / 128 * 128);
+  uint8_t* sHp = reinterpret_cast<uint8_t*>(((uintptr_t)(bars + 32) + 127) & ~(uintptr_t)127);   // 2 groups x 2 fp16 patches
+  uint8_t* sRaw = sHp + 4 * ((HP_BYTES + 127) / 128 * 128);
+  (void)A_BYTES; (void)NA;
   const uint32_t bar0 = smem_u32(bars);
   const uint32_t full_raw = bar0, empty_raw = bar0 + 8u * 6, a_full = bar0 + 8u * 12, a_empty = bar0 + 8u * 16,
                  d_full = bar0 + 8u * 20, d_empty = bar0 + 8u * 24;
@@ -881,17 +895,16 @@ __global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUte
     sBias[i] = p.bias[i];
     sAlpha[i] = p.act == kActPrelu ? p.alpha[i] : (p.act == kActRelu ? 0.f : 1.f);
   }
-  for (int i = tid; i < (int)(NA * A_BYTES / 16); i += kStemThreads) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);   // pad chunks stay zero
   if (tid == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(full_raw + 8u * i, 1); mbar_init(empty_raw + 8u * i, 8); }
-    for (int i = 0; i < NA; ++i) { mbar_init(a_full + 8u * i, 8); mbar_init(a_empty + 8u * i, 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(full_raw + 8u * i, 1); mbar_init(empty_raw + 8u * i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(a_full + 8u * i, 4); mbar_init(a_empty + 8u * i, 1); }
     for (int i = 0; i < NT; ++i) { mbar_init(d_full + 8u * i, 1); mbar_init(d_empty + 8u * i, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
   }
   constexpr int kW0 = 4 * kStemEG;                  // first builder warp
   if (warp == kW0 + 9) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)p.tmem_cols));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(kStemTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   cp_async_wait_all();
@@ -962,25 +975,29 @@ __global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUte
       if (lane == 0) mbar_arrive_relaxed(d_empty + 8u * di);
     }
   } else if (warp < kW0 + 8) {
-    // =============================== builders: raw patch -> fp16 patch -> im2col A =======================
-    const int bt = tid - kW0 * 32;
-    const int r = bt & 127, part = bt >> 7;
-    const int r_ty = r >> 4, r_tx = r & 15;
-    const uint32_t a_row = ((uint32_t)r >> 3) * SBO + ((uint32_t)r & 7u) * 16u;
+    // =============================== builders: raw patch -> fp16 patch -> im2col row -> TMEM ==============
+    const int grp = (warp - kW0) >> 2, quarter = warp & 3;     // group g takes the CTA's tiles k = g, g + 2, ...; hardware lane quarter = warp % 4
+    const int bt = (quarter << 5) | lane;                      // thread of the group = row of the M-tile = TMEM lane
+    const int r_ty = bt >> 4, r_tx = bt & 15;
     const uint32_t src_px = (uint32_t)((2 * r_ty) * PWP + 2 * r_tx) * 8u;
-    constexpr int KY0 = KW == 5 ? 3 : 2;                 // part 0: ky < KY0, part 1: the rest
-    const int ky_lo = part == 0 ? 0 : KY0;
-    const uint32_t sA_a = smem_u32(sA), sHp_a = smem_u32(sHp), sRaw_a = smem_u32(sRaw);
+    const uint32_t sHp_a = smem_u32(sHp), sRaw_a = smem_u32(sRaw);
     constexpr uint32_t HP_STRIDE = (HP_BYTES + 127) / 128 * 128;
-    int si = 0, sph = 0, ai = 0, aph = 0, hb = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint32_t tm_a = tmem_base + ((uint32_t)(quarter * 32) << 16) + kStemACol + 64u * (uint32_t)grp;
+    // the K pad (chunks KW * CPK .. NCH - 1) of this group's operand slot stays zero for the whole kernel
+#pragma unroll
+    for (int j = KW * CPK; j < NCH; ++j)
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %1, %1, %1};" ::"r"(tm_a + 4u * (uint32_t)j), "r"(0u) : "memory");
+    int hb = 0;
+    for (int k = grp; blockIdx.x + (long long)k * gridDim.x < ntiles; k += 2) {
+      const int tile = blockIdx.x + k * gridDim.x;
+      const int si = k % NS;
       const int b = tile / tiles_per_img;
       const int trem = tile - b * tiles_per_img;
       const int iy0 = (trem / tilesX) * TH * 2 - p.pt, ix0 = (trem % tilesX) * TW * 2 - p.pl;
-      mbar_wait(full_raw + 8u * si, (uint32_t)sph);
+      mbar_wait(full_raw + 8u * si, (uint32_t)((k / NS) & 1));
       // ---- convert: u8x4 BGRX -> {B,G,R,0} - 127.5 as halves; pixels outside the image (SAME padding) -> 0
-      const uint32_t raw_a = sRaw_a + (uint32_t)si * RAW_STAGE, hp_a = sHp_a + (uint32_t)hb * HP_STRIDE;
-      for (int i = bt; i < PH * PWP; i += 256) {
+      const uint32_t raw_a = sRaw_a + (uint32_t)si * RAW_STAGE, hp_a = sHp_a + (uint32_t)(2 * grp + hb) * HP_STRIDE;
+      for (int i = bt; i < PH * PWP; i += 128) {
         const int ly = i / PWP, lx = i - ly * PWP;
         uint32_t raw;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw) : "r"(raw_a + 4u * (uint32_t)(ly * RAWW + lx + rx_off)));
@@ -996,33 +1013,29 @@ __global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUte
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty_raw + 8u * si);   // raw stage consumed
-      asm volatile("bar.sync 1, 256;" ::: "memory");      // patch complete (also: every builder has finished the previous gather)
-      mbar_wait(a_empty + 8u * ai, (uint32_t)(aph ^ 1));
-      // ---- im2col: CPK 16-byte chunks per (pixel, ky), copied verbatim
-      const uint32_t dst = sA_a + (uint32_t)ai * A_BYTES + a_row;
-      {
-        // all loads of this thread's tap rows first, then all stores (the asm statements keep their order)
-        constexpr int NK0 = KY0 * CPK, NK1 = (KW - KY0) * CPK;
-        uint4 v[NK0];
-        const uint32_t src = hp_a + src_px + (uint32_t)(ky_lo * PWP * 8);
-        const uint32_t dst2 = dst + (uint32_t)(ky_lo * CPK * 128);
-        const int nk = part == 0 ? NK0 : NK1;
+      // patch complete; also: every thread of the group has finished gathering from the patch of two tiles ago (same buffer)
+      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+      mbar_wait(a_empty + 8u * (uint32_t)grp, (uint32_t)((((k >> 1) & 1)) ^ 1));   // the MMAs of this group's previous tile have read the slot
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // ---- im2col row of this thread's output pixel: CPK 16-byte chunks per kernel row, LDS.128 -> four TMEM columns each
+      const uint32_t src = hp_a + src_px;
 #pragma unroll
-        for (int q = 0; q < NK0; ++q)
-          if (q < nk)
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[q].x), "=r"(v[q].y), "=r"(v[q].z), "=r"(v[q].w)
-                         : "r"(src + (uint32_t)((q / CPK) * PWP * 8 + (q % CPK) * 16)));
+      for (int ky = 0; ky < KW; ++ky) {
+        uint4 v[CPK];
 #pragma unroll
-        for (int q = 0; q < NK0; ++q)
-          if (q < nk)
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst2 + (uint32_t)(q * 128)), "r"(v[q].x), "r"(v[q].y), "r"(v[q].z), "r"(v[q].w) : "memory");
+        for (int c = 0; c < CPK; ++c)
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[c].x), "=r"(v[c].y), "=r"(v[c].z), "=r"(v[c].w)
+                       : "r"(src + (uint32_t)(ky * PWP * 8 + c * 16)));
+#pragma unroll
+        for (int c = 0; c < CPK; ++c)
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                       ::"r"(tm_a + 4u * (uint32_t)(ky * CPK + c)), "r"(v[c].x), "r"(v[c].y), "r"(v[c].z), "r"(v[c].w) : "memory");
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(a_full + 8u * ai);
+      if (lane == 0) mbar_arrive(a_full + 8u * (uint32_t)grp);
       hb ^= 1;
-      if (++si == NS) { si = 0; sph ^= 1; }
-      if (++ai == NA) { ai = 0; aph ^= 1; }
     }
   } else if (warp == kW0 + 8) {
     // =============================== TMA producer ===================================================
@@ -1050,29 +1063,26 @@ __global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUte
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Npad >> 3) << 17) | ((128u >> 4) << 24);   // D f32, A/B f16, K-major
       const uint32_t part_q = ((uint32_t)p.Npad * K8 * 2u) >> 4;   // one weight part, in descriptor address units
-      const uint32_t hi = desc_hi(SBO), a_desc0 = desc_lo(smem_u32(sA)), w_desc0 = desc_lo(sW_u32);
+      const uint32_t hi = desc_hi(SBO), w_desc0 = desc_lo(sW_u32);
       const int parts = p.w_parts;
-      int ai = 0, aph = 0, k = 0;
+      int k = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
-        const int di = k & (NT - 1);
-        mbar_wait(a_full + 8u * ai, (uint32_t)aph);
+        const int di = k & (NT - 1), slot = k & 1;
+        mbar_wait(a_full + 8u * (uint32_t)slot, (uint32_t)((k >> 1) & 1));
         mbar_wait(d_empty + 8u * di, (uint32_t)(((k / NT) & 1) ^ 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t dcol = tmem_base + (uint32_t)(di * p.Npad);
-        const uint32_t a_lo0 = a_desc0 + (uint32_t)ai * (A_BYTES >> 4);
+        const uint32_t acol = tmem_base + kStemACol + 64u * (uint32_t)slot;
         uint32_t acc = 0u;
-        {
 #pragma unroll
-          for (int ks = 0; ks < K8 / 16; ++ks) {
-            mma_ss<1>(dcol, a_lo0 + 16u * ks, hi, w_desc0 + 16u * ks, hi, idesc, acc);
-            acc = 1u;
-            if (parts > 1) mma_ss<1>(dcol, a_lo0 + 16u * ks, hi, w_desc0 + part_q + 16u * ks, hi, idesc, 1u);
-            if (parts > 2) mma_ss<1>(dcol, a_lo0 + 16u * ks, hi, w_desc0 + 2u * part_q + 16u * ks, hi, idesc, 1u);
-          }
+        for (int ks = 0; ks < K8 / 16; ++ks) {
+          mma_ts_f16(dcol, acol + 8u * (uint32_t)ks, w_desc0 + 16u * ks, hi, idesc, acc);
+          acc = 1u;
+          if (parts > 1) mma_ts_f16(dcol, acol + 8u * (uint32_t)ks, w_desc0 + part_q + 16u * ks, hi, idesc, 1u);
+          if (parts > 2) mma_ts_f16(dcol, acol + 8u * (uint32_t)ks, w_desc0 + 2u * part_q + 16u * ks, hi, idesc, 1u);
         }
-        mma_commit(a_empty + 8u * ai);
+        mma_commit(a_empty + 8u * (uint32_t)slot);
         mma_commit(d_full + 8u * di);
-        if (++ai == NA) { ai = 0; aph ^= 1; }
       }
     }
     __syncwarp();
@@ -1081,7 +1091,7 @@ __global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUte
   __syncthreads();
   if (warp == kW0 + 9) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kStemTmemCols));
   }
 }
 
@@ -1240,7 +1250,7 @@ void launch_stem_ws_kw(const CUtensorMap& tm, const StemWsP& p, int B, cudaStrea
       // do run concurrently: 101 vs 124 us measured): shared memory, registers (allocated per 4 warps), TMEM columns.
       const int by_smem = (int)((227u * 1024u) / (p.smem_bytes + 1024u));
       const int by_regs = 65536 / (((kStemThreads / 32 + 3) / 4 * 4) * 32 * 56);
-      const int by_tmem = 512 / std::max(32, p.tmem_cols);
+      const int by_tmem = 512 / 256;                 // kStemTmemCols
       int nb = std::max(1, std::min(std::min(by_smem, by_regs), by_tmem));
       it = occ.emplace(key, nb).first;
     }
