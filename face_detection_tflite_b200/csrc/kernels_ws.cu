@@ -312,6 +312,49 @@ __device__ __forceinline__ void epi_fast(uint32_t tcol0, uint32_t res_a, uint32_
   }
 }
 
+// ---- fast epilogue with the residual already in registers (RES 3, up to 32 output channels) --------------------------------
+// The expand blocks of the full-range / iris nets (8 -> 32 channels ...) add a residual that lives in ANOTHER HBM tensor.  ncu: the
+// kernel ran at 23 % SM throughput with the stall samples on long scoreboard - four epilogue warps with four LDG.128 in flight each
+// keep 8 KB per SM on the way, which bounds the residual stream at ~1.2 TB/s.  Here the caller issues all eight loads of the tile
+// before it waits for the accumulator: twice the bytes in flight, and the round trip overlaps the wait for the MMA.
+template <int LEAKY>
+__device__ __forceinline__ void epi_pre3(uint32_t tcol0, uint32_t bias_a, uint32_t alpha_a, float* orow, bool valid, int cout_s,
+                                         const float4 (&pre)[8], bool wide) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (16 * h >= cout_s) break;
+    uint32_t u[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+          "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+        : "r"(tcol0 + 16u * (uint32_t)h));
+    float4 bv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bv[q] = lds4(bias_a + 64u * (uint32_t)h + 16u * q);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    float4 vq[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 v = make_float4(__uint_as_float(u[4 * q]) + bv[q].x, __uint_as_float(u[4 * q + 1]) + bv[q].y,
+                             __uint_as_float(u[4 * q + 2]) + bv[q].z, __uint_as_float(u[4 * q + 3]) + bv[q].w);
+      add4(v, pre[4 * h + q]);
+      if (LEAKY) v = leaky4(v, lds4(alpha_a + 64u * (uint32_t)h + 16u * q));
+      else v = max4(v, make_float4(0.f, 0.f, 0.f, 0.f));
+      vq[q] = v;
+    }
+    if (valid) {
+#pragma unroll
+      for (int q = 0; q < 4; q += 2) {
+        const int c = 16 * h + 4 * q;
+        if (c >= cout_s) break;
+        if (wide) stg8(orow + c, vq[q], vq[q + 1]);
+        else { *reinterpret_cast<float4*>(orow + c) = vq[q]; if (c + 4 < cout_s) *reinterpret_cast<float4*>(orow + c + 4) = vq[q + 1]; }
+      }
+    }
+  }
+}
+
 // ---- epilogue of one tile for the thread's pixel: TMEM -> + bias + residual -> activation -> HBM --------------
 // RES: 0 none, 1 from the staged input tile, 2 from the staged tile with 2x2 max-pool, 3 from HBM (generic path).
 // LEAKY: 0 = ReLU (max only), 1 = slope from sAlpha (1 = identity, PReLU slopes otherwise).
@@ -399,7 +442,9 @@ __device__ __forceinline__ void epi_tile(const DwPwTcP& p, uint32_t tcol0, uint3
 //   [W (w_parts x Npad x K8)] [bias Npad] [alpha Npad] [dw taps+bias 10 x K8] [dtab n_items x 4 B] [barriers 256 B]
 //   | 128-byte aligned: [A ring: NA x (hi, lo) x a_rows x K8] [input ring: NS x in_stage_bytes] [output tiles]
 // S: depthwise stride (0 = no depthwise, pointwise only); RS: output rows per depthwise work item.
-template <int ND, int S, int RS>
+// PRE: the epilogue preloads an HBM residual of up to 32 channels before the accumulator wait (epi_pre3); a template parameter
+// because the eight float4 it keeps live would spill in the 96-register (ND = 12) variants: the planner gives such layers ND = 8.
+template <int ND, int S, int RS, int PRE>
 __global__ void __launch_bounds__((ND + kEpiWarps + 2 + kMmaWarps) * 32, 1)
 k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out, DwPwTcP p, int B, int ntiles) {
   extern __shared__ __align__(128) float smem[];
@@ -446,6 +491,7 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
   const int gmul = p.res_pool ? 2 : 1, gks = p.res_Cs, grow = p.res_W * p.res_Cs;
   const bool tma_out = fast && p.no > 0;
   const bool wide = p.vec_store == 2;
+  const bool pre3 = PRE != 0 && fast && res_kind == 3 && !p.res_pool && !tma_out && p.c2 == 0 && p.CoutS <= 32;   // epi_pre3
   const uint32_t sOut_a = smem_u32(sIn0 + (size_t)NS * in_stage_floats), out_stage_b = (uint32_t)p.out_stage_floats * 4u, kso_b = (uint32_t)p.KSo * 4u;
   const uint32_t out_full = bar0 + 8u * 28, out_empty = bar0 + 8u * 30;
 
@@ -561,17 +607,27 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
       const int b0 = grp * p.G;
       WS_TRACE(0, it, 0);
       const uint32_t res_a = sIn0_a + ((uint32_t)si * in_stage_floats + res_off) * 4u;
+      const int oy = ty0 + e_ty, ox = tx0 + e_tx, b = b0 + e_g;
+      const bool valid = slot_ok && b < B && oy < p.OH && ox < p.OW;
+      // residual from another HBM tensor, up to 32 output channels: all of the tile's loads go out before the accumulator wait
+      float4 pre[PRE ? 8 : 1];
+      if (PRE && pre3) {
+        const float* gr = p.res + (size_t)(valid ? b : 0) * p.res_istride + ((size_t)(valid ? oy : 0) * p.res_W + (size_t)(valid ? ox : 0)) * p.res_Cs;
+#pragma unroll
+        for (int q = 0; q < (PRE ? 8 : 1); ++q) pre[q] = (valid && 4 * q < p.res_C && 4 * q < p.CoutS) ? ldg4(gr + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       if (epi_reads_stage) mbar_wait(full_in + 8u * si, (uint32_t)sph);   // visibility of the TMA writes to this thread
       mbar_wait(d_full + 8u * di, (uint32_t)dph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       WS_TRACE(0, it, 1);
-      const int oy = ty0 + e_ty, ox = tx0 + e_tx, b = b0 + e_g;
-      const bool valid = slot_ok && b < B && oy < p.OH && ox < p.OW;
       float* orow = p.out + (long long)b0 * p.out_istride + ((long long)ty0 * p.OW + tx0) * p.CoutS + o_rel;
       float* orow2 = p.c2 > 0 ? p.out2 + (long long)b0 * p.out2_istride + ((long long)ty0 * p.OW + tx0) * p.Cs2 + o_rel2 : nullptr;
       const float* rbase = p.res_mode == 2 ? p.res + (size_t)(valid ? b : 0) * p.res_istride : nullptr;
       const uint32_t tcol0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(di * p.Npad);
-      if (fast) {
+      if (PRE && pre3) {
+        if (p.act == kActRelu) epi_pre3<0>(tcol0, bias_a, alpha_a, orow, valid, p.CoutS, reinterpret_cast<const float4 (&)[8]>(pre), wide);
+        else epi_pre3<1>(tcol0, bias_a, alpha_a, orow, valid, p.CoutS, reinterpret_cast<const float4 (&)[8]>(pre), wide);
+      } else if (fast) {
         const float* gres = res_kind == 3 ? rbase + ((size_t)(valid ? oy : 0) * gmul * p.res_W + (size_t)(valid ? ox : 0) * gmul) * p.res_Cs : nullptr;
         if (tma_out) {
           // the output tile is assembled in shared memory and leaves with one TMA store (full-line writes; direct
@@ -1167,7 +1223,7 @@ bool output_tensor_map(const DwPwTcP& p, int cap, CUtensorMap* out) {
   return true;
 }
 
-template <int ND, int S, int RS>
+template <int ND, int S, int RS, int PRE = 0>
 void launch_ws_k(const CUtensorMap& tm, const CUtensorMap& tmo, const DwPwTcP& p, int B, int ntiles, cudaStream_t s) {
   static std::mutex mu;
   static std::map<int, size_t> cur;
@@ -1177,18 +1233,30 @@ void launch_ws_k(const CUtensorMap& tm, const CUtensorMap& tmo, const DwPwTcP& p
     std::lock_guard<std::mutex> g(mu);
     size_t& c = cur[dev];
     if (p.smem_bytes > c) {
-      cudaFuncSetAttribute(k_block_ws<ND, S, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
+      cudaFuncSetAttribute(k_block_ws<ND, S, RS, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
       c = p.smem_bytes;
     }
   }
   int grid = std::min(ntiles, 148);
   if (grid < 1) grid = 1;
-  launch_pdl(k_block_ws<ND, S, RS>, grid, (ND + kEpiWarps + 2 + kMmaWarps) * 32, p.smem_bytes, s, tm, tmo, p, B, ntiles);
+  launch_pdl(k_block_ws<ND, S, RS, PRE>, grid, (ND + kEpiWarps + 2 + kMmaWarps) * 32, p.smem_bytes, s, tm, tmo, p, B, ntiles);
 }
 
 template <int ND>
 bool launch_ws_nd(const CUtensorMap& tm, const CUtensorMap& tmo, const DwPwTcP& p, int B, int ntiles, cudaStream_t s) {
   const int S = p.has_dw ? p.s : 0;
+  // stride-1 block whose residual is another HBM tensor of up to 32 channels, float4-aligned, planned with 8 depthwise warps (128
+  // registers): the preloading epilogue
+  const bool pre = ND == 8 && S == 1 && p.res_mode == 2 && !p.res_pool && p.vec_store && p.no == 0 && p.c2 == 0 && p.CoutS <= 32 && p.res_Cs % 4 == 0 &&
+                   p.res_C % 4 == 0 && p.res_istride % 4 == 0 && (size_t)p.res % 16 == 0;
+  if (pre) {
+    switch (p.RS) {
+      case 1: launch_ws_k<8, 1, 1, 1>(tm, tmo, p, B, ntiles, s); return true;
+      case 2: launch_ws_k<8, 1, 2, 1>(tm, tmo, p, B, ntiles, s); return true;
+      case 4: launch_ws_k<8, 1, 4, 1>(tm, tmo, p, B, ntiles, s); return true;
+      default: break;
+    }
+  }
   switch (S * 16 + (S ? p.RS : 1)) {
     case 1: launch_ws_k<ND, 0, 1>(tm, tmo, p, B, ntiles, s); break;
     case 16 + 1: launch_ws_k<ND, 1, 1>(tm, tmo, p, B, ntiles, s); break;

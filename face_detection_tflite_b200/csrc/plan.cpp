@@ -636,6 +636,14 @@ struct Builder {
           }
         }
       }
+      // expand blocks (residual in another HBM tensor, up to 32 output channels): the preloading epilogue (epi_pre3) needs the
+      // 128-register variant, and their depthwise work (K <= 16) is small anyway
+      if (s.has_dw && s.dws == 1 && s.res_mode == 2 && !s.res_pool && ru(s.Cout, 4) <= 32 && s.K8 <= 16) {
+        s.nd = 8;
+        int items = s.G * (s.K8 / 4) * s.TH * s.TW;
+        s.RS = (items > 256 && s.TH % 2 == 0) ? 2 : 1;
+        if (s.G * (s.K8 / 4) * (s.TH / s.RS) * s.TW > 256 && s.TH % 4 == 0) s.RS = 4;
+      }
       size_t n_items = s.has_dw ? (size_t)s.G * (s.K8 / 4) * (s.TH / s.RS) * s.TW : 0;
       size_t head = ((size_t)s.w_parts * s.Npad * s.K8 + 2 * (size_t)s.Npad + (s.has_dw ? 10 * (size_t)s.K8 : 0)) * 4 + (n_items + 1) / 2 * 8 + 32 * 8 + 128;
       size_t a_bytes = (size_t)2 * s.a_rows * s.K8 * 4;
