@@ -215,6 +215,7 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         p.smem_bytes = st.smem;
         p.ns = st.ns; p.na = st.na; p.nd = st.nd; p.nt = st.nt; p.trace = nullptr;
         p.deint = st.deint; p.plane_floats = st.plane_floats; p.PW = st.PW;
+        p.nr = st.in2 >= 0 ? st.nr : 0; p.KSr = st.KSr; p.res_stage_floats = st.res_stage_floats;
         p.no = st.no; p.KSo = st.KSo; p.out_stage_floats = st.out_stage_floats;
         p.out2 = nullptr; p.out2_istride = 0; p.Cs2 = 0; p.c1 = 0; p.c2 = 0;
         if (st.out2 >= 0) {

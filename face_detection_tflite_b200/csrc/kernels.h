@@ -138,6 +138,7 @@ struct DwPwTcP {
   const float* bias; const float* alpha;   // [Npad]
   int act, Npad, tmem_cols, a_rows, RS;
   int in_floats, n_chunks, n_items;   // staged tile size (floats), staging-table / depthwise-table entries
+  int nr, KSr, res_stage_floats;      // residual from another HBM tensor staged by TMA: ring stages (0 = direct loads), record stride, floats per stage
   int deint, plane_floats, PW;        // stride 2: the stage holds the even and the odd input columns as two planes [G][IH][PW][KS] (see kernels_ts.cu)
   int w_parts;              // 1: weights exact in TF32; 2: W = W_hi + W_lo (fp32 weights), wB holds both
   int nbuf;                 // 2: double-buffered input tile (the next tile is prefetched during compute)

@@ -312,49 +312,6 @@ __device__ __forceinline__ void epi_fast(uint32_t tcol0, uint32_t res_a, uint32_
   }
 }
 
-// ---- fast epilogue with the residual already in registers (RES 3, up to 32 output channels) --------------------------------
-// The expand blocks of the full-range / iris nets (8 -> 32 channels ...) add a residual that lives in ANOTHER HBM tensor.  ncu: the
-// kernel ran at 23 % SM throughput with the stall samples on long scoreboard - four epilogue warps with four LDG.128 in flight each
-// keep 8 KB per SM on the way, which bounds the residual stream at ~1.2 TB/s.  Here the caller issues all eight loads of the tile
-// before it waits for the accumulator: twice the bytes in flight, and the round trip overlaps the wait for the MMA.
-template <int LEAKY>
-__device__ __forceinline__ void epi_pre3(uint32_t tcol0, uint32_t bias_a, uint32_t alpha_a, float* orow, bool valid, int cout_s,
-                                         const float4 (&pre)[8], bool wide) {
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    if (16 * h >= cout_s) break;
-    uint32_t u[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
-          "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
-        : "r"(tcol0 + 16u * (uint32_t)h));
-    float4 bv[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) bv[q] = lds4(bias_a + 64u * (uint32_t)h + 16u * q);
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    float4 vq[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float4 v = make_float4(__uint_as_float(u[4 * q]) + bv[q].x, __uint_as_float(u[4 * q + 1]) + bv[q].y,
-                             __uint_as_float(u[4 * q + 2]) + bv[q].z, __uint_as_float(u[4 * q + 3]) + bv[q].w);
-      add4(v, pre[4 * h + q]);
-      if (LEAKY) v = leaky4(v, lds4(alpha_a + 64u * (uint32_t)h + 16u * q));
-      else v = max4(v, make_float4(0.f, 0.f, 0.f, 0.f));
-      vq[q] = v;
-    }
-    if (valid) {
-#pragma unroll
-      for (int q = 0; q < 4; q += 2) {
-        const int c = 16 * h + 4 * q;
-        if (c >= cout_s) break;
-        if (wide) stg8(orow + c, vq[q], vq[q + 1]);
-        else { *reinterpret_cast<float4*>(orow + c) = vq[q]; if (c + 4 < cout_s) *reinterpret_cast<float4*>(orow + c + 4) = vq[q + 1]; }
-      }
-    }
-  }
-}
-
 // ---- epilogue of one tile for the thread's pixel: TMEM -> + bias + residual -> activation -> HBM --------------
 // RES: 0 none, 1 from the staged input tile, 2 from the staged tile with 2x2 max-pool, 3 from HBM (generic path).
 // LEAKY: 0 = ReLU (max only), 1 = slope from sAlpha (1 = identity, PReLU slopes otherwise).
@@ -442,11 +399,10 @@ __device__ __forceinline__ void epi_tile(const DwPwTcP& p, uint32_t tcol0, uint3
 //   [W (w_parts x Npad x K8)] [bias Npad] [alpha Npad] [dw taps+bias 10 x K8] [dtab n_items x 4 B] [barriers 256 B]
 //   | 128-byte aligned: [A ring: NA x (hi, lo) x a_rows x K8] [input ring: NS x in_stage_bytes] [output tiles]
 // S: depthwise stride (0 = no depthwise, pointwise only); RS: output rows per depthwise work item.
-// PRE: the epilogue preloads an HBM residual of up to 32 channels before the accumulator wait (epi_pre3); a template parameter
-// because the eight float4 it keeps live would spill in the 96-register (ND = 12) variants: the planner gives such layers ND = 8.
-template <int ND, int S, int RS, int PRE>
+template <int ND, int S, int RS>
 __global__ void __launch_bounds__((ND + kEpiWarps + 2 + kMmaWarps) * 32, 1)
-k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out, DwPwTcP p, int B, int ntiles) {
+k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
+           DwPwTcP p, int B, int ntiles) {
   extern __shared__ __align__(128) float smem[];
   __shared__ uint32_t tmem_base_s;
   constexpr int kThreads = (ND + kEpiWarps + 2 + kMmaWarps) * 32;
@@ -465,7 +421,7 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
   // operand buffer: hi + lo parts of a_rows (<= 128) rows; the MMA always reads 128 rows, the surplus rows come from
   // whatever follows in shared memory (finite or not, they only feed accumulator rows that are never stored)
   const uint32_t a_part_floats = (uint32_t)p.a_rows * (uint32_t)p.K8, a_stage_floats = 2u * a_part_floats;
-  float* sA = reinterpret_cast<float*>(((uintptr_t)(bars + 32) + 127) & ~(uintptr_t)127);
+  float* sA = reinterpret_cast<float*>(((uintptr_t)(bars + 48) + 127) & ~(uintptr_t)127);
   float* sIn0 = sA + (size_t)NA * a_stage_floats;
   const uint32_t in_stage_floats = (uint32_t)p.in_floats;     // multiple of 32 floats (128 B)
   // barrier slots: full_in[NS] | empty_in[NS] | a_full[NA] | a_empty[NA] | d_full[NT] | d_empty[NT]   (NS <= 6, NA, NT <= 4)
@@ -482,18 +438,25 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
   const int thw = p.TH * p.TW;
   const int nslots = p.G * thw;
   const bool epi_reads_stage = p.res_mode == 1;
+  // residual in another HBM tensor, staged by TMA into its own ring (plan_ws: nr stages of [G][m TH][m TW][KSr], m = 2 when pooled):
+  // the epilogue then reads it like a staged residual (kinds 1 / 2), several tiles' worth of it are in flight
+  const int NR = p.res_mode == 2 ? p.nr : 0;
+  const bool res_ring = NR > 0;
+  const int rm = p.res_pool ? 2 : 1;
+  const uint32_t ksr_b = (uint32_t)p.KSr * 4u, rowr_b = (uint32_t)(rm * p.TW) * ksr_b, res_stage_b = (uint32_t)p.res_stage_floats * 4u;
+  const uint32_t res_tma_bytes = (uint32_t)(p.G * rm * p.TH * rm * p.TW * p.KSr) * 4u;
   // epilogue mode (uniform for the CTA; the epilogue and the store warp must agree on it)
-  const int res_kind = p.res_mode == 1 ? (p.res_pool ? 2 : 1) : (p.res_mode == 2 ? 3 : 0);
+  const int res_kind = p.res_mode == 1 ? (p.res_pool ? 2 : 1) : (p.res_mode == 2 ? (res_ring ? (p.res_pool ? 2 : 1) : 3) : 0);
   // global residual fast path: float4-aligned residual tensor; pooled windows must lie inside it (even dimensions)
   const bool gfast = res_kind == 3 && p.res_Cs % 4 == 0 && p.res_C % 4 == 0 && p.res_istride % 4 == 0 && ((size_t)p.res % 16 == 0) &&
                      (!p.res_pool || (p.res_H == 2 * p.OH && p.res_W == 2 * p.OW));
-  const bool fast = p.vec_store && (res_kind == 3 ? gfast : (res_kind == 0 || p.KS >= p.CoutS));
+  const bool fast = p.vec_store && (res_kind == 3 ? gfast : (res_kind == 0 || res_ring || p.KS >= p.CoutS));
   const int gmul = p.res_pool ? 2 : 1, gks = p.res_Cs, grow = p.res_W * p.res_Cs;
   const bool tma_out = fast && p.no > 0;
   const bool wide = p.vec_store == 2;
-  const bool pre3 = PRE != 0 && fast && res_kind == 3 && !p.res_pool && !tma_out && p.c2 == 0 && p.CoutS <= 32;   // epi_pre3
   const uint32_t sOut_a = smem_u32(sIn0 + (size_t)NS * in_stage_floats), out_stage_b = (uint32_t)p.out_stage_floats * 4u, kso_b = (uint32_t)p.KSo * 4u;
-  const uint32_t out_full = bar0 + 8u * 28, out_empty = bar0 + 8u * 30;
+  const uint32_t out_full = bar0 + 8u * 28, out_empty = bar0 + 8u * 30, full_res = bar0 + 8u * 32, empty_res = bar0 + 8u * 36;
+  const uint32_t sRes_a = sOut_a + (uint32_t)p.no * out_stage_b;
 
   // ---- prologue ---------------------------------------------------------------------------------------
   // The producer lane arms the input ring and fires the CTA's first loads before anything else, so their latency
@@ -507,6 +470,7 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     if (p.no > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_out) : "memory");
+    if (res_ring) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_res) : "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");          // (PDL) the input is the previous kernel's output
     for (int tile = blockIdx.x; tile < ntiles && early < NS; tile += gridDim.x, ++early) {
       int grp, trem, tyi, txi;
@@ -563,6 +527,10 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
       mbar_init(out_full + 8u * i, kEpiWarps);
       mbar_init(out_empty + 8u * i, 1);
     }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(full_res + 8u * i, 1);
+      mbar_init(empty_res + 8u * i, kEpiWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kEpiWarps + ND + 1) {
@@ -595,7 +563,10 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
     const uint32_t sIn0_a = smem_u32(sIn0), bias_a = smem_u32(sBias), alpha_a = smem_u32(sAlpha);
     int ob = 0, oph = 0;
     // byte distance of the residual's right / lower neighbour in the stage (pooled residuals only read them)
-    const uint32_t ks_b = deint ? plane_b : (uint32_t)p.KS * 4u, row_b = (uint32_t)RW * (uint32_t)p.KS * 4u;
+    const uint32_t ks_b = res_ring ? ksr_b : (deint ? plane_b : (uint32_t)p.KS * 4u), row_b = res_ring ? rowr_b : (uint32_t)RW * (uint32_t)p.KS * 4u;
+    // this thread's residual record inside a stage of the residual ring
+    const uint32_t rr_off = slot_ok ? (uint32_t)((((size_t)e_g * rm * p.TH + e_ty * rm) * rm * p.TW + e_tx * rm) * p.KSr) * 4u : 0u;
+    int ri = 0, rph = 0;
     int si = 0, sph = 0, di = 0, dph = 0;
     long long* tr = (p.trace && blockIdx.x == 0 && tid == 0) ? p.trace : nullptr;
     int it = 0;
@@ -606,17 +577,11 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
       const int ty0 = tyi * p.TH, tx0 = txi * p.TW;
       const int b0 = grp * p.G;
       WS_TRACE(0, it, 0);
-      const uint32_t res_a = sIn0_a + ((uint32_t)si * in_stage_floats + res_off) * 4u;
+      const uint32_t res_a = res_ring ? sRes_a + (uint32_t)ri * res_stage_b + rr_off : sIn0_a + ((uint32_t)si * in_stage_floats + res_off) * 4u;
       const int oy = ty0 + e_ty, ox = tx0 + e_tx, b = b0 + e_g;
       const bool valid = slot_ok && b < B && oy < p.OH && ox < p.OW;
-      // residual from another HBM tensor, up to 32 output channels: all of the tile's loads go out before the accumulator wait
-      float4 pre[PRE ? 8 : 1];
-      if (PRE && pre3) {
-        const float* gr = p.res + (size_t)(valid ? b : 0) * p.res_istride + ((size_t)(valid ? oy : 0) * p.res_W + (size_t)(valid ? ox : 0)) * p.res_Cs;
-#pragma unroll
-        for (int q = 0; q < (PRE ? 8 : 1); ++q) pre[q] = (valid && 4 * q < p.res_C && 4 * q < p.CoutS) ? ldg4(gr + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
       if (epi_reads_stage) mbar_wait(full_in + 8u * si, (uint32_t)sph);   // visibility of the TMA writes to this thread
+      if (res_ring) mbar_wait(full_res + 8u * ri, (uint32_t)rph);
       mbar_wait(d_full + 8u * di, (uint32_t)dph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       WS_TRACE(0, it, 1);
@@ -624,10 +589,7 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
       float* orow2 = p.c2 > 0 ? p.out2 + (long long)b0 * p.out2_istride + ((long long)ty0 * p.OW + tx0) * p.Cs2 + o_rel2 : nullptr;
       const float* rbase = p.res_mode == 2 ? p.res + (size_t)(valid ? b : 0) * p.res_istride : nullptr;
       const uint32_t tcol0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(di * p.Npad);
-      if (PRE && pre3) {
-        if (p.act == kActRelu) epi_pre3<0>(tcol0, bias_a, alpha_a, orow, valid, p.CoutS, reinterpret_cast<const float4 (&)[8]>(pre), wide);
-        else epi_pre3<1>(tcol0, bias_a, alpha_a, orow, valid, p.CoutS, reinterpret_cast<const float4 (&)[8]>(pre), wide);
-      } else if (fast) {
+      if (fast) {
         const float* gres = res_kind == 3 ? rbase + ((size_t)(valid ? oy : 0) * gmul * p.res_W + (size_t)(valid ? ox : 0) * gmul) * p.res_Cs : nullptr;
         if (tma_out) {
           // the output tile is assembled in shared memory and leaves with one TMA store (full-line writes; direct
@@ -693,7 +655,9 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
       if (lane == 0) {
         mbar_arrive_relaxed(d_empty + 8u * di);
         if (epi_reads_stage) mbar_arrive(empty_in + 8u * si);     // release: the warp's residual loads from the stage precede the producer's refill
+        if (res_ring) mbar_arrive(empty_res + 8u * ri);
       }
+      if (res_ring && ++ri == NR) { ri = 0; rph ^= 1; }
       WS_TRACE(0, it, 2);
       if (++si == NS) { si = 0; sph ^= 1; }
       if (++di == NT) { di = 0; dph ^= 1; }
@@ -796,6 +760,21 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
     // =============================== output store warp ==============================================
     // One TMA store per tile from the shared-memory output tile the epilogue warps have filled; keeps the bulk-group
     // bookkeeping (commit / wait_group.read) off the epilogue's critical path.
+    if (lane == 0 && res_ring) {
+      // residual producer: one TMA per tile into the residual ring
+      int ri = 0, rph = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int grp, trem, tyi, txi;
+        p.fd_tpg.divmod(tile, grp, trem);
+        p.fd_tilesX.divmod(trem, tyi, txi);
+        mbar_wait(empty_res + 8u * ri, (uint32_t)(rph ^ 1));
+        const uint32_t bar = full_res + 8u * ri;
+        mbar_expect_tx(bar, res_tma_bytes);
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                     ::"r"(sRes_a + (uint32_t)ri * res_stage_b), "l"(&tmap_res), "r"(0), "r"(txi * p.TW * rm), "r"(tyi * p.TH * rm), "r"(grp * p.G), "r"(bar) : "memory");
+        if (++ri == NR) { ri = 0; rph ^= 1; }
+      }
+    }
     if (lane == 0 && tma_out) {
       int ob = 0, oph = 0, prev = -1;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -1198,6 +1177,34 @@ bool input_tensor_map(const DwPwTcP& p, int cap, CUtensorMap* out) {
   return true;
 }
 
+// Tensor map of the block's residual tensor: f32 [cap][res_H][res_W][res_Cs], box {KSr, m TW, m TH, G} (m = 2 when the residual is
+// 2x2 max-pooled); channels >= res_Cs are zero-filled: the residual's zero channel pad.
+bool res_tensor_map(const DwPwTcP& p, int cap, CUtensorMap* out) {
+  typedef std::tuple<const void*, int, int, int, int, int, int, int, int, long long> Key;
+  static std::mutex mu;
+  static std::map<Key, CUtensorMap> cache;
+  const int m = p.res_pool ? 2 : 1;
+  Key key(p.res, cap, p.res_H, p.res_W, p.res_Cs, p.KSr, m * p.TW, m * p.TH, p.G, p.res_istride);
+  std::lock_guard<std::mutex> g(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return true; }
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t gdim[4] = {(cuuint64_t)p.res_Cs, (cuuint64_t)p.res_W, (cuuint64_t)p.res_H, (cuuint64_t)cap};
+  cuuint64_t gstr[3] = {(cuuint64_t)p.res_Cs * 4, (cuuint64_t)p.res_W * p.res_Cs * 4, (cuuint64_t)p.res_istride * 4};
+  cuuint32_t box[4] = {(cuuint32_t)p.KSr, (cuuint32_t)(m * p.TW), (cuuint32_t)(m * p.TH), (cuuint32_t)p.G};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap tm;
+  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.res), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  if (cache.size() > 256) cache.clear();
+  cache[key] = tm;
+  *out = tm;
+  return true;
+}
+
 // Tensor map of the block's output activation: f32 [cap][OH][OW][CoutS], box {KSo, TW, TH, G}; channels >= CoutS of the
 // shared-memory tile, pixels outside the image and images >= cap are dropped by the store.
 bool output_tensor_map(const DwPwTcP& p, int cap, CUtensorMap* out) {
@@ -1223,8 +1230,8 @@ bool output_tensor_map(const DwPwTcP& p, int cap, CUtensorMap* out) {
   return true;
 }
 
-template <int ND, int S, int RS, int PRE = 0>
-void launch_ws_k(const CUtensorMap& tm, const CUtensorMap& tmo, const DwPwTcP& p, int B, int ntiles, cudaStream_t s) {
+template <int ND, int S, int RS>
+void launch_ws_k(const CUtensorMap& tm, const CUtensorMap& tmo, const CUtensorMap& tmr, const DwPwTcP& p, int B, int ntiles, cudaStream_t s) {
   static std::mutex mu;
   static std::map<int, size_t> cur;
   int dev = 0;
@@ -1233,38 +1240,26 @@ void launch_ws_k(const CUtensorMap& tm, const CUtensorMap& tmo, const DwPwTcP& p
     std::lock_guard<std::mutex> g(mu);
     size_t& c = cur[dev];
     if (p.smem_bytes > c) {
-      cudaFuncSetAttribute(k_block_ws<ND, S, RS, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
+      cudaFuncSetAttribute(k_block_ws<ND, S, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
       c = p.smem_bytes;
     }
   }
   int grid = std::min(ntiles, 148);
   if (grid < 1) grid = 1;
-  launch_pdl(k_block_ws<ND, S, RS, PRE>, grid, (ND + kEpiWarps + 2 + kMmaWarps) * 32, p.smem_bytes, s, tm, tmo, p, B, ntiles);
+  launch_pdl(k_block_ws<ND, S, RS>, grid, (ND + kEpiWarps + 2 + kMmaWarps) * 32, p.smem_bytes, s, tm, tmo, tmr, p, B, ntiles);
 }
 
 template <int ND>
-bool launch_ws_nd(const CUtensorMap& tm, const CUtensorMap& tmo, const DwPwTcP& p, int B, int ntiles, cudaStream_t s) {
+bool launch_ws_nd(const CUtensorMap& tm, const CUtensorMap& tmo, const CUtensorMap& tmr, const DwPwTcP& p, int B, int ntiles, cudaStream_t s) {
   const int S = p.has_dw ? p.s : 0;
-  // stride-1 block whose residual is another HBM tensor of up to 32 channels, float4-aligned, planned with 8 depthwise warps (128
-  // registers): the preloading epilogue
-  const bool pre = ND == 8 && S == 1 && p.res_mode == 2 && !p.res_pool && p.vec_store && p.no == 0 && p.c2 == 0 && p.CoutS <= 32 && p.res_Cs % 4 == 0 &&
-                   p.res_C % 4 == 0 && p.res_istride % 4 == 0 && (size_t)p.res % 16 == 0;
-  if (pre) {
-    switch (p.RS) {
-      case 1: launch_ws_k<8, 1, 1, 1>(tm, tmo, p, B, ntiles, s); return true;
-      case 2: launch_ws_k<8, 1, 2, 1>(tm, tmo, p, B, ntiles, s); return true;
-      case 4: launch_ws_k<8, 1, 4, 1>(tm, tmo, p, B, ntiles, s); return true;
-      default: break;
-    }
-  }
   switch (S * 16 + (S ? p.RS : 1)) {
-    case 1: launch_ws_k<ND, 0, 1>(tm, tmo, p, B, ntiles, s); break;
-    case 16 + 1: launch_ws_k<ND, 1, 1>(tm, tmo, p, B, ntiles, s); break;
-    case 16 + 2: launch_ws_k<ND, 1, 2>(tm, tmo, p, B, ntiles, s); break;
-    case 16 + 4: launch_ws_k<ND, 1, 4>(tm, tmo, p, B, ntiles, s); break;
-    case 32 + 1: launch_ws_k<ND, 2, 1>(tm, tmo, p, B, ntiles, s); break;
-    case 32 + 2: launch_ws_k<ND, 2, 2>(tm, tmo, p, B, ntiles, s); break;
-    case 32 + 4: launch_ws_k<ND, 2, 4>(tm, tmo, p, B, ntiles, s); break;
+    case 1: launch_ws_k<ND, 0, 1>(tm, tmo, tmr, p, B, ntiles, s); break;
+    case 16 + 1: launch_ws_k<ND, 1, 1>(tm, tmo, tmr, p, B, ntiles, s); break;
+    case 16 + 2: launch_ws_k<ND, 1, 2>(tm, tmo, tmr, p, B, ntiles, s); break;
+    case 16 + 4: launch_ws_k<ND, 1, 4>(tm, tmo, tmr, p, B, ntiles, s); break;
+    case 32 + 1: launch_ws_k<ND, 2, 1>(tm, tmo, tmr, p, B, ntiles, s); break;
+    case 32 + 2: launch_ws_k<ND, 2, 2>(tm, tmo, tmr, p, B, ntiles, s); break;
+    case 32 + 4: launch_ws_k<ND, 2, 4>(tm, tmo, tmr, p, B, ntiles, s); break;
     default: return false;      // no instantiation for this (stride, rows per item): the caller marks the engine failed
   }
   return true;
@@ -1340,6 +1335,14 @@ bool launch_block_ws(const DwPwTcP& p0, int B, int cap, cudaStream_t s) {
   if (p.no > 0 && !(p.vec_store && p.CoutS % 4 == 0 && p.out_istride % 4 == 0)) p.no = 0;
   if (p.c2 > 0 && (!p.vec_store || p.res_mode != 0 || p.no > 0 || p.act != kActNone)) return false;   // merged heads: float4-aligned first output, no residual
   if (p.no > 0) { if (!output_tensor_map(p, cap, &tmo)) return false; } else tmo = tm;
+  // residual ring: float4-aligned residual tensor of the output's size (or exactly twice it when pooled); anything else loads directly
+  CUtensorMap tmr = tm;
+  if (p.nr > 0) {
+    const int m = p.res_pool ? 2 : 1;
+    const bool ok = p.res_mode == 2 && p.no == 0 && p.c2 == 0 && p.vec_store && p.res_Cs % 4 == 0 && p.res_istride % 4 == 0 && (size_t)p.res % 16 == 0 &&
+                    p.res_H == m * p.OH && p.res_W == m * p.OW && p.res_C <= p.KSr;
+    if (!ok || !res_tensor_map(p, cap, &tmr)) p.nr = 0;
+  }
   int groups = (B + p.G - 1) / p.G;
   int ntiles = groups * p.tilesX * p.tilesY;
   // FDT_WS_TRACE=1 (library built with FDT_NVCC_FLAGS=-DFDT_TRACE_BUILD): per-role timeline of CTA 0 (diagnostic;
@@ -1355,7 +1358,7 @@ bool launch_block_ws(const DwPwTcP& p0, int B, int cap, cudaStream_t s) {
     cudaMemsetAsync(d_trace, 0, 7 * 64 * 3 * sizeof(long long), s);
     p.trace = d_trace;
   }
-  if (!(p.nd == 12 ? launch_ws_nd<12>(tm, tmo, p, B, ntiles, s) : launch_ws_nd<8>(tm, tmo, p, B, ntiles, s))) return false;
+  if (!(p.nd == 12 ? launch_ws_nd<12>(tm, tmo, tmr, p, B, ntiles, s) : launch_ws_nd<8>(tm, tmo, tmr, p, B, ntiles, s))) return false;
   if (trace) {
     static long long h[7 * 64 * 3];
     cudaStreamSynchronize(s);

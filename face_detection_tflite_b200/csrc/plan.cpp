@@ -636,8 +636,7 @@ struct Builder {
           }
         }
       }
-      // expand blocks (residual in another HBM tensor, up to 32 output channels): the preloading epilogue (epi_pre3) needs the
-      // 128-register variant, and their depthwise work (K <= 16) is small anyway
+      // expand blocks (K <= 16, residual in another HBM tensor): eight depthwise warps are plenty for two to four channel quads
       if (s.has_dw && s.dws == 1 && s.res_mode == 2 && !s.res_pool && ru(s.Cout, 4) <= 32 && s.K8 <= 16) {
         s.nd = 8;
         int items = s.G * (s.K8 / 4) * s.TH * s.TW;
@@ -645,7 +644,7 @@ struct Builder {
         if (s.G * (s.K8 / 4) * (s.TH / s.RS) * s.TW > 256 && s.TH % 4 == 0) s.RS = 4;
       }
       size_t n_items = s.has_dw ? (size_t)s.G * (s.K8 / 4) * (s.TH / s.RS) * s.TW : 0;
-      size_t head = ((size_t)s.w_parts * s.Npad * s.K8 + 2 * (size_t)s.Npad + (s.has_dw ? 10 * (size_t)s.K8 : 0)) * 4 + (n_items + 1) / 2 * 8 + 32 * 8 + 128;
+      size_t head = ((size_t)s.w_parts * s.Npad * s.K8 + 2 * (size_t)s.Npad + (s.has_dw ? 10 * (size_t)s.K8 : 0)) * 4 + (n_items + 1) / 2 * 8 + 48 * 8 + 128;
       size_t a_bytes = (size_t)2 * s.a_rows * s.K8 * 4;
       size_t in_bytes = ((size_t)s.G * s.IH * s.IW * s.KS * 4 + 127) / 128 * 128;
       // stride 2 (even input, no padding before): even and odd columns as two planes, one TMA each (element stride 2 along x), so
@@ -669,17 +668,39 @@ struct Builder {
       // preference: two output tiles + prefetching input ring (ns >= 2), then one output tile + prefetching ring, then any
       // ring with an output tile, then direct stores
       static const int prefs[5][2] = {{2, 2}, {1, 2}, {2, 1}, {1, 1}, {0, 1}};     // (output tiles, min input stages)
+      // Residual in ANOTHER HBM tensor (the expand blocks of the full-range / iris nets): staged by TMA into a ring of its own, so that
+      // several tiles' worth of residual are in flight (ncu: with direct loads the four epilogue warps keep 8 KB per SM on the way and
+      // the kernel idles on long scoreboard at 23 % SM throughput).  Same-size or exactly 2x2-pooled residuals only.
+      size_t res_bytes = 0;
+      int want_nr = 0;
+      s.nr = 0; s.KSr = 0; s.res_stage_floats = 0;
+      if (s.res_mode == 2 && s.c2 == 0) {
+        const int m = s.res_pool ? 2 : 1;
+        s.KSr = odd_quads(ru(s.Cout, 4));
+        if (s.KSr <= 256 && m * s.TW <= 256 && m * s.TH <= 256) {
+          res_bytes = ((size_t)s.G * (m * s.TH) * (m * s.TW) * s.KSr * 4 + 127) / 128 * 128;
+          want_nr = 3;
+        }
+      }
       for (const auto& pr : prefs) {
         const int no = pr[0];
         if (no > want_no || (no > 0 && (!can_tma_out || s.c2 > 0))) continue;
         for (const auto& c : combos) {
           if (c[0] == 0 || c[0] > max_na || c[1] > max_ns || c[1] < pr[1]) continue;
           size_t total = head + c[0] * a_bytes + c[1] * in_bytes + no * out_bytes;
+          int nr = 0;
+          if (want_nr && no == 0) {
+            // the ring takes what the input / operand rings leave, two to four stages; rings one step smaller are preferred over none
+            nr = (int)std::min<size_t>(4, total < cap ? (cap - total) / res_bytes : 0);
+            if (nr < 2) { if (c[0] > 1 || c[1] > 2) continue; nr = 0; }
+            total += (size_t)nr * res_bytes;
+          }
           // the MMA reads 128 operand rows: its over-read past the last A buffer must stay inside the allocation
           const size_t over = (size_t)(128 - s.a_rows) * s.K8 * 4, after = c[1] * in_bytes + no * out_bytes;
           if (over > after) total += over - after;
           if (total > cap) continue;
           s.na = c[0]; s.ns = c[1]; s.no = no;
+          s.nr = nr; s.res_stage_floats = (int)(res_bytes / 4);
           s.in_stage_floats = (int)(in_bytes / 4);
           s.out_stage_floats = (int)(out_bytes / 4);
           s.smem = total;
@@ -1715,6 +1736,11 @@ std::string Plan::describe() const {
              st.res_pool ? "(pool)" : "", st.res_mode, o.tf, o.H, o.W, o.C, o.Cs, o.root >= 0 ? "view" : "arena", st.act,
              (int)st.has_dw, st.dws, st.K, st.NC, st.nchunks, st.TM, st.NPG, st.TH, st.TW, st.G, st.RS, st.nd, st.ns, st.na, st.no, st.smem, st.name.c_str());
     s += buf;
+    if (st.kind == kStepBlockWs && (st.nr > 0 || st.deint)) {
+      snprintf(buf, sizeof buf, "      k_block_ws: residual ring %d x %d B (record %d floats)%s\n", st.nr, st.res_stage_floats * 4, st.KSr,
+               st.deint ? ", stride 2 on even / odd column planes" : "");
+      s += buf;
+    }
     if (st.tail_wide) {
       snprintf(buf, sizeof buf, "      k_chain_wide: %zu W blocks (ring %d x %d B), act %d floats, %zu HBM residual tensor(s)\n", st.tail_blks.size(), st.tail_wdepth, st.tail_wbuf,
                st.tail_act_floats, st.tail_rsrc.size());

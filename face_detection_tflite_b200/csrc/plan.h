@@ -44,6 +44,7 @@ struct PStep {
   double out_scale = 1.0;    // k_stem_ws: D * out_scale + bias
   int ns = 0, na = 0, nd = 8, nt = 2, in_stage_floats = 0;
   int no = 0, KSo = 0, out_stage_floats = 0;           // TMA-store epilogue (k_block_ws)
+  int nr = 0, KSr = 0, res_stage_floats = 0;           // k_block_ws: ring of TMA-staged residual tiles (residual in another HBM tensor)
   int deint = 0, plane_floats = 0, PW = 0;             // k_block_ws stride 2: even / odd input columns staged as two planes of PW columns
   int out2 = -1, c1 = 0, c2 = 0;                        // two heads in one launch: columns [0,c1) -> out, [c1,c1+c2) -> out2   // warp-specialised variant: input stages, A buffers, depthwise warps
   int fh = 1, fw = 1, align = 0, half = 0;
