@@ -260,7 +260,9 @@ __device__ __forceinline__ void epi_fast(uint32_t tcol0, uint32_t res_a, uint32_
       if (RES == 1) {
         rv[q] = lds4(res_a + o);
       } else if (RES == 2) {
-        rv[q] = max4(max4(lds4(res_a + o), lds4(res_a + ks_b + o)), max4(lds4(res_a + row_b + o), lds4(res_a + row_b + ks_b + o)));
+        // gres_c != 0: the staged record holds only the residual's own gres_c channels (pooled tiles of the residual ring)
+        if (gres_c == 0 || c0 + 4 * q < gres_c)
+          rv[q] = max4(max4(lds4(res_a + o), lds4(res_a + ks_b + o)), max4(lds4(res_a + row_b + o), lds4(res_a + row_b + ks_b + o)));
       } else if (RES == 3) {
         if (valid && c0 + 4 * q < gres_c) rv[q] = ldg4(gres + c0 + 4 * q);
       } else if (RES == 4) {
@@ -566,6 +568,7 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
     const uint32_t ks_b = res_ring ? ksr_b : (deint ? plane_b : (uint32_t)p.KS * 4u), row_b = res_ring ? rowr_b : (uint32_t)RW * (uint32_t)p.KS * 4u;
     // this thread's residual record inside a stage of the residual ring
     const uint32_t rr_off = slot_ok ? (uint32_t)((((size_t)e_g * rm * p.TH + e_ty * rm) * rm * p.TW + e_tx * rm) * p.KSr) * 4u : 0u;
+    const int ring_c = (res_ring && p.KSr < p.CoutS) ? p.KSr : 0;     // channel limit of a staged residual record narrower than the output
     int ri = 0, rph = 0;
     int si = 0, sph = 0, di = 0, dph = 0;
     long long* tr = (p.trace && blockIdx.x == 0 && tid == 0) ? p.trace : nullptr;
@@ -635,11 +638,11 @@ k_block_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
             }
           } else if (p.act == kActRelu) {
             if (res_kind == 1) epi_fast<1, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, 0, wide);
-            else if (res_kind == 2) epi_fast<2, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, 0, wide);
+            else if (res_kind == 2) epi_fast<2, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, ring_c, wide);
             else epi_fast<0, 0, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, 0, wide);
           } else {
             if (res_kind == 1) epi_fast<1, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, 0, wide);
-            else if (res_kind == 2) epi_fast<2, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, 0, wide);
+            else if (res_kind == 2) epi_fast<2, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, ring_c, wide);
             else if (p.c2 > 0) epi_fast<0, 1, 0, 1>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, 0, wide, orow2, c1, p.c2);
             else epi_fast<0, 1, 0>(tcol0, res_a, bias_a, alpha_a, orow, out_s, valid, valid, cout_loop, ks_b, row_b, nullptr, 0, 0, 0, wide);
           }

@@ -397,7 +397,9 @@ struct Builder {
     bool tc = false;
     if (use_tc) {
       PStep t = F->st;                       // shapes the warp-specialised kernel cannot take stay on the CUDA-core kernel
+      res_c_hint = res >= 0 ? m.tensors[res].dim(3) : 0;
       tc = plan_tc(&t, Cin, OH, OW, w_parts) && plan_ws(&t, OH, OW);
+      res_c_hint = 0;
       if (tc) F->st = t;
     }
     if (F->st.c2 > 0 && F->st.kind != kStepBlockWs) return fail("internal: merged heads need the warp-specialised kernel");
@@ -580,6 +582,7 @@ struct Builder {
   // Re-plans a kStepDwPwTc step for k_block_ws (kernels_ws.cu): one CTA per SM, the input tile arrives by TMA
   // into a ring of `ns` stages, the A operand (hi + lo, always 128 rows) is double-buffered when it fits.
   // Shared-memory formula mirrors the kernel's carve-up.
+  int res_c_hint = 0;          // channels of the residual tensor of the step being planned (0: unknown / none)
   bool plan_ws(PStep* st, int OH, int OW) {
     constexpr int max_ns = 6, max_na = 4;
     PStep s = *st;
@@ -676,7 +679,10 @@ struct Builder {
       s.nr = 0; s.KSr = 0; s.res_stage_floats = 0;
       if (s.res_mode == 2 && s.c2 == 0) {
         const int m = s.res_pool ? 2 : 1;
+        // record stride: the output's channels (no channel guard in the epilogue); a pooled tile holds four times the pixels, so it
+        // keeps only the residual's own channels and the epilogue guards the rest (res_C arrives with the launch: KSr is fixed up there)
         s.KSr = odd_quads(ru(s.Cout, 4));
+        if (s.res_pool && res_c_hint > 0) s.KSr = odd_quads(ru(res_c_hint, 4));
         if (s.KSr <= 256 && m * s.TW <= 256 && m * s.TH <= 256) {
           res_bytes = ((size_t)s.G * (m * s.TH) * (m * s.TW) * s.KSr * 4 + 127) / 128 * 128;
           want_nr = 3;
