@@ -155,6 +155,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
     const uint32_t k16_b = (uint32_t)p.K16 * 4u, bias_a = smem_u32(sBias);
     const int couts = p.CoutS, nc8 = (couts + 7) >> 3;             // 8-column groups that hold real channels
 
+    // S == 2: the pooled residual of the tile whose epilogue is still to come, pulled out of the input stage right after the tile's
+    // depthwise so that the stage goes back to the producer one iteration earlier (with two stages the next tile's TMA otherwise
+    // starts only when the previous epilogue has finished: its whole latency was exposed, ~2.5 of 5.9 us per tile on block 6)
+    float4 rvp[3][2];
     auto epilogue = [&](int i) {
       const int slot = i & 1, stage = i % NS;
       const int tile = (int)blockIdx.x + i * (int)gridDim.x;
@@ -169,7 +173,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
         // residual: S == 1 the centre of the window of output row t; S == 2 the 2x2 max-pool at the window's top-left
         const uint32_t res_a = S == 1 ? st_a + (uint32_t)(t + 1) * row_b + ks_b : st_a;
         const uint32_t dcol = tm_lane + col_d(slot, t);
-        for (int c8 = g; c8 < nc8; c8 += 3) {
+#pragma unroll
+        for (int c8i = 0; c8i < 3; ++c8i) {
+          const int c8 = g + 3 * c8i;
+          if (c8 >= nc8) break;
           uint32_t u[8];
           asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
@@ -181,7 +188,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
             const uint32_t qo = 16u * (uint32_t)cq;
             bv[j] = lds4(bias_a + qo);
             rv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.res == 1) {
+            if (S == 2) {
+              rv[j] = rvp[c8i][j];
+            } else if (p.res == 1) {
               if (cq < ks_q) rv[j] = lds4(res_a + qo);
             } else if (p.res == 2) {
               if (cq < ks_q) rv[j] = max4(max4(lds4(res_a + qo), lds4(res_a + plane_b + qo)), max4(lds4(res_a + row_b + qo), lds4(res_a + row_b + plane_b + qo)));
@@ -204,10 +213,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
           }
         }
       }
-      // this tile's accumulators and input stage are consumed
+      // this tile's accumulators and (S == 1) input stage are consumed
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(in_empty + 8u * (uint32_t)stage);
+      if (S == 1 && lane == 0) mbar_arrive(in_empty + 8u * (uint32_t)stage);
     };
 
     for (int i = 0; i < n_my; ++i) {
@@ -259,6 +268,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full + 8u * (uint32_t)slot);
       if (i > 0) epilogue(i - 1);                      // the previous tile's MMAs ran during this tile's depthwise
+      if (S == 2) {
+        // residual of THIS tile (2x2 max-pool at the window's top-left; zero when the block has none) -> registers; stage released
+#pragma unroll
+        for (int c8i = 0; c8i < 3; ++c8i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int cq = 2 * (g + 3 * c8i) + j;
+            const uint32_t qo = 16u * (uint32_t)cq;
+            rvp[c8i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.res == 2 && g + 3 * c8i < nc8 && cq < ks_q)
+              rvp[c8i][j] = max4(max4(lds4(st_a + qo), lds4(st_a + plane_b + qo)), max4(lds4(st_a + row_b + qo), lds4(st_a + row_b + plane_b + qo)));
+          }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(in_empty + 8u * (uint32_t)stage);
+      }
     }
     if (n_my > 0) epilogue(n_my - 1);
   } else if (warp == kC) {

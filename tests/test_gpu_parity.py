@@ -501,6 +501,7 @@ print("variant ok")
                                  {"FDT_TS": "0"},                    # k_block_ws (TF32 hi/lo, operand in shared memory) for every BlazeBlock
                                  {"FDT_TS": "2"},                    # k_block_ts (fp16 hi/lo, operand in TMEM) also for the 24-channel blocks
                                  {"FDT_TAIL": "0"},                  # one launch per 16x16 / 8x8 block and head pair instead of k_tail_ws
+                                 {"FDT_CHAIN": "0"},                 # per-layer kernels instead of the image-resident chains (k_chain_wide, mesh trunk)
                                  {"FDT_TAIL": "0", "FDT_TS": "0"}])  # the round-1 plan: k_block_ws everywhere
 def test_kernel_variants_match_the_oracle(env):
     """Every tuning switch selects code that must stay parity-green: raw heads of two models vs the fp64 oracle."""
@@ -509,3 +510,27 @@ def test_kernel_variants_match_the_oracle(env):
     e.update(env)
     r = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT % (str(ROOT), str(ROOT))], env=e, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0 and "variant ok" in r.stdout, (env, r.stdout[-500:], r.stderr[-1500:])
+
+
+@pytest.mark.gpu
+def test_wide_chains_walk_several_images_per_cta(fdt, model_bytes):
+    """k_chain_wide (full-range layers wider than 128 channels): 400 frames in one chunk, so that every CTA of the image-resident
+    chains processes two or three images (buffer hand-over, W-block ring phases, loader warp).  The input repeats with period 16:
+    the same frame must give bit-identical heads wherever it sits in the chunk, and the first frames match the fp64 oracle."""
+    from face_detection_tflite_b200 import synth
+    n, per = 400, 16
+    base = np.concatenate([synth.face_frames(per - 2, 640, 360, start=2), synth.noise_frames(2, 640, 360)])
+    frames = np.ascontiguousarray(np.concatenate([base] * (n // per))[:n])
+    d = fdt.FaceDetector.create(fdt.FaceDetectionModel.full, withMesh=False, maxBatch=n)
+    faces, counts, _ = d.detectBatchRaw(frames, count=n, width=640, height=360)
+    boxes, scores = d.debugRawHeads(n)
+    for i in range(per, n):
+        assert np.array_equal(boxes[i], boxes[i % per]) and np.array_equal(scores[i], scores[i % per]), i
+    assert int(counts.sum()) >= n // 2
+    o = get_oracle(model_bytes, "full")
+    k = 4
+    want = o.det.run(np.stack([o.preprocess(fr)[0] for fr in frames[:k]]))
+    for got, w in ((boxes[:k], want[0]), (scores[:k], want[1])):
+        w = np.asarray(w).reshape(got.shape)
+        assert np.abs(got - w).max() <= HEAD_REL_TOL * np.abs(w).max()
+    d.dispose()
