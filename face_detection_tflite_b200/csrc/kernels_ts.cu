@@ -25,6 +25,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <type_traits>
 
 #include "kernels.h"
 
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
     const uint32_t rec_a = smem_u32(sRec), dww_a = rec_a + (uint32_t)(p.Npad * p.K16) * 2u, dwb_a = dww_a + 9u * (uint32_t)p.K16 * 4u;
     const uint32_t k16_b = (uint32_t)p.K16 * 4u, bias_a = smem_u32(sBias);
     const int couts = p.CoutS, nc8 = (couts + 7) >> 3;             // 8-column groups that hold real channels
+    const int gw = (nc8 + 2) / 3, g0 = gw * g, gn = max(0, min(gw, nc8 - g0));   // this warp's share of them: groups g0 .. g0 + gn - 1 (gn <= 3)
 
     // S == 2: the pooled residual of the tile whose epilogue is still to come, pulled out of the input stage right after the tile's
     // depthwise so that the stage goes back to the producer one iteration earlier (with two stages the next tile's TMA otherwise
@@ -173,23 +175,33 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
         // residual: S == 1 the centre of the window of output row t; S == 2 the 2x2 max-pool at the window's top-left
         const uint32_t res_a = S == 1 ? st_a + (uint32_t)(t + 1) * row_b + ks_b : st_a;
         const uint32_t dcol = tm_lane + col_d(slot, t);
+        // The warp's share of the 8-column groups is contiguous: gw = ceil(nc8 / 3) groups from gw * g.  Two groups go through ONE
+        // 16-column TMEM round trip (with the deal g, g + 3, ... every group cost its own tcgen05.ld / wait, and four groups - 25..32
+        // output channels - gave one warp of three double work); lg = index of the group inside the warp's share.
+        auto unit = [&](auto ngc, auto lgc, int c8) {
+          constexpr int NG = decltype(ngc)::value;             // groups in this unit: 1 (8 columns) or 2 (16 columns)
+          constexpr int lg = decltype(lgc)::value;             // (compile-time: rvp must stay in registers)
+          uint32_t u[8 * NG];
+          if (NG == 2)
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                  "=r"(u[8 * (NG - 1)]), "=r"(u[8 * (NG - 1) + 1]), "=r"(u[8 * (NG - 1) + 2]), "=r"(u[8 * (NG - 1) + 3]),
+                  "=r"(u[8 * (NG - 1) + 4]), "=r"(u[8 * (NG - 1) + 5]), "=r"(u[8 * (NG - 1) + 6]), "=r"(u[8 * (NG - 1) + 7])
+                : "r"(dcol + 8u * (uint32_t)c8));
+          else
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                         : "r"(dcol + 8u * (uint32_t)c8));
+          float4 bv[2 * NG], rv[2 * NG];
 #pragma unroll
-        for (int c8i = 0; c8i < 3; ++c8i) {
-          const int c8 = g + 3 * c8i;
-          if (c8 >= nc8) break;
-          uint32_t u[8];
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                       : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
-                       : "r"(dcol + 8u * (uint32_t)c8));
-          float4 bv[2], rv[2];
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
+          for (int j = 0; j < 2 * NG; ++j) {
             const int cq = 2 * c8 + j;
             const uint32_t qo = 16u * (uint32_t)cq;
             bv[j] = lds4(bias_a + qo);
             rv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (S == 2) {
-              rv[j] = rvp[c8i][j];
+              rv[j] = rvp[lg + (j >> 1)][j & 1];
             } else if (p.res == 1) {
               if (cq < ks_q) rv[j] = lds4(res_a + qo);
             } else if (p.res == 2) {
@@ -197,21 +209,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
             }
           }
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          float4 v[2];
+          float4 v[2 * NG];
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
+          for (int j = 0; j < 2 * NG; ++j) {
             v[j] = make_float4(__uint_as_float(u[4 * j]) + bv[j].x + rv[j].x, __uint_as_float(u[4 * j + 1]) + bv[j].y + rv[j].y,
                                __uint_as_float(u[4 * j + 2]) + bv[j].z + rv[j].z, __uint_as_float(u[4 * j + 3]) + bv[j].w + rv[j].w);
             if (p.relu) v[j] = max4(v[j], make_float4(0.f, 0.f, 0.f, 0.f));
           }
-          const int c = 8 * c8;                                  // columns >= Cout inside CoutS are exact zeros
-          if (c + 8 <= couts) {
-            if (p.wide) stg8(orow + c, v[0], v[1]);
-            else { *reinterpret_cast<float4*>(orow + c) = v[0]; *reinterpret_cast<float4*>(orow + c + 4) = v[1]; }
-          } else if (c + 4 <= couts) {
-            *reinterpret_cast<float4*>(orow + c) = v[0];
+#pragma unroll
+          for (int k = 0; k < NG; ++k) {
+            const int c = 8 * (c8 + k);                          // columns >= Cout inside CoutS are exact zeros
+            if (c + 8 <= couts) {
+              if (p.wide) stg8(orow + c, v[2 * k], v[2 * k + 1]);
+              else { *reinterpret_cast<float4*>(orow + c) = v[2 * k]; *reinterpret_cast<float4*>(orow + c + 4) = v[2 * k + 1]; }
+            } else if (c + 4 <= couts) {
+              *reinterpret_cast<float4*>(orow + c) = v[2 * k];
+            }
           }
-        }
+        };
+        if (gn >= 2) unit(std::integral_constant<int, 2>(), std::integral_constant<int, 0>(), g0);
+        if (gn == 1) unit(std::integral_constant<int, 1>(), std::integral_constant<int, 0>(), g0);
+        if (gn == 3) unit(std::integral_constant<int, 1>(), std::integral_constant<int, 2>(), g0 + 2);
       }
       // this tile's accumulators and (S == 1) input stage are consumed
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -274,10 +292,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
         for (int c8i = 0; c8i < 3; ++c8i)
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            const int cq = 2 * (g + 3 * c8i) + j;
+            const int cq = 2 * (g0 + c8i) + j;
             const uint32_t qo = 16u * (uint32_t)cq;
             rvp[c8i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.res == 2 && g + 3 * c8i < nc8 && cq < ks_q)
+            if (p.res == 2 && c8i < gn && cq < ks_q)
               rvp[c8i][j] = max4(max4(lds4(st_a + qo), lds4(st_a + plane_b + qo)), max4(lds4(st_a + row_b + qo), lds4(st_a + row_b + plane_b + qo)));
           }
         __syncwarp();
