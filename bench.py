@@ -395,10 +395,10 @@ def main():
             total_ms = sum(k["ms"] for k in kernels)
             # DRAM traffic of the same launch from the committed ncu --set full capture (profiles/), when the kernel matches
             traffic, traffic_src = None, None
-            tfile = sorted((ROOT / "profiles").glob("r*_traffic.json"))
-            if tfile and args.config == "c2":
+            tfile = sorted((ROOT / "profiles").glob("r*_%s_traffic.json" % args.config))
+            if tfile:
                 tj = json.loads(tfile[-1].read_text())
-                ent = [e for e in tj["launches"] if e.get("tensor") == top["tensor"] or e["launch"] == top["launch"]]
+                ent = [e for e in tj["launches"] if e["launch"] == top["launch"]]      # (launch 0 = k_letterbox in both numberings)
                 if ent and ent[0]["kernel"].split("<")[0] == top["kernel"] and ent[0]["images_per_launch"] == n:
                     traffic, traffic_src = ent[0]["dram_bytes_per_launch"], "profiles/" + tfile[-1].name
             det_k = kernels[1:ndet - 1]

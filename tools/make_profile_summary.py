@@ -20,6 +20,10 @@ w.writerow(['launch'] + keep)
 w.writerow([''] + [units[idx[k]] for k in keep])
 scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
 traffic = []
+# the capture window may start mid-chunk: rotate so that launch 0 is the chunk's first kernel (k_letterbox), as bench.py numbers them
+first = [i for i, r in enumerate(data) if 'k_letterbox' in r[idx['Kernel Name']]]
+if first:
+    data = data[first[0]:] + data[:first[0]]
 for i, r in enumerate(data):
     w.writerow([i] + [r[idx[k]] for k in keep])
     rd = float(r[idx['dram__bytes_read.sum']].replace(',', '')) * scale[units[idx['dram__bytes_read.sum']]]
