@@ -277,6 +277,10 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         p.stride = st.dws; p.res = st.ts_res; p.relu = st.ts_relu;
         p.wide = (out.Cs % 8 == 0 && out.istride % 8 == 0 && ((size_t)out.p % 32 == 0)) ? 1 : 0;
         p.ns = st.ts_ns; p.stage_bytes = st.ts_stage_bytes; p.smem_bytes = st.smem;
+        {
+          const float* hdw = plan_.blob.data() + st.ts_rec + (size_t)st.ts_npad * st.ts_k16 / 2;    // [9][K16] taps, [K16] bias (host copy)
+          for (int i = 0; i < 10 * 64; ++i) p.dw[i] = i < 10 * st.ts_k16 ? hdw[i] : 0.f;
+        }
         if (!launch_block_ts(p, B, ctx.cap, s)) { failed_ = true; fprintf(stderr, "fdt: k_block_ts could not be launched for step '%s'\n", st.name.c_str()); }
         break;
       }

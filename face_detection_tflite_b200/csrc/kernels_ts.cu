@@ -100,7 +100,7 @@ __device__ __forceinline__ uint32_t col_a(int slot, int t) { return 256u + (uint
 // record apart (KS = an odd number of 16-byte quads: conflict-free LDS.128) instead of two records apart (every load 2-way
 // bank-conflicted: ncu counted 12.7 M conflict cycles per 1024 frames on short-range block 3).
 template <int S>
-__global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant__ CUtensorMap tmap, BlockTsP p, int B) {
+__global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ BlockTsP p, int B) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint32_t tmem_base_s;
   constexpr int NT = S == 1 ? 2 : 1;                         // M-tiles per output tile
@@ -152,8 +152,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
     // S == 2 rows 2yy .. 2yy + 2, cols 2x .. 2x + 2 = entries x (even plane), x (odd plane), x + 1 (even plane)
     const uint32_t win = (uint32_t)((2 * yy) * IW + x) * ks_b;
     const int nq = p.K16 >> 2, nq_real = (p.Cin + 3) >> 2, ks_q = p.KS >> 2;
-    const uint32_t rec_a = smem_u32(sRec), dww_a = rec_a + (uint32_t)(p.Npad * p.K16) * 2u, dwb_a = dww_a + 9u * (uint32_t)p.K16 * 4u;
-    const uint32_t k16_b = (uint32_t)p.K16 * 4u, bias_a = smem_u32(sBias);
+    const uint32_t bias_a = smem_u32(sBias);
     const int couts = p.CoutS, nc8 = (couts + 7) >> 3;             // 8-column groups that hold real channels
     const int gw = (nc8 + 2) / 3, g0 = gw * g, gn = max(0, min(gw, nc8 - g0));   // this warp's share of them: groups g0 .. g0 + gn - 1 (gn <= 3)
 
@@ -246,10 +245,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
         float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
         if (q < nq_real) {
           const uint32_t qo = 16u * (uint32_t)q;
+          // taps and bias of the quad from the kernel parameters (constant bank: the address is the same for every lane)
+          const float4* cw = reinterpret_cast<const float4*>(p.dw) + q;
+          const int kq = p.K16 >> 2;
           float4 w[9];
 #pragma unroll
-          for (int k = 0; k < 9; ++k) w[k] = lds4(dww_a + (uint32_t)k * k16_b + qo);
-          const float4 bias = lds4(dwb_a + qo);
+          for (int k = 0; k < 9; ++k) w[k] = cw[k * kq];
+          const float4 bias = cw[9 * kq];
           const uint32_t pa = st_a + qo;
           if (S == 1) {
             // rows 0..3 of the window feed output rows 0 (rows 0-2) and 1 (rows 1-3); each output: bias, then taps in (ky, kx) order

@@ -448,10 +448,9 @@ struct Builder {
   void plan_ts(PStep* st, const TfTensor& in, int OH, int OW, bool prelu) {
     static const int want = [] { const char* e = std::getenv("FDT_TS"); return e ? std::atoi(e) : 1; }();      // FDT_TS=0: A/B against k_block_ws
     if (!want || !st->has_dw || st->c2 > 0 || st->w_parts != 1 || prelu) return;
-    // Below 28 input channels the choice follows the output width (measured per 1024 frames, 64x64x24 input): up to 24 output
-    // channels (three 8-column epilogue groups, one per warp of a lane quarter) 228 us here vs 257 us on k_block_ws; 28 output
-    // channels (four groups: one warp of three does double work) 296-308 vs 273 us.  From 28 input channels on this kernel always wins.
-    if (in.dim(3) < 28 && cs(st->Cout) > 24 && want < 2) return;
+    // (Round 1 kept blocks of up to 24 input channels on k_block_ws, whose threads hold their depthwise taps in registers for the whole
+    // kernel.  With the taps read from the kernel parameters - constant bank, no shared-memory traffic - and two column groups per
+    // TMEM round trip this kernel wins there too: 64x64x24 -> 24: 215 vs 257 us per 1024 frames, 24 -> 28: 249 vs 277.)
     if (st->act != kActRelu && st->act != kActNone) return;
     const int Cin = in.dim(3), K16 = ru(Cin, 16), Npad = ru(st->Cout, 16);
     if (K16 > 64 || Npad > 64) return;
