@@ -48,6 +48,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
 }
+// The single-lane roles (TMA producer, MMA issuer) wait with a suspend-time hint: with the bare try_wait loop the two lanes re-issued
+// YIELD / TRYWAIT / BRA every ~16 cycles - ncu counted 7.1 M spin iterations per 1024 frames on short-range block 1, 13.5 % of ALL
+// issued instructions, on the two schedulers that also host compute warps.
+__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+}
 __device__ __forceinline__ float4 lds4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -85,6 +94,27 @@ __device__ __forceinline__ void mma_ts_f16(uint32_t tmem_d, uint32_t tmem_a, uin
 }
 __device__ __forceinline__ void stg8(float* p, const float4& a, const float4& b) {
   asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
+
+// Incremental walk over the tiles blockIdx.x + i * gridDim.x of a persistent CTA (tile = (image b, tile row ty, tile column tx))
+struct TileAt { int b, ty, tx; };
+struct TileStep { int b, ty, tx; };
+__device__ __forceinline__ TileAt tile_at(int tile, int tpi, int tiles_x) {
+  TileAt a;
+  a.b = tile / tpi;
+  const int r = tile - a.b * tpi;
+  a.ty = r / tiles_x; a.tx = r - a.ty * tiles_x;
+  return a;
+}
+__device__ __forceinline__ TileStep tile_step(int stride, int tpi, int tiles_x) {
+  const TileAt a = tile_at(stride, tpi, tiles_x);
+  TileStep s; s.b = a.b; s.ty = a.ty; s.tx = a.tx;
+  return s;
+}
+__device__ __forceinline__ void tile_advance(TileAt& a, const TileStep& s, int tiles_x, int tiles_y) {
+  a.tx += s.tx; a.ty += s.ty; a.b += s.b;
+  if (a.tx >= tiles_x) { a.tx -= tiles_x; ++a.ty; }
+  if (a.ty >= tiles_y) { a.ty -= tiles_y; ++a.b; }
 }
 
 // TMEM columns: accumulators at (slot * 2 + t) * 64, operands at 256 + (slot * 2 + t) * 64 (hi halves +0, lo halves +32):
@@ -160,10 +190,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
     // depthwise so that the stage goes back to the producer one iteration earlier (with two stages the next tile's TMA otherwise
     // starts only when the previous epilogue has finished: its whole latency was exposed, ~2.5 of 5.9 us per tile on block 6)
     float4 rvp[3][2];
-    auto epilogue = [&](int i) {
-      const int slot = i & 1, stage = i % NS;
-      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-      const int b = tile / tpi, trem = tile - b * tpi, ty = trem / tiles_x, tx = trem - ty * tiles_x;
+    auto epilogue = [&](int i, int stage, int b, int ty, int tx) {
+      const int slot = i & 1;
       mbar_wait(d_full + 8u * (uint32_t)slot, (uint32_t)((i >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t st_a = ring_a + (uint32_t)stage * stage_b + win;
@@ -236,9 +264,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
       if (S == 1 && lane == 0) mbar_arrive(in_empty + 8u * (uint32_t)stage);
     };
 
+    // The tile walk is INCREMENTAL: tile i of this CTA is blockIdx.x + i * gridDim.x; its (image, tile row, tile column) and its ring
+    // stage advance by constant steps with a carry.  (With tile / tpi, trem / tiles_x and i % NS spelled as divisions every compute
+    // warp spent ~170 of its ~680 instructions per tile on integer division - ncu source counters, short-range block 1.)
+    const TileStep step = tile_step((int)gridDim.x, tpi, tiles_x);
+    TileAt at = tile_at((int)blockIdx.x, tpi, tiles_x), at_prev = at;
+    int stage = 0, stage_prev = 0;
+    uint32_t in_phase = 0;
     for (int i = 0; i < n_my; ++i) {
-      const int slot = i & 1, stage = i % NS;
-      mbar_wait(in_full + 8u * (uint32_t)stage, (uint32_t)((i / NS) & 1));
+      const int slot = i & 1;
+      mbar_wait(in_full + 8u * (uint32_t)stage, in_phase);
       const uint32_t st_a = ring_a + (uint32_t)stage * stage_b + win;
       const uint32_t acol0 = tm_lane + col_a(slot, 0), acol1 = tm_lane + col_a(slot, 1);
       for (int q = g; q < nq; q += 3) {
@@ -287,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full + 8u * (uint32_t)slot);
-      if (i > 0) epilogue(i - 1);                      // the previous tile's MMAs ran during this tile's depthwise
+      if (i > 0) epilogue(i - 1, stage_prev, at_prev.b, at_prev.ty, at_prev.tx);      // the previous tile's MMAs ran during this tile's depthwise
       if (S == 2) {
         // residual of THIS tile (2x2 max-pool at the window's top-left; zero when the block has none) -> registers; stage released
 #pragma unroll
@@ -303,16 +338,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(in_empty + 8u * (uint32_t)stage);
       }
+      at_prev = at; stage_prev = stage;
+      tile_advance(at, step, tiles_x, tiles_y);
+      if (++stage == NS) { stage = 0; in_phase ^= 1u; }
     }
-    if (n_my > 0) epilogue(n_my - 1);
+    if (n_my > 0) epilogue(n_my - 1, stage_prev, at_prev.b, at_prev.ty, at_prev.tx);
   } else if (warp == kC) {
     // =============================== TMA producer ===============================================================
     if (lane == 0) {
+      const TileStep step = tile_step((int)gridDim.x, tpi, tiles_x);
+      TileAt at = tile_at((int)blockIdx.x, tpi, tiles_x);
+      int stage = 0;
+      uint32_t empty_phase = 1;                                  // parity of the in_empty phase that frees the stage: ((i / NS) - 1) & 1
       for (int i = 0; i < n_my; ++i) {
-        const int stage = i % NS;
-        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-        const int b = tile / tpi, trem = tile - b * tpi, ty = trem / tiles_x, tx = trem - ty * tiles_x;
-        if (i >= NS) mbar_wait(in_empty + 8u * (uint32_t)stage, (uint32_t)(((i / NS) - 1) & 1));
+        const int b = at.b, ty = at.ty, tx = at.tx;
+        if (i >= NS) mbar_wait_idle(in_empty + 8u * (uint32_t)stage, empty_phase);
         const uint32_t bar = in_full + 8u * (uint32_t)stage;
         mbar_expect_tx(bar, (uint32_t)((S == 1 ? 18 * 18 : 2 * 17 * 17) * p.KS) * 4u);
         const int ix0 = S == 1 ? tx * TW - 1 : tx * TW * 2, iy0 = S == 1 ? ty * TH - 1 : ty * TH * 2;
@@ -321,6 +361,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
         if (S == 2)        // the odd input columns (the map walks x with an element stride of 2)
           asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
                        ::"r"(ring_a + (uint32_t)stage * stage_b + plane_b), "l"(&tmap), "r"(0), "r"(ix0 + 1), "r"(iy0), "r"(b), "r"(bar) : "memory");
+        tile_advance(at, step, tiles_x, tiles_y);
+        if (++stage == NS) { stage = 0; empty_phase ^= 1u; }
       }
     }
     __syncwarp();
@@ -334,7 +376,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
       const int ksteps = p.K16 >> 4;
       for (int i = 0; i < n_my; ++i) {
         const int slot = i & 1;
-        mbar_wait(a_full + 8u * (uint32_t)slot, (uint32_t)((i >> 1) & 1));
+        mbar_wait_idle(a_full + 8u * (uint32_t)slot, (uint32_t)((i >> 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
