@@ -28,6 +28,7 @@
 #include <type_traits>
 
 #include "kernels.h"
+#include "tile_walk.h"
 
 namespace fdt {
 namespace {
@@ -94,27 +95,6 @@ __device__ __forceinline__ void mma_ts_f16(uint32_t tmem_d, uint32_t tmem_a, uin
 }
 __device__ __forceinline__ void stg8(float* p, const float4& a, const float4& b) {
   asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
-}
-
-// Incremental walk over the tiles blockIdx.x + i * gridDim.x of a persistent CTA (tile = (image b, tile row ty, tile column tx))
-struct TileAt { int b, ty, tx; };
-struct TileStep { int b, ty, tx; };
-__device__ __forceinline__ TileAt tile_at(int tile, int tpi, int tiles_x) {
-  TileAt a;
-  a.b = tile / tpi;
-  const int r = tile - a.b * tpi;
-  a.ty = r / tiles_x; a.tx = r - a.ty * tiles_x;
-  return a;
-}
-__device__ __forceinline__ TileStep tile_step(int stride, int tpi, int tiles_x) {
-  const TileAt a = tile_at(stride, tpi, tiles_x);
-  TileStep s; s.b = a.b; s.ty = a.ty; s.tx = a.tx;
-  return s;
-}
-__device__ __forceinline__ void tile_advance(TileAt& a, const TileStep& s, int tiles_x, int tiles_y) {
-  a.tx += s.tx; a.ty += s.ty; a.b += s.b;
-  if (a.tx >= tiles_x) { a.tx -= tiles_x; ++a.ty; }
-  if (a.ty >= tiles_y) { a.ty -= tiles_y; ++a.b; }
 }
 
 // TMEM columns: accumulators at (slot * 2 + t) * 64, operands at 256 + (slot * 2 + t) * 64 (hi halves +0, lo halves +32):

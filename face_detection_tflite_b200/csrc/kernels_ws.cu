@@ -29,6 +29,7 @@
 #include <tuple>
 
 #include "kernels.h"
+#include "tile_walk.h"
 
 namespace fdt {
 namespace {
@@ -903,7 +904,7 @@ __global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUte
   constexpr int NS = 6, NA = FDT_STEM_NA;           // (NA only sizes the plan's shared-memory estimate now: A lives in TMEM)
   // TMEM: accumulators [0, 128) (four of <= 32 columns, or two of <= 64), operand slot of builder group g at 128 + 64 g:
   // 256 columns per CTA, two CTAs per SM
-  const int NT = p.Npad <= 32 ? 4 : 2;
+  const int NT = p.Npad <= 32 ? 4 : 2, nt_sh = p.Npad <= 32 ? 2 : 1;
   constexpr uint32_t kStemTmemCols = 256, kStemACol = 128;
   constexpr int RAWW = 40;                             // raw patch row: the TMA box must start 16-byte aligned in x, so it
                                                        // begins up to 3 pixels left of the patch (offset rx_off) and is 40 wide
@@ -967,15 +968,16 @@ __global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUte
     const float scale = p.out_scale;
     const bool relu = p.act == kActRelu;
     int k = 0;
-    for (int tile = blockIdx.x + g * gridDim.x; tile < ntiles; tile += kStemEG * gridDim.x, ++k) {
-      const int b = tile / tiles_per_img;
-      const int trem = tile - b * tiles_per_img;
-      const int ty0 = (trem / tilesX) * TH, tx0 = (trem % tilesX) * TW;
+    const TileStep step = tile_step(kStemEG * (int)gridDim.x, tiles_per_img, tilesX);        // (tile_walk.h: no division per tile)
+    TileAt at = tile_at((int)(blockIdx.x + g * gridDim.x), tiles_per_img, tilesX);
+    for (int tile = blockIdx.x + g * gridDim.x; tile < ntiles; tile += kStemEG * gridDim.x, ++k, tile_advance(at, step, tilesX, tilesY)) {
+      const int b = at.b;
+      const int ty0 = at.ty * TH, tx0 = at.tx * TW;
       const int oy = ty0 + e_ty, ox = tx0 + e_tx;
       const bool valid = oy < p.OH && ox < p.OW;
       float* orow = p.out + (size_t)b * p.out_istride + ((size_t)(valid ? oy : 0) * p.OW + (valid ? ox : 0)) * p.CoutS;
       const int kl = kStemEG * k + g, di = kl & (NT - 1);  // CTA-local tile index -> accumulator buffer
-      mbar_wait(d_full + 8u * di, (uint32_t)((kl / NT) & 1));
+      mbar_wait(d_full + 8u * di, (uint32_t)((kl >> nt_sh) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tcol0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(di * p.Npad);
 #pragma unroll 1
@@ -1026,13 +1028,13 @@ __global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUte
     for (int j = KW * CPK; j < NCH; ++j)
       asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %1, %1, %1};" ::"r"(tm_a + 4u * (uint32_t)j), "r"(0u) : "memory");
     int hb = 0;
+    const TileStep step = tile_step(2 * (int)gridDim.x, tiles_per_img, tilesX);              // (tile_walk.h: no division per tile)
+    TileAt at = tile_at((int)(blockIdx.x + grp * gridDim.x), tiles_per_img, tilesX);
+    int si = grp % NS;                                                                       // ring stage k % NS and its phase (k / NS) & 1
+    uint32_t raw_phase = (uint32_t)((grp / NS) & 1);
     for (int k = grp; blockIdx.x + (long long)k * gridDim.x < ntiles; k += 2) {
-      const int tile = blockIdx.x + k * gridDim.x;
-      const int si = k % NS;
-      const int b = tile / tiles_per_img;
-      const int trem = tile - b * tiles_per_img;
-      const int iy0 = (trem / tilesX) * TH * 2 - p.pt, ix0 = (trem % tilesX) * TW * 2 - p.pl;
-      mbar_wait(full_raw + 8u * si, (uint32_t)((k / NS) & 1));
+      const int iy0 = at.ty * TH * 2 - p.pt, ix0 = at.tx * TW * 2 - p.pl;
+      mbar_wait(full_raw + 8u * si, raw_phase);
       // ---- convert: u8x4 BGRX -> {B,G,R,0} - 127.5 as halves; pixels outside the image (SAME padding) -> 0
       const uint32_t raw_a = sRaw_a + (uint32_t)si * RAW_STAGE, hp_a = sHp_a + (uint32_t)(2 * grp + hb) * HP_STRIDE;
       for (int i = bt; i < PH * PWP; i += 128) {
@@ -1074,15 +1076,18 @@ __global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUte
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full + 8u * (uint32_t)grp);
       hb ^= 1;
+      tile_advance(at, step, tilesX, tilesY);
+      for (int j = 0; j < 2; ++j) if (++si == NS) { si = 0; raw_phase ^= 1u; }
     }
   } else if (warp == kW0 + 8) {
     // =============================== TMA producer ===================================================
     if (lane == 0) {
       int si = 0, sph = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int b = tile / tiles_per_img;
-        const int trem = tile - b * tiles_per_img;
-        const int iy0 = (trem / tilesX) * TH * 2 - p.pt, ix0 = (trem % tilesX) * TW * 2 - p.pl;
+      const TileStep step = tile_step((int)gridDim.x, tiles_per_img, tilesX);
+      TileAt at = tile_at((int)blockIdx.x, tiles_per_img, tilesX);
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tile_advance(at, step, tilesX, tilesY)) {
+        const int b = at.b;
+        const int iy0 = at.ty * TH * 2 - p.pt, ix0 = at.tx * TW * 2 - p.pl;
         mbar_wait(empty_raw + 8u * si, (uint32_t)(sph ^ 1));
         const uint32_t bar = full_raw + 8u * si;
         {
@@ -1107,7 +1112,7 @@ __global__ void __launch_bounds__(576, 2) k_stem_ws(const __grid_constant__ CUte
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
         const int di = k & (NT - 1), slot = k & 1;
         mbar_wait(a_full + 8u * (uint32_t)slot, (uint32_t)((k >> 1) & 1));
-        mbar_wait(d_empty + 8u * di, (uint32_t)(((k / NT) & 1) ^ 1));
+        mbar_wait(d_empty + 8u * di, (uint32_t)(((k >> nt_sh) & 1) ^ 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t dcol = tmem_base + (uint32_t)(di * p.Npad);
         const uint32_t acol = tmem_base + kStemACol + 64u * (uint32_t)slot;
