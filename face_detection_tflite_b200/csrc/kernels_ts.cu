@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
   // ---- prologue ---------------------------------------------------------------------------------------------------
   for (int i = tid; i < (p.rec_bytes >> 4); i += kThreads) reinterpret_cast<uint4*>(sRec)[i] = reinterpret_cast<const uint4*>(p.rec)[i];
   for (int i = tid; i < p.Npad; i += kThreads) sBias[i] = p.bias[i];
+  if (tid < 2) bars[24 + tid] = 0ull;                           // 16 zero bytes: what a column quad without residual reads
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(in_full + 8u * i, 1); mbar_init(in_empty + 8u * i, kC); }
     for (int i = 0; i < 2; ++i) { mbar_init(a_full + 8u * i, kC); mbar_init(d_full + 8u * i, 1); }
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
     // S == 2 rows 2yy .. 2yy + 2, cols 2x .. 2x + 2 = entries x (even plane), x (odd plane), x + 1 (even plane)
     const uint32_t win = (uint32_t)((2 * yy) * IW + x) * ks_b;
     const int nq = p.K16 >> 2, nq_real = (p.Cin + 3) >> 2, ks_q = p.KS >> 2;
-    const uint32_t bias_a = smem_u32(sBias);
+    const uint32_t bias_a = smem_u32(sBias), zero_a = bar0 + 192u;
     const int couts = p.CoutS, nc8 = (couts + 7) >> 3;             // 8-column groups that hold real channels
     const int gw = (nc8 + 2) / 3, g0 = gw * g, gn = max(0, min(gw, nc8 - g0));   // this warp's share of them: groups g0 .. g0 + gn - 1 (gn <= 3)
 
@@ -175,10 +176,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
       mbar_wait(d_full + 8u * (uint32_t)slot, (uint32_t)((i >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t st_a = ring_a + (uint32_t)stage * stage_b + win;
+      // the thread's first output pixel (one 64-bit multiply per tile; an image is far below 2^31 floats); t = 1 is the row below
+      float* const orow0 = p.out + (size_t)b * p.out_istride + (uint32_t)(((ty * TH + (S == 1 ? 2 * yy : yy)) * p.OW + tx * TW + x) * couts);
+      const uint32_t orow_step = (uint32_t)(p.OW * couts);
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
-        const int oy = ty * TH + (S == 1 ? 2 * yy + t : yy), ox = tx * TW + x;
-        float* orow = p.out + (size_t)b * p.out_istride + ((size_t)oy * p.OW + ox) * couts;
+        float* orow = orow0 + (t ? orow_step : 0u);
         // residual: S == 1 the centre of the window of output row t; S == 2 the 2x2 max-pool at the window's top-left
         const uint32_t res_a = S == 1 ? st_a + (uint32_t)(t + 1) * row_b + ks_b : st_a;
         const uint32_t dcol = tm_lane + col_d(slot, t);
@@ -209,8 +212,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
             rv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (S == 2) {
               rv[j] = rvp[lg + (j >> 1)][j & 1];
-            } else if (p.res == 1) {
-              if (cq < ks_q) rv[j] = lds4(res_a + qo);
+            } else if (S == 1) {                    // (stride 1: residual = the window's centre pixel or none; no branch: a quad without one reads zeros)
+              rv[j] = lds4(p.res == 1 && cq < ks_q ? res_a + qo : zero_a);
             } else if (p.res == 2) {
               if (cq < ks_q) rv[j] = max4(max4(lds4(res_a + qo), lds4(res_a + plane_b + qo)), max4(lds4(res_a + row_b + qo), lds4(res_a + row_b + plane_b + qo)));
             }
