@@ -279,7 +279,9 @@ int Engine::run(const EngineCtx& ctx, const uint8_t* in_u8, int B, cudaStream_t 
         p.ns = st.ts_ns; p.stage_bytes = st.ts_stage_bytes; p.smem_bytes = st.smem;
         {
           const float* hdw = plan_.blob.data() + st.ts_rec + (size_t)st.ts_npad * st.ts_k16 / 2;    // [9][K16] taps, [K16] bias (host copy)
-          for (int i = 0; i < 10 * 64; ++i) p.dw[i] = i < 10 * st.ts_k16 ? hdw[i] : 0.f;
+          for (int q = 0; q < 16; ++q)                               // quad-major: 9 taps + bias of channels 4 q .. 4 q + 3 in one 160-byte run
+            for (int k = 0; k < 10; ++k)                             // (immediate offsets in the kernel, two or three constant-cache lines per quad)
+              for (int c = 0; c < 4; ++c) p.dw[(q * 10 + k) * 4 + c] = 4 * q + c < st.ts_k16 ? hdw[k * st.ts_k16 + 4 * q + c] : 0.f;
         }
         if (!launch_block_ts(p, B, ctx.cap, s)) { failed_ = true; fprintf(stderr, "fdt: k_block_ts could not be launched for step '%s'\n", st.name.c_str()); }
         break;

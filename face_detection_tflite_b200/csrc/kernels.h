@@ -181,9 +181,9 @@ struct BlockTsP {
   int relu, wide;           // wide: pixel records 32-byte aligned -> 256-bit stores
   int ns, stage_bytes;      // input ring
   size_t smem_bytes;
-  // depthwise taps [9][K16] and bias [K16] once more, as KERNEL PARAMETERS: the taps of a channel quad are the same for every lane, and as
+  // depthwise taps and bias once more, quad-major ([16 quads][9 taps + bias][4 channels]), as KERNEL PARAMETERS: the taps of a channel quad are the same for every lane, and as
   // broadcast LDS.128 they made up 40 of the 88 shared-memory wavefronts per quad and pixel pair; from the constant bank they cost none
-  float dw[10 * 64];
+  alignas(16) float dw[10 * 64];
 };
 size_t ts_smem_bytes(int rec_bytes, int Npad, int ns, int stage_bytes);
 bool launch_block_ts(const BlockTsP& p, int B, int cap, cudaStream_t s);

@@ -109,7 +109,9 @@ __device__ __forceinline__ uint32_t col_a(int slot, int t) { return 256u + (uint
 // its own TMA with an element stride of 2 along x.  Neighbouring lanes (output columns x, x + 1) then read pixels that are ONE
 // record apart (KS = an odd number of 16-byte quads: conflict-free LDS.128) instead of two records apart (every load 2-way
 // bank-conflicted: ncu counted 12.7 M conflict cycles per 1024 frames on short-range block 3).
-template <int S>
+// KSC = staged pixel stride in floats as a COMPILE-TIME value (28 / 36 / 44: the 24..44-channel layers; 0 = read p.KS): the twelve
+// window loads of a quad then carry immediate offsets instead of ~20 address multiply-adds per quad.
+template <int S, int KSC>
 __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ BlockTsP p, int B) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint32_t tmem_base_s;
@@ -147,7 +149,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
-  const uint32_t ring_a = smem_u32(ring), ks_b = (uint32_t)p.KS * 4u, row_b = (uint32_t)IW * ks_b;
+  const int KS = KSC ? KSC : p.KS;
+  const uint32_t ring_a = smem_u32(ring), ks_b = (uint32_t)KS * 4u, row_b = (uint32_t)IW * ks_b;
   const uint32_t stage_b = (uint32_t)p.stage_bytes;
   const uint32_t plane_b = (17u * 17u * ks_b + 127u) & ~127u;   // S == 2: the odd-column plane follows the even-column plane (TMA destinations are 128-byte aligned)
   // S == 2: byte offset of window column kx = 0, 1, 2 (input columns 2x, 2x + 1, 2x + 2)
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
     // top-left of this thread's input window inside a stage: S == 1 rows 2yy .. 2yy + 3, cols x .. x + 2 (halo included);
     // S == 2 rows 2yy .. 2yy + 2, cols 2x .. 2x + 2 = entries x (even plane), x (odd plane), x + 1 (even plane)
     const uint32_t win = (uint32_t)((2 * yy) * IW + x) * ks_b;
-    const int nq = p.K16 >> 2, nq_real = (p.Cin + 3) >> 2, ks_q = p.KS >> 2;
+    const int nq = p.K16 >> 2, nq_real = (p.Cin + 3) >> 2, ks_q = KS >> 2;
     const uint32_t bias_a = smem_u32(sBias), zero_a = bar0 + 192u;
     const int couts = p.CoutS, nc8 = (couts + 7) >> 3;             // 8-column groups that hold real channels
     const int gw = (nc8 + 2) / 3, g0 = gw * g, gn = max(0, min(gw, nc8 - g0));   // this warp's share of them: groups g0 .. g0 + gn - 1 (gn <= 3)
@@ -264,12 +267,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
         if (q < nq_real) {
           const uint32_t qo = 16u * (uint32_t)q;
           // taps and bias of the quad from the kernel parameters (constant bank: the address is the same for every lane)
-          const float4* cw = reinterpret_cast<const float4*>(p.dw) + q;
-          const int kq = p.K16 >> 2;
+          const float4* cw = reinterpret_cast<const float4*>(p.dw) + 10 * q;      // quad-major: the ten float4 of a quad are contiguous
           float4 w[9];
 #pragma unroll
-          for (int k = 0; k < 9; ++k) w[k] = cw[k * kq];
-          const float4 bias = cw[9 * kq];
+          for (int k = 0; k < 9; ++k) w[k] = cw[k];
+          const float4 bias = cw[9];
           const uint32_t pa = st_a + qo;
           if (S == 1) {
             // rows 0..3 of the window feed output rows 0 (rows 0-2) and 1 (rows 1-3); each output: bias, then taps in (ky, kx) order
@@ -337,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
         const int b = at.b, ty = at.ty, tx = at.tx;
         if (i >= NS) mbar_wait_idle(in_empty + 8u * (uint32_t)stage, empty_phase);
         const uint32_t bar = in_full + 8u * (uint32_t)stage;
-        mbar_expect_tx(bar, (uint32_t)((S == 1 ? 18 * 18 : 2 * 17 * 17) * p.KS) * 4u);
+        mbar_expect_tx(bar, (uint32_t)((S == 1 ? 18 * 18 : 2 * 17 * 17) * KS) * 4u);
         const int ix0 = S == 1 ? tx * TW - 1 : tx * TW * 2, iy0 = S == 1 ? ty * TH - 1 : ty * TH * 2;
         asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
                      ::"r"(ring_a + (uint32_t)stage * stage_b), "l"(&tmap), "r"(0), "r"(ix0), "r"(iy0), "r"(b), "r"(bar) : "memory");
@@ -425,7 +427,7 @@ bool ts_tensor_map(const BlockTsP& p, int cap, CUtensorMap* out) {
   return true;
 }
 
-template <int S>
+template <int S, int KSC>
 bool launch_ts(const CUtensorMap& tm, const BlockTsP& p, int B, cudaStream_t s) {
   static std::mutex mu;
   static std::map<int, size_t> cur;
@@ -436,13 +438,13 @@ bool launch_ts(const CUtensorMap& tm, const BlockTsP& p, int B, cudaStream_t s) 
     std::lock_guard<std::mutex> g(mu);
     size_t& c = cur[dev];
     if (p.smem_bytes > c) {
-      if (cudaFuncSetAttribute(k_block_ts<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes) != cudaSuccess) return false;
+      if (cudaFuncSetAttribute(k_block_ts<S, KSC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes) != cudaSuccess) return false;
       c = p.smem_bytes;
     }
   }
   const int ntiles = B * (p.OW / 16) * (p.OH / (S == 1 ? 16 : 8));
   const int grid = std::max(1, std::min(ntiles, sms));
-  k_block_ts<S><<<grid, kThreads, p.smem_bytes, s>>>(tm, p, B);
+  k_block_ts<S, KSC><<<grid, kThreads, p.smem_bytes, s>>>(tm, p, B);
   return true;
 }
 
@@ -456,7 +458,20 @@ bool launch_block_ts(const BlockTsP& p, int B, int cap, cudaStream_t s) {
   if (B <= 0) return true;
   CUtensorMap tm;
   if (!ts_tensor_map(p, cap, &tm)) return false;
-  return p.stride == 1 ? launch_ts<1>(tm, p, B, s) : launch_ts<2>(tm, p, B, s);
+  if (p.stride == 1) {
+    switch (p.KS) {
+      case 28: return launch_ts<1, 28>(tm, p, B, s);
+      case 36: return launch_ts<1, 36>(tm, p, B, s);
+      case 44: return launch_ts<1, 44>(tm, p, B, s);
+      default: return launch_ts<1, 0>(tm, p, B, s);
+    }
+  }
+  switch (p.KS) {
+    case 28: return launch_ts<2, 28>(tm, p, B, s);
+    case 36: return launch_ts<2, 36>(tm, p, B, s);
+    case 44: return launch_ts<2, 44>(tm, p, B, s);
+    default: return launch_ts<2, 0>(tm, p, B, s);
+  }
 }
 
 }  // namespace fdt
