@@ -499,7 +499,7 @@ print("variant ok")
 @pytest.mark.gpu
 @pytest.mark.parametrize("env", [{"FDT_WS_NO": "2"},                 # k_block_ws with the TMA-store epilogue (output tile in shared memory + store warp)
                                  {"FDT_TS": "0"},                    # k_block_ws (TF32 hi/lo, operand in shared memory) for every BlazeBlock
-                                 {"FDT_TS": "2"},                    # k_block_ts (fp16 hi/lo, operand in TMEM) also for the 24-channel blocks
+                                 {"FDT_TS": "2"},                    # (historical switch: k_block_ts for the 24 -> 28 block too; the default since the taps come from the constant bank)
                                  {"FDT_TAIL": "0"},                  # one launch per 16x16 / 8x8 block and head pair instead of k_tail_ws
                                  {"FDT_CHAIN": "0"},                 # per-layer kernels instead of the image-resident chains (k_chain_wide, mesh trunk)
                                  {"FDT_TAIL": "0", "FDT_TS": "0"}])  # the round-1 plan: k_block_ws everywhere
