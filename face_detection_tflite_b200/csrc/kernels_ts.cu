@@ -109,7 +109,7 @@ __device__ __forceinline__ uint32_t col_a(int slot, int t) { return 256u + (uint
 // its own TMA with an element stride of 2 along x.  Neighbouring lanes (output columns x, x + 1) then read pixels that are ONE
 // record apart (KS = an odd number of 16-byte quads: conflict-free LDS.128) instead of two records apart (every load 2-way
 // bank-conflicted: ncu counted 12.7 M conflict cycles per 1024 frames on short-range block 3).
-// KSC = staged pixel stride in floats as a COMPILE-TIME value (28 / 36 / 44: the 24..44-channel layers; 0 = read p.KS): the twelve
+// KSC = staged pixel stride in floats as a COMPILE-TIME value (28 / 36 / 44 / 52: the 24..48-channel layers; 0 = read p.KS): the twelve
 // window loads of a quad then carry immediate offsets instead of ~20 address multiply-adds per quad.
 template <int S, int KSC>
 __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ BlockTsP p, int B) {
@@ -263,6 +263,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_block_ts(const __grid_constant_
       const uint32_t st_a = ring_a + (uint32_t)stage * stage_b + win;
       const uint32_t acol0 = tm_lane + col_a(slot, 0), acol1 = tm_lane + col_a(slot, 1);
       for (int q = g; q < nq; q += 3) {
+        // a pad quad (channels beyond Cin, up to K16) is all zeros: written by the first tile of each operand slot, then left alone
+        if (q >= nq_real && i >= 2) break;
         float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
         if (q < nq_real) {
           const uint32_t qo = 16u * (uint32_t)q;
@@ -463,6 +465,7 @@ bool launch_block_ts(const BlockTsP& p, int B, int cap, cudaStream_t s) {
       case 28: return launch_ts<1, 28>(tm, p, B, s);
       case 36: return launch_ts<1, 36>(tm, p, B, s);
       case 44: return launch_ts<1, 44>(tm, p, B, s);
+      case 52: return launch_ts<1, 52>(tm, p, B, s);
       default: return launch_ts<1, 0>(tm, p, B, s);
     }
   }
@@ -470,6 +473,7 @@ bool launch_block_ts(const BlockTsP& p, int B, int cap, cudaStream_t s) {
     case 28: return launch_ts<2, 28>(tm, p, B, s);
     case 36: return launch_ts<2, 36>(tm, p, B, s);
     case 44: return launch_ts<2, 44>(tm, p, B, s);
+    case 52: return launch_ts<2, 52>(tm, p, B, s);
     default: return launch_ts<2, 0>(tm, p, B, s);
   }
 }
