@@ -90,6 +90,7 @@ SIGNATURES = {
     "fdt_host_resize_taps": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, P, P, P, P]),
     "fdt_host_decode_box": (C.c_int32, [P, C.c_double, C.c_double, C.c_double, P, P]),
     "fdt_host_face_roi": (C.c_int32, [P, C.c_double, C.c_double, C.c_int32, P]),
+    "fdt_host_tile_walk": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, P]),
     "fdt_last_error": (C.c_char_p, [P]),
     "fdt_version": (C.c_char_p, []),
 }

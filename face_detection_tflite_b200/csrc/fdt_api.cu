@@ -23,6 +23,7 @@
 #include "jpeg_host.h"
 #include "fdt_math.h"
 #include "kernels.h"
+#include "tile_walk.h"
 
 using namespace fdt;
 
@@ -1633,6 +1634,18 @@ int32_t fdt_host_resize_taps(int32_t src, int32_t dst, int32_t is_x_axis, int32_
 int32_t fdt_host_decode_box(const float* raw16, double ax, double ay, double scale, double* out_box4, double* out_kp12) {
   if (!raw16 || !out_box4 || !out_kp12) return FDT_ERR_BAD_ARG;
   decode_box(raw16, ax, ay, scale, out_box4, out_kp12);
+  return FDT_OK;
+}
+
+int32_t fdt_host_tile_walk(int32_t first, int32_t stride, int32_t tiles_x, int32_t tiles_y, int32_t n, int32_t* out3) {
+  if (!out3 || first < 0 || stride <= 0 || tiles_x <= 0 || tiles_y <= 0 || n < 0) return FDT_ERR_BAD_ARG;
+  const int tpi = tiles_x * tiles_y;
+  const TileStep step = tile_step(stride, tpi, tiles_x);
+  TileAt at = tile_at(first, tpi, tiles_x);
+  for (int i = 0; i < n; ++i) {
+    out3[3 * i] = at.b; out3[3 * i + 1] = at.ty; out3[3 * i + 2] = at.tx;
+    tile_advance(at, step, tiles_x, tiles_y);
+  }
   return FDT_OK;
 }
 

@@ -312,6 +312,10 @@ FDT_EXPORT int32_t fdt_host_face_roi(const double* kp12, double img_w, double im
                                      double* out10);
 FDT_EXPORT int32_t fdt_host_eye_rois(const double* corners8, double* out8);
 FDT_EXPORT int32_t fdt_host_embedding_roi(const double* left_eye_xy, const double* right_eye_xy, double* out4);
+/* The incremental tile walk of the persistent kernels (csrc/tile_walk.h), run on the host: tiles first, first + stride, ...
+ * (n of them) of a batch tiled tiles_x by tiles_y per image -> out3[3 i] = image, tile row, tile column.  Test hook: the
+ * kernels advance (image, row, column) with adds and carries instead of dividing the tile index. */
+FDT_EXPORT int32_t fdt_host_tile_walk(int32_t first, int32_t stride, int32_t tiles_x, int32_t tiles_y, int32_t n, int32_t* out3);
 /* Host half of the JPEG front end, for tests and bindings: info8 = width, height, components, progressive, EXIF
  * orientation, hmax, vmax, 0.  fdt_host_jpeg_coefficients copies component `comp`'s quantised coefficients
  * ([blocks_h][blocks_w][64] int16, natural order, MCU-padded) and its quantisation table (natural order); dims6 =

@@ -229,3 +229,25 @@ print("survived", n_ok, n_bad)
     assert r.returncode == 0 and "survived" in r.stdout, (r.returncode, r.stdout[-300:], r.stderr[-1500:])
     n_bad = int(r.stdout.split()[-1])
     assert n_bad >= 30            # the mutations do reach the validation paths
+
+
+def test_incremental_tile_walk_equals_division(lib):
+    """csrc/tile_walk.h: the persistent kernels advance (image, tile row, tile column) with adds and carries; the walk must
+    visit exactly the tiles first + i * stride decomposed by division (what the kernels did before)."""
+    import ctypes as C
+    import random
+    rng = random.Random(7)
+    cases = [(0, 148, 4, 4, 500), (147, 148, 4, 4, 500), (3, 296, 4, 8, 300), (5, 1, 1, 1, 50), (0, 16, 4, 4, 64),
+             (10, 148, 12, 12, 400), (1, 444, 2, 4, 200), (0, 7, 3, 5, 1000)]
+    for _ in range(40):
+        tx, ty = rng.randint(1, 16), rng.randint(1, 16)
+        cases.append((rng.randint(0, 300), rng.randint(1, 600), tx, ty, rng.randint(1, 400)))
+    for first, stride, tiles_x, tiles_y, n in cases:
+        out = (C.c_int32 * (3 * n))()
+        assert lib.fdt_host_tile_walk(first, stride, tiles_x, tiles_y, n, out) == 0
+        tpi = tiles_x * tiles_y
+        for i in range(n):
+            t = first + i * stride
+            b, r = divmod(t, tpi)
+            assert (out[3 * i], out[3 * i + 1], out[3 * i + 2]) == (b, r // tiles_x, r % tiles_x), (first, stride, tiles_x, tiles_y, i)
+    assert lib.fdt_host_tile_walk(0, 0, 4, 4, 1, (C.c_int32 * 3)()) != 0      # a zero stride is refused
