@@ -123,8 +123,18 @@ __device__ __forceinline__ void mma_ts_f16(uint32_t tmem_d, uint32_t tmem_a, uin
 // GEN = false: the detector tails (blocks with ReLU + head pairs, exact fp16 weights, residual = the block's own input);
 // GEN = true adds what the face-landmark chain needs (PReLU, W = hi + lo, weight scale, pointwise-only and dot layers, residual
 // from another buffer, results mirrored to HBM).
+// Build with FDT_NVCC_FLAGS=-DFDT_TAIL_TRACE: warp 0 of CTA 0 stamps clock64 at the phases of every layer of its second image and
+// prints the per-layer cycle counts (wait for taps / depthwise + operand stores / wait for the MMAs / epilogue / layer barrier).
+#ifdef FDT_TAIL_TRACE
+#define TT(k) do { if (blockIdx.x == 0 && tid == 0 && it == 1) tt[l * 6 + (k)] = clock64(); } while (0)
+#else
+#define TT(k) do { } while (0)
+#endif
 template <bool GEN>
 __global__ void __launch_bounds__(kTThreads, 1) k_tail_ws(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TailP p, int B) {
+#ifdef FDT_TAIL_TRACE
+  __shared__ long long tt[16 * 6];
+#endif
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -183,6 +193,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_tail_ws(const __grid_constant_
       mbar_wait(in_full, (uint32_t)(it & 1));
       for (int l = 0; l < nl; ++l, ++gl) {
         const TailLayerD L = sL[l];                           // registers: the loops below must not re-read it from shared memory
+        TT(0);
         const uint32_t src_a = act_a + 4u * (uint32_t)p.buf_off[L.src], kss_b = 4u * (uint32_t)p.buf_ks[L.src];
         const uint32_t dst_a = L.dst >= 0 ? act_a + 4u * (uint32_t)p.buf_off[L.dst] : 0u, ksd_b = L.dst >= 0 ? 4u * (uint32_t)p.buf_ks[L.dst] : 0u;
         const int src_q = (int)(kss_b >> 4), dst_q = (int)(ksd_b >> 4);       // quads per pixel record
@@ -191,6 +202,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_tail_ws(const __grid_constant_
         if (L.tap_bytes) {                                    // this layer's depthwise record (kind 3: its filter) has landed
           if (gl & 1) { mbar_wait(t_full + 8u, ph_t1); ph_t1 ^= 1u; } else { mbar_wait(t_full, ph_t0); ph_t0 ^= 1u; }
         }
+        TT(1);
         if (GEN && L.kind == 3) {
           // ---- whole-map dot product (a k x k VALID convolution over a k x k map with one filter) ------------------------
           const int n = npix * L.Cin;
@@ -305,6 +317,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_tail_ws(const __grid_constant_
           }
         }
         if (warp_on) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        TT(2);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) { if (!half_done) mbar_arrive(a_full); mbar_arrive(a_full + 8u); }
@@ -316,6 +329,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_tail_ws(const __grid_constant_
           const uint32_t rsrc_a = GEN ? act_a + 4u * (uint32_t)p.buf_off[L.rbuf] : src_a, ksr_b = GEN ? 4u * (uint32_t)p.buf_ks[L.rbuf] : kss_b;
           const int res_q = (int)(ksr_b >> 4);
           mbar_wait(d_full, ph_d);
+          TT(3);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t row_b = (uint32_t)L.IW * ksr_b;
 #pragma unroll 1
@@ -390,12 +404,21 @@ __global__ void __launch_bounds__(kTThreads, 1) k_tail_ws(const __grid_constant_
           }
         }
         ph_d ^= 1u;
+        TT(4);
         // the layer's writes (shared memory: generic proxy; TMEM reads done) before anybody starts the next layer
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("bar.sync 1, %0;" ::"n"(kTComputeThreads) : "memory");
+        TT(5);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (l == p.last_a_layer && lane == 0) mbar_arrive(a_free);              // buffer 0 may take the next image
       }
+#ifdef FDT_TAIL_TRACE
+      if (blockIdx.x == 0 && tid == 0 && it == 1)
+        for (int l2 = 0; l2 < nl; ++l2)
+          printf("tail layer %2d: taps-wait %5lld  depthwise %6lld  mma-wait %5lld  epilogue %5lld  barrier %5lld  | total %6lld\n", l2, tt[l2 * 6 + 1] - tt[l2 * 6],
+                 tt[l2 * 6 + 2] - tt[l2 * 6 + 1], tt[l2 * 6 + 3] - tt[l2 * 6 + 2], tt[l2 * 6 + 4] - tt[l2 * 6 + 3], tt[l2 * 6 + 5] - tt[l2 * 6 + 4],
+                 tt[l2 * 6 + 5] - tt[l2 * 6]);
+#endif
     }
   } else if (lane == 0) {
     // =============================== control lane: TMA + weight rings + MMA issue =====================================
