@@ -140,7 +140,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (weak) / per job (strong); 0 = the config's batch")
-    ap.add_argument("--chunk", type=int, default=0, help="frames per internal chunk (fdt_config.max_batch); 0 = 1024 (c2), 256 otherwise")
+    ap.add_argument("--chunk", type=int, default=0, help="frames per internal chunk (fdt_config.max_batch); 0 = 1024 (c2), 512 (c4), 256 (c3)")
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -149,7 +149,9 @@ def main():
     cfg = CONFIGS[args.config]
     W, H = cfg["w"], cfg["h"]
     Bcfg = args.batch or cfg["batch"]
-    chunk = args.chunk or (1024 if args.config == "c2" else 256)
+    # measured on the final kernels: c2 763 k / 778 k / 782 k images/s at chunks of 512 / 1024 / 2048; c3 106 k / 110 k at 256 / 512 (256 kept: the
+    # committed ncu capture of c3 is per 256 frames); c4 133 k / 142 k / 146 k at 256 / 512 / 1024 (512: two chunks keep the upload overlapped)
+    chunk = args.chunk or {"c2": 1024, "c4": 512}.get(args.config, 256)
     standard = cfg["mode"] == "standard"
 
     rank = int(os.environ.get("RANK", "0"))
